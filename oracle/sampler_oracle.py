@@ -32,7 +32,7 @@ _LN2_LO = f32(-2.12194440e-4)
 # minimax-ish coefficients for e^r on |r| <= ln2/2 (Cephes expf)
 _C = [f32(1.9875691500e-4), f32(1.3981999507e-3), f32(8.3334519073e-3),
       f32(4.1665795894e-2), f32(1.6666665459e-1), f32(5.0000001201e-1)]
-_EXP_LO = f32(-87.0)
+_EXP_LO = f32(-86.0)
 
 
 def det_exp(x):

@@ -1,0 +1,883 @@
+// libt5gtts engine: owns packed weights, the paged KV pool and all workspaces; orchestrates the
+// prefill (encoder -> cross K/V -> decoder over BOS+prompt) and the CUDA-graph decode step.
+// C ABI in include/t5gtts.h.  Host control flow mirrors models/t5gemma.py:835-1129 (inference_tts).
+#include "../../include/t5gtts.h"
+#include "kernels.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <map>
+#include <set>
+#include <algorithm>
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void t5g_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* t5g_last_error(void) { return g_err; }
+extern "C" int t5g_abi_version(void) { return T5G_ABI_VERSION; }
+
+namespace {
+
+struct EncLayer { bf16 *wqkv, *wo, *wgu, *wd; float *g_pre_sa, *g_post_sa, *g_pre_ff, *g_post_ff; };
+struct DecLayer {
+  bf16 *wqkv, *wo, *wq_c, *wkv_c, *wo_c, *wgu, *wd;
+  float *g_pre_sa, *g_post_sa, *g_pre_ca, *g_post_ca, *g_pre_ff, *g_post_ff;
+};
+
+struct HostSlot {
+  bool in_use = false;
+  std::vector<int> self_pages, cross_pages;
+  int n_text = 0, n_dec = 0;
+  int mem_off = -1;      // token offset of this slot's encoder output in `memory` (last prefill)
+  int dec_off = -1;      // token offset of this slot's decoder states in `dec_final`
+  uint64_t prefill_id = 0;
+};
+
+}  // namespace
+
+struct T5GEngine {
+  T5GConfig c;
+  int device = 0, num_sms = 148;
+  int d, I, Hq, Hkv, D, QD, KD, QKV, V, Vpad, PT;
+  int max_self_pages, max_cross_pages, n_pages;
+  bool use_pdl = true, use_graph = true;
+  int gemm_impl = 0;                       // 0 simt, 1 tcgen05
+  cudaStream_t load_stream = nullptr;
+  std::vector<void*> allocs;               // every cudaMalloc of this engine
+  size_t bytes_allocated = 0;
+  // weights
+  bf16* enc_embed = nullptr; float* g_enc_final = nullptr; float* g_dec_final = nullptr;
+  std::vector<EncLayer> enc; std::vector<DecLayer> dec;
+  bf16* audio_emb = nullptr; bf16* head_w1 = nullptr; float* head_b1 = nullptr; bf16* head_w2 = nullptr; float* head_b2 = nullptr;
+  float* inv_freq = nullptr;
+  std::set<std::string> required, loaded;
+  bool finalized = false;
+  // kv
+  KVPool pool{}; std::vector<int> free_pages;
+  int* d_self_bt = nullptr; int* d_cross_bt = nullptr;
+  std::vector<HostSlot> hslots;
+  // slot state
+  SlotDev* d_slots = nullptr; std::vector<SlotDev> h_slots;   // host shadow used when (re)initialising
+  int* h_mirror = nullptr; int* d_mirror = nullptr;           // mapped pinned [max_slots][4]
+  int* h_tokens = nullptr; int* d_tokens = nullptr;           // mapped pinned [max_slots][max_dec_len]
+  int* h_picks = nullptr; int* d_picks = nullptr;             // mapped pinned [max_slots][max_dec_len]
+  int* d_forced = nullptr;                                    // [max_slots][max_dec_len]
+  int* d_topk_pool = nullptr; int topk_pool_cap = 0, topk_pool_used = 0;
+  // prefill workspaces (T = max_prefill_tokens)
+  float *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_memory = nullptr, *p_ckv = nullptr, *p_final = nullptr;
+  bf16 *p_xn = nullptr, *p_q = nullptr, *p_k = nullptr, *p_v = nullptr, *p_att = nullptr, *p_act = nullptr,
+       *p_mem_bf = nullptr, *p_ck = nullptr, *p_cv = nullptr;
+  float* p_logits = nullptr; int logits_chunk = 128;
+  int *p_ids = nullptr, *p_seg_of = nullptr, *p_seg_off_e = nullptr, *p_seg_off_d = nullptr, *p_tok_slot = nullptr,
+      *p_tok_idx = nullptr, *p_last_rows = nullptr;
+  float* p_pos = nullptr;
+  void* h_stage = nullptr; size_t h_stage_bytes = 0;          // pinned staging for prefill metadata
+  uint64_t prefill_counter = 0;
+  // decode workspaces (B = max_slots)
+  float *d_hA = nullptr, *d_hB = nullptr, *d_y = nullptr, *d_qkv = nullptr, *d_qc = nullptr, *d_act = nullptr,
+        *d_t1 = nullptr, *d_logits = nullptr, *d_part_o = nullptr, *d_part_ml = nullptr;
+  float* d_sample_u = nullptr; SlotDev* d_sample_slots = nullptr;   // t5g_sample scratch
+  int ns_self = 8, ns_cross = 2;
+  int h_end = 0;                                               // which h buffer holds the residual at step end
+  cudaGraphExec_t step_graph = nullptr; cudaStream_t graph_built_for = nullptr; int nodes_per_step = 0;
+  int64_t launches = 0;
+  cudaEvent_t ev[6] = {};
+  float timings[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int dmalloc(T5GEngine* e, void** p, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  cudaError_t err = cudaMalloc(p, bytes);
+  if (err != cudaSuccess) { t5g_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err)); return T5G_ERR_OOM; }
+  e->allocs.push_back(*p);
+  e->bytes_allocated += bytes;
+  return T5G_OK;
+}
+#define DM(ptr, count) do { int _r = dmalloc(e, (void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)); if (_r) return _r; } while (0)
+
+std::string lname(const char* side, int l, const char* rest) {
+  char buf[256]; snprintf(buf, sizeof(buf), "backbone.model.%s.layers.%d.%s", side, l, rest); return buf;
+}
+
+struct Dest { void* ptr; bool is_bf16; int64_t rows, cols, row_off, row_mul; bool add_one; int64_t dst_rows; };
+
+// maps a reference state_dict key to its packed destination
+bool resolve(T5GEngine* e, const std::string& name, Dest* out) {
+  auto mk = [&](void* p, bool bf, int64_t r, int64_t c, int64_t off = 0, int64_t mul = 1, bool one = false) {
+    *out = Dest{p, bf, r, c, off, mul, one, 0}; return true;
+  };
+  const int d = e->d, I = e->I, QD = e->QD, KD = e->KD;
+  if (name == "backbone.model.encoder.embed_tokens.weight") return mk(e->enc_embed, true, e->c.text_vocab, d);
+  if (name == "backbone.model.encoder.norm.weight") return mk(e->g_enc_final, false, 1, d, 0, 1, true);
+  if (name == "backbone.model.decoder.norm.weight") return mk(e->g_dec_final, false, 1, d, 0, 1, true);
+  if (name == "audio_embedding.0.weight") return mk(e->audio_emb, true, e->V, d);
+  if (name == "predict_layer.0.0.weight") return mk(e->head_w1, true, d, d);
+  if (name == "predict_layer.0.0.bias") return mk(e->head_b1, false, 1, d);
+  if (name == "predict_layer.0.2.weight") return mk(e->head_w2, true, e->V, d);
+  if (name == "predict_layer.0.2.bias") return mk(e->head_b2, false, 1, e->V);
+  int l = -1; char rest[128];
+  bool is_enc = sscanf(name.c_str(), "backbone.model.encoder.layers.%d.%127s", &l, rest) == 2;
+  bool is_dec = !is_enc && sscanf(name.c_str(), "backbone.model.decoder.layers.%d.%127s", &l, rest) == 2;
+  if (!is_enc && !is_dec) return false;
+  if (l < 0 || l >= (is_enc ? e->c.n_enc_layers : e->c.n_dec_layers)) return false;
+  const std::string r = rest;
+  bf16 *wqkv, *wo, *wgu, *wd; float *pre_sa, *post_sa, *pre_ff, *post_ff;
+  if (is_enc) { EncLayer& L = e->enc[l]; wqkv = L.wqkv; wo = L.wo; wgu = L.wgu; wd = L.wd; pre_sa = L.g_pre_sa; post_sa = L.g_post_sa; pre_ff = L.g_pre_ff; post_ff = L.g_post_ff; }
+  else { DecLayer& L = e->dec[l]; wqkv = L.wqkv; wo = L.wo; wgu = L.wgu; wd = L.wd; pre_sa = L.g_pre_sa; post_sa = L.g_post_sa; pre_ff = L.g_pre_ff; post_ff = L.g_post_ff; }
+  if (r == "self_attn.q_proj.weight") return mk(wqkv, true, QD, d, 0);
+  if (r == "self_attn.k_proj.weight") return mk(wqkv, true, KD, d, QD);
+  if (r == "self_attn.v_proj.weight") return mk(wqkv, true, KD, d, QD + KD);
+  if (r == "self_attn.o_proj.weight") return mk(wo, true, d, QD);
+  if (r == "mlp.gate_proj.weight") return mk(wgu, true, I, d, 0, 2);
+  if (r == "mlp.up_proj.weight") return mk(wgu, true, I, d, 1, 2);
+  if (r == "mlp.down_proj.weight") return mk(wd, true, d, I);
+  if (r == "pre_self_attn_layernorm.weight") return mk(pre_sa, false, 1, d, 0, 1, true);
+  if (r == "post_self_attn_layernorm.weight") return mk(post_sa, false, 1, d, 0, 1, true);
+  if (r == "pre_feedforward_layernorm.weight") return mk(pre_ff, false, 1, d, 0, 1, true);
+  if (r == "post_feedforward_layernorm.weight") return mk(post_ff, false, 1, d, 0, 1, true);
+  if (is_dec) {
+    DecLayer& L = e->dec[l];
+    if (r == "cross_attn.q_proj.weight") return mk(L.wq_c, true, QD, d);
+    if (r == "cross_attn.k_proj.weight") return mk(L.wkv_c, true, KD, d, 0);
+    if (r == "cross_attn.v_proj.weight") return mk(L.wkv_c, true, KD, d, KD);
+    if (r == "cross_attn.o_proj.weight") return mk(L.wo_c, true, d, QD);
+    if (r == "pre_cross_attn_layernorm.weight") return mk(L.g_pre_ca, false, 1, d, 0, 1, true);
+    if (r == "post_cross_attn_layernorm.weight") return mk(L.g_post_ca, false, 1, d, 0, 1, true);
+  }
+  return false;
+}
+
+void add_required(T5GEngine* e) {
+  auto& R = e->required;
+  R.insert("backbone.model.encoder.embed_tokens.weight");
+  R.insert("backbone.model.encoder.norm.weight");
+  R.insert("backbone.model.decoder.norm.weight");
+  R.insert("audio_embedding.0.weight");
+  R.insert("predict_layer.0.0.weight"); R.insert("predict_layer.0.0.bias");
+  R.insert("predict_layer.0.2.weight"); R.insert("predict_layer.0.2.bias");
+  const char* common[] = {"self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight",
+                          "self_attn.o_proj.weight", "mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight",
+                          "pre_self_attn_layernorm.weight", "post_self_attn_layernorm.weight",
+                          "pre_feedforward_layernorm.weight", "post_feedforward_layernorm.weight"};
+  const char* cross[] = {"cross_attn.q_proj.weight", "cross_attn.k_proj.weight", "cross_attn.v_proj.weight",
+                         "cross_attn.o_proj.weight", "pre_cross_attn_layernorm.weight", "post_cross_attn_layernorm.weight"};
+  for (int l = 0; l < e->c.n_enc_layers; ++l) for (auto s : common) R.insert(lname("encoder", l, s));
+  for (int l = 0; l < e->c.n_dec_layers; ++l) {
+    for (auto s : common) R.insert(lname("decoder", l, s));
+    for (auto s : cross) R.insert(lname("decoder", l, s));
+  }
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- GEMM dispatch (prefill / batched path) ----------------------------------------------------
+cudaError_t gemm(T5GEngine* e, const bf16* A, const bf16* W, int M, int N, int K, int epi, const float* bias,
+                 void* out, int ldo, cudaStream_t st) {
+  GemmArgs g{A, W, M, N, K, epi, bias, out, ldo};
+  e->launches++;
+  if (e->gemm_impl == 1) return launch_gemm_tc(g, st);
+  return launch_gemm_simt(g, st);
+}
+
+#define CU(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { t5g_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); return T5G_ERR_CUDA; } } while (0)
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
+  T5G_CHECK(cfg && out, T5G_ERR_INVALID, "null argument");
+  T5G_CHECK(cfg->abi_version == T5G_ABI_VERSION, T5G_ERR_INVALID, "ABI version mismatch: %d vs %d", cfg->abi_version, T5G_ABI_VERSION);
+  T5G_CHECK(cfg->n_enc_layers > 0 && cfg->n_enc_layers <= T5G_MAX_LAYERS && cfg->n_dec_layers > 0 && cfg->n_dec_layers <= T5G_MAX_LAYERS,
+            T5G_ERR_INVALID, "layer count out of range");
+  T5G_CHECK(cfg->n_heads % cfg->n_kv_heads == 0, T5G_ERR_INVALID, "n_heads must be a multiple of n_kv_heads");
+  const int G = cfg->n_heads / cfg->n_kv_heads, D = cfg->head_dim;
+  T5G_CHECK((G == 1 || G == 2 || G == 4) && (D == 16 || D == 32 || D == 64 || D == 128 || D == 256) && !(G == 4 && D == 256),
+            T5G_ERR_UNSUPPORTED, "unsupported attention geometry G=%d D=%d", G, D);
+  T5G_CHECK(cfg->hidden % 8 == 0 && cfg->inter % 8 == 0 && cfg->hidden <= 4096, T5G_ERR_UNSUPPORTED, "hidden/inter must be multiples of 8, hidden<=4096");
+  T5G_CHECK(cfg->max_slots >= 1 && cfg->max_text_len >= 1 && cfg->max_dec_len >= 2 && cfg->max_prefill_tokens >= 1,
+            T5G_ERR_INVALID, "bad engine sizing");
+  T5G_CHECK(cfg->kv_page_tokens > 0 && cfg->kv_page_tokens % 4 == 0, T5G_ERR_INVALID, "kv_page_tokens must be a positive multiple of 4");
+  T5G_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  T5G_CUDA(cudaGetDeviceProperties(&prop, device));
+  T5G_CHECK(prop.major == 10, T5G_ERR_UNSUPPORTED, "libt5gtts requires an sm_100 (B200) device, found sm_%d%d", prop.major, prop.minor);
+
+  T5GEngine* e = new T5GEngine();
+  e->c = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount;
+  e->d = cfg->hidden; e->I = cfg->inter; e->Hq = cfg->n_heads; e->Hkv = cfg->n_kv_heads; e->D = D;
+  e->QD = e->Hq * D; e->KD = e->Hkv * D; e->QKV = e->QD + 2 * e->KD;
+  e->V = cfg->n_audio_tokens; e->Vpad = cdiv(e->V, 64) * 64; e->PT = cfg->kv_page_tokens;
+  if (const char* s = getenv("T5G_PDL")) e->use_pdl = atoi(s) != 0;
+  if (const char* s = getenv("T5G_GRAPH")) e->use_graph = atoi(s) != 0;
+  if (const char* s = getenv("T5G_GEMM")) e->gemm_impl = atoi(s);
+  *out = e;   // so that the caller can destroy on failure
+  T5G_CUDA(cudaStreamCreateWithFlags(&e->load_stream, cudaStreamNonBlocking));
+  for (auto& ev : e->ev) T5G_CUDA(cudaEventCreate(&ev));
+
+  const int d = e->d, I = e->I, QD = e->QD, KD = e->KD, QKV = e->QKV;
+  // ---- weights ----
+  DM(e->enc_embed, (size_t)cfg->text_vocab * d);
+  DM(e->g_enc_final, d); DM(e->g_dec_final, d);
+  e->enc.resize(cfg->n_enc_layers); e->dec.resize(cfg->n_dec_layers);
+  for (auto& L : e->enc) {
+    DM(L.wqkv, (size_t)QKV * d); DM(L.wo, (size_t)d * QD); DM(L.wgu, (size_t)2 * I * d); DM(L.wd, (size_t)d * I);
+    DM(L.g_pre_sa, d); DM(L.g_post_sa, d); DM(L.g_pre_ff, d); DM(L.g_post_ff, d);
+  }
+  for (auto& L : e->dec) {
+    DM(L.wqkv, (size_t)QKV * d); DM(L.wo, (size_t)d * QD); DM(L.wq_c, (size_t)QD * d); DM(L.wkv_c, (size_t)2 * KD * d);
+    DM(L.wo_c, (size_t)d * QD); DM(L.wgu, (size_t)2 * I * d); DM(L.wd, (size_t)d * I);
+    DM(L.g_pre_sa, d); DM(L.g_post_sa, d); DM(L.g_pre_ca, d); DM(L.g_post_ca, d); DM(L.g_pre_ff, d); DM(L.g_post_ff, d);
+  }
+  DM(e->audio_emb, (size_t)e->V * d);
+  DM(e->head_w1, (size_t)d * d); DM(e->head_b1, d);
+  DM(e->head_w2, (size_t)e->Vpad * d); DM(e->head_b2, e->Vpad);
+  T5G_CUDA(cudaMemset(e->head_w2, 0, sizeof(bf16) * (size_t)e->Vpad * d));
+  T5G_CUDA(cudaMemset(e->head_b2, 0, sizeof(float) * e->Vpad));
+  DM(e->inv_freq, D / 2);
+  {
+    std::vector<float> f(D / 2);
+    // HF:143-145: 1/(theta^(2i/D)) in fp32
+    for (int i = 0; i < D / 2; ++i) f[i] = (float)(1.0 / pow((double)cfg->rope_theta, (double)(2 * i) / (double)D));
+    T5G_CUDA(cudaMemcpy(e->inv_freq, f.data(), sizeof(float) * f.size(), cudaMemcpyHostToDevice));
+  }
+  add_required(e);
+
+  // ---- KV pool ----
+  const int B = cfg->max_slots;
+  e->max_self_pages = cdiv(cfg->max_dec_len, e->PT);
+  e->max_cross_pages = cdiv(cfg->max_text_len, e->PT);
+  e->n_pages = B * (e->max_self_pages + e->max_cross_pages);
+  e->pool.n_pages = e->n_pages; e->pool.page_tokens = e->PT; e->pool.Hkv = e->Hkv; e->pool.D = D;
+  DM(e->pool.base, (size_t)cfg->n_dec_layers * 2 * e->n_pages * e->pool.page_elems());
+  for (int p = e->n_pages - 1; p >= 0; --p) e->free_pages.push_back(p);
+  DM(e->d_self_bt, (size_t)B * e->max_self_pages); DM(e->d_cross_bt, (size_t)B * e->max_cross_pages);
+  T5G_CUDA(cudaMemset(e->d_self_bt, 0, sizeof(int) * (size_t)B * e->max_self_pages));
+  T5G_CUDA(cudaMemset(e->d_cross_bt, 0, sizeof(int) * (size_t)B * e->max_cross_pages));
+  e->hslots.resize(B); e->h_slots.resize(B);
+  memset(e->h_slots.data(), 0, sizeof(SlotDev) * B);
+  DM(e->d_slots, B);
+  T5G_CUDA(cudaMemset(e->d_slots, 0, sizeof(SlotDev) * B));
+  T5G_CUDA(cudaHostAlloc((void**)&e->h_mirror, sizeof(int) * 4 * B, cudaHostAllocMapped));
+  memset(e->h_mirror, 0, sizeof(int) * 4 * B);
+  T5G_CUDA(cudaHostGetDevicePointer((void**)&e->d_mirror, e->h_mirror, 0));
+  T5G_CUDA(cudaHostAlloc((void**)&e->h_tokens, sizeof(int) * (size_t)B * cfg->max_dec_len, cudaHostAllocMapped));
+  T5G_CUDA(cudaHostGetDevicePointer((void**)&e->d_tokens, e->h_tokens, 0));
+  T5G_CUDA(cudaHostAlloc((void**)&e->h_picks, sizeof(int) * (size_t)B * cfg->max_dec_len, cudaHostAllocMapped));
+  T5G_CUDA(cudaHostGetDevicePointer((void**)&e->d_picks, e->h_picks, 0));
+  DM(e->d_forced, (size_t)B * cfg->max_dec_len);
+  e->topk_pool_cap = B * cfg->max_dec_len;
+  DM(e->d_topk_pool, e->topk_pool_cap);
+
+  // ---- prefill workspaces ----
+  const size_t T = cfg->max_prefill_tokens;
+  DM(e->p_h, T * d); DM(e->p_y, T * d); DM(e->p_qkv, T * QKV); DM(e->p_memory, T * d); DM(e->p_ckv, T * 2 * KD); DM(e->p_final, T * d);
+  DM(e->p_xn, T * d); DM(e->p_q, T * QD); DM(e->p_k, T * KD); DM(e->p_v, T * KD); DM(e->p_att, T * QD); DM(e->p_act, T * I);
+  DM(e->p_mem_bf, T * d); DM(e->p_ck, T * KD); DM(e->p_cv, T * KD);
+  DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
+  DM(e->p_ids, T); DM(e->p_seg_of, T); DM(e->p_seg_off_e, B + 1); DM(e->p_seg_off_d, B + 1); DM(e->p_tok_slot, T); DM(e->p_tok_idx, T);
+  DM(e->p_last_rows, B); DM(e->p_pos, T);
+  e->h_stage_bytes = (T * 5 + 3 * (B + 1)) * 4 + 256;
+  T5G_CUDA(cudaHostAlloc(&e->h_stage, e->h_stage_bytes, cudaHostAllocDefault));
+
+  // ---- decode workspaces ----
+  e->h_end = (cfg->n_dec_layers - 1) & 1;
+  e->ns_self = std::max(1, std::min(16, (2 * e->num_sms) / (e->Hkv * B)));
+  e->ns_cross = std::max(1, std::min(4, e->num_sms / (e->Hkv * B)));
+  const int NS = std::max(e->ns_self, e->ns_cross);
+  DM(e->d_hA, (size_t)B * d); DM(e->d_hB, (size_t)B * d); DM(e->d_y, (size_t)B * d); DM(e->d_qkv, (size_t)B * QKV);
+  DM(e->d_qc, (size_t)B * QD); DM(e->d_act, (size_t)B * I); DM(e->d_t1, (size_t)B * d); DM(e->d_logits, (size_t)B * e->Vpad);
+  DM(e->d_part_o, (size_t)B * e->Hq * NS * D); DM(e->d_part_ml, (size_t)B * e->Hq * NS * 2);
+  T5G_CUDA(cudaMemset(e->d_y, 0, sizeof(float) * (size_t)B * d));
+  DM(e->d_sample_u, 4096); DM(e->d_sample_slots, 4096);
+  T5G_CUDA(cudaDeviceSynchronize());
+  return T5G_OK;
+}
+
+extern "C" int t5g_destroy(T5GEngine* e) {
+  if (!e) return T5G_OK;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->h_mirror) cudaFreeHost(e->h_mirror);
+  if (e->h_tokens) cudaFreeHost(e->h_tokens);
+  if (e->h_picks) cudaFreeHost(e->h_picks);
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->load_stream) cudaStreamDestroy(e->load_stream);
+  for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+  delete e;
+  return T5G_OK;
+}
+
+extern "C" int t5g_load_tensor(T5GEngine* e, const char* name, const void* data, int dtype, int ndim,
+                               const int64_t* shape, int on_device) {
+  T5G_CHECK(e && name && data && shape, T5G_ERR_INVALID, "null argument");
+  T5G_CHECK(dtype >= 0 && dtype <= 2, T5G_ERR_INVALID, "bad dtype %d", dtype);
+  T5G_CUDA(cudaSetDevice(e->device));
+  const std::string n = name;
+  // aliases / pruned text modules / buffers of the reference module are accepted and ignored
+  if (n.rfind("encoder_module.", 0) == 0 || n.rfind("decoder_module.", 0) == 0 || n.rfind("backbone.lm_head", 0) == 0 ||
+      n.rfind("backbone.model.decoder.embed_tokens", 0) == 0 || n == "class_weight" || n.find("inv_freq") != std::string::npos)
+    return T5G_OK;
+  Dest dst;
+  T5G_CHECK(resolve(e, n, &dst), T5G_ERR_INVALID, "unknown tensor name '%s'", name);
+  int64_t rows = 1, cols = 1;
+  if (ndim == 1) { rows = 1; cols = shape[0]; }
+  else if (ndim == 2) { rows = shape[0]; cols = shape[1]; }
+  else T5G_CHECK(false, T5G_ERR_INVALID, "tensor '%s': ndim %d unsupported", name, ndim);
+  T5G_CHECK(rows == dst.rows && cols == dst.cols, T5G_ERR_INVALID, "tensor '%s': shape [%lld,%lld] != expected [%lld,%lld]",
+            name, (long long)rows, (long long)cols, (long long)dst.rows, (long long)dst.cols);
+  const size_t esz = dtype == T5G_F32 ? 4 : 2;
+  const void* src = data;
+  void* tmp = nullptr;
+  if (!on_device) {
+    T5G_CUDA(cudaMalloc(&tmp, (size_t)rows * cols * esz));
+    cudaError_t er = cudaMemcpyAsync(tmp, data, (size_t)rows * cols * esz, cudaMemcpyHostToDevice, e->load_stream);
+    if (er != cudaSuccess) { cudaFree(tmp); T5G_CUDA(er); }
+    src = tmp;
+  } else {
+    T5G_CUDA(cudaDeviceSynchronize());   // the caller's producer stream is unknown
+  }
+  cudaError_t er = launch_pack(src, dtype, dst.ptr, dst.is_bf16 ? 1 : 0, rows, cols, dst.row_off, dst.row_mul, dst.add_one ? 1 : 0, e->load_stream);
+  e->launches++;
+  if (er == cudaSuccess) er = cudaStreamSynchronize(e->load_stream);
+  if (tmp) cudaFree(tmp);
+  T5G_CUDA(er);
+  e->loaded.insert(n);
+  return T5G_OK;
+}
+
+extern "C" int t5g_finalize_weights(T5GEngine* e) {
+  T5G_CHECK(e, T5G_ERR_INVALID, "null engine");
+  for (const auto& r : e->required)
+    T5G_CHECK(e->loaded.count(r), T5G_ERR_STATE, "missing tensor '%s' (%zu of %zu loaded)", r.c_str(), e->loaded.size(), e->required.size());
+  e->finalized = true;
+  return T5G_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prefill
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+int alloc_pages(T5GEngine* e, std::vector<int>& dst, int n) {
+  T5G_CHECK((int)e->free_pages.size() >= n, T5G_ERR_OOM, "KV pool exhausted: need %d pages, %zu free", n, e->free_pages.size());
+  for (int i = 0; i < n; ++i) { dst.push_back(e->free_pages.back()); e->free_pages.pop_back(); }
+  return T5G_OK;
+}
+void free_slot_pages(T5GEngine* e, HostSlot& hs) {
+  for (int p : hs.self_pages) e->free_pages.push_back(p);
+  for (int p : hs.cross_pages) e->free_pages.push_back(p);
+  hs.self_pages.clear(); hs.cross_pages.clear();
+}
+
+// one transformer stack pass over M packed tokens.  is_dec selects the decoder (self causal + cross).
+struct StackIO {
+  int M; const int* seg_off; const int* seg_of; const float* pos;   // this stack's tokens
+  int n_seg;
+};
+
+}  // namespace
+
+extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void* stream_) {
+  T5G_CHECK(e && reqs && n_req > 0, T5G_ERR_INVALID, "bad arguments");
+  T5G_CHECK(e->finalized, T5G_ERR_STATE, "weights not finalized");
+  T5G_CHECK(n_req <= e->c.max_slots, T5G_ERR_INVALID, "n_req %d > max_slots %d", n_req, e->c.max_slots);
+  T5G_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int d = e->d, I = e->I, QD = e->QD, KD = e->KD, QKV = e->QKV, D = e->D, PT = e->PT;
+  const T5GConfig& c = e->c;
+  // ---- validate + host bookkeeping ----
+  int Te = 0, Td = 0;
+  std::set<int> seen;
+  for (int r = 0; r < n_req; ++r) {
+    const T5GRequest& q = reqs[r];
+    T5G_CHECK(q.slot >= 0 && q.slot < c.max_slots && !seen.count(q.slot), T5G_ERR_INVALID, "request %d: bad/duplicate slot %d", r, q.slot);
+    seen.insert(q.slot);
+    T5G_CHECK(q.n_text >= 1 && q.n_text <= c.max_text_len && q.text_ids, T5G_ERR_INVALID, "request %d: n_text %d out of range (max %d)", r, q.n_text, c.max_text_len);
+    T5G_CHECK(q.n_dec >= 1 && q.dec_ids, T5G_ERR_INVALID, "request %d: n_dec must be >= 1 (BOS)", r);
+    for (int i = 0; i < q.n_text; ++i) T5G_CHECK(q.text_ids[i] >= 0 && q.text_ids[i] < c.text_vocab, T5G_ERR_INVALID, "request %d: text id %lld out of range", r, (long long)q.text_ids[i]);
+    for (int i = 0; i < q.n_dec; ++i) T5G_CHECK(q.dec_ids[i] >= 0 && q.dec_ids[i] < e->V, T5G_ERR_INVALID, "request %d: audio id %lld out of range", r, (long long)q.dec_ids[i]);
+    const T5GSampling& s = q.sampling;
+    const bool minp = s.min_p > 0.f && s.min_p < 1.f;
+    T5G_CHECK(s.temperature > 0.f, T5G_ERR_INVALID, "request %d: temperature must be > 0", r);
+    if (!q.top_k_schedule)
+      T5G_CHECK(minp || s.top_k > 0 || s.top_p >= 1.0f, T5G_ERR_UNSUPPORTED, "request %d: top_p<1 without top_k>0 needs a full-vocabulary sort (not implemented)", r);
+    T5G_CHECK(s.top_k <= 1024, T5G_ERR_UNSUPPORTED, "request %d: top_k > 1024 not supported", r);
+    Te += q.n_text; Td += q.n_dec;
+  }
+  T5G_CHECK(Te <= c.max_prefill_tokens && Td <= c.max_prefill_tokens, T5G_ERR_INVALID, "prefill tokens (%d text, %d audio) exceed max_prefill_tokens %d", Te, Td, c.max_prefill_tokens);
+
+  // staging layout (pinned): ids_e[Te] ids_d[Td] seg_of_e[Te] seg_of_d[Td] pos_e[Te] pos_d[Td] slot_e idx_e slot_d idx_d offs
+  const int Tm = c.max_prefill_tokens;
+  int* hs = (int*)e->h_stage;
+  int* h_ids = hs; int* h_seg_of = hs + Tm; float* h_pos = (float*)(hs + 2 * Tm); int* h_tslot = hs + 3 * Tm; int* h_tidx = hs + 4 * Tm;
+  int* h_off_e = hs + 5 * Tm; int* h_off_d = h_off_e + (c.max_slots + 1); int* h_last = h_off_d + (c.max_slots + 1);
+
+  e->prefill_counter++;
+  e->topk_pool_used = 0;   // schedules live until the next prefill call
+  std::vector<int> est_totals(n_req);
+  for (int r = 0; r < n_req; ++r) {
+    const T5GRequest& q = reqs[r];
+    HostSlot& hsl = e->hslots[q.slot];
+    free_slot_pages(e, hsl);
+    const int prompt_offset = q.prompt_frames + 1;
+    const int est_total = std::max(q.target_total + 1, q.n_dec);          // models/t5gemma.py:925-933
+    est_totals[r] = est_total;
+    const double lim = (double)q.target_total - (double)prompt_offset + (double)c.encodec_sr * (double)c.extra_cutoff;
+    int budget_limit = (int)std::floor(lim);
+    int max_new = budget_limit + 2;
+    if (max_new < 1) max_new = 1;
+    if (q.max_new_tokens > 0) max_new = std::min(max_new, q.max_new_tokens);
+    const int max_len = q.n_dec + max_new;
+    T5G_CHECK(max_len <= c.max_dec_len, T5G_ERR_INVALID, "request %d: needs %d decoder tokens > max_dec_len %d", r, max_len, c.max_dec_len);
+    int rc = alloc_pages(e, hsl.self_pages, cdiv(max_len, PT)); if (rc) return rc;
+    rc = alloc_pages(e, hsl.cross_pages, cdiv(q.n_text, PT)); if (rc) return rc;
+    hsl.in_use = true; hsl.n_text = q.n_text; hsl.n_dec = q.n_dec; hsl.prefill_id = e->prefill_counter;
+    SlotDev& sd = e->h_slots[q.slot];
+    memset(&sd, 0, sizeof(sd));
+    sd.active = 1; sd.finished = 0; sd.n_generated = 0; sd.cur_len = q.n_dec; sd.prompt_offset = prompt_offset;
+    sd.target_total = q.target_total; sd.est_total = est_total; sd.n_text = q.n_text; sd.budget_limit = budget_limit;
+    sd.max_new_tokens = q.max_new_tokens; sd.top_k = q.sampling.top_k; sd.top_p = q.sampling.top_p; sd.min_p = q.sampling.min_p;
+    sd.temperature = q.sampling.temperature; sd.uniforms = q.uniforms; sd.n_uniforms = q.n_uniforms;
+    sd.topk_sched_off = -1; sd.n_topk_sched = 0; sd.last_token = 0; sd.pos = 0.f;
+    if (q.top_k_schedule && q.n_top_k_schedule > 0) {
+      T5G_CHECK(e->topk_pool_used + q.n_top_k_schedule <= e->topk_pool_cap, T5G_ERR_OOM, "top_k schedule pool exhausted");
+      for (int i = 0; i < q.n_top_k_schedule; ++i)
+        T5G_CHECK((q.top_k_schedule[i] > 0 && q.top_k_schedule[i] <= 1024) || (q.sampling.top_p >= 1.0f && q.top_k_schedule[i] <= 1024), T5G_ERR_UNSUPPORTED, "request %d: schedule entry needs top_k in [1,1024] when top_p<1", r);
+      CU(cudaMemcpyAsync(e->d_topk_pool + e->topk_pool_used, q.top_k_schedule, sizeof(int) * q.n_top_k_schedule, cudaMemcpyHostToDevice, st));
+      sd.topk_sched_off = e->topk_pool_used; sd.n_topk_sched = q.n_top_k_schedule;
+      e->topk_pool_used += q.n_top_k_schedule;
+    }
+    if (q.forced_tokens && q.n_forced > 0) {
+      T5G_CHECK(q.n_forced <= c.max_dec_len, T5G_ERR_INVALID, "request %d: n_forced %d > max_dec_len", r, q.n_forced);
+      for (int i = 0; i < q.n_forced; ++i) T5G_CHECK(q.forced_tokens[i] >= 0 && q.forced_tokens[i] < e->V, T5G_ERR_INVALID, "request %d: forced token out of range", r);
+      CU(cudaMemcpyAsync(e->d_forced + (size_t)q.slot * c.max_dec_len, q.forced_tokens, sizeof(int) * q.n_forced, cudaMemcpyHostToDevice, st));
+      sd.n_forced = q.n_forced;
+    }
+    CU(cudaMemcpyAsync(e->d_slots + q.slot, &sd, sizeof(SlotDev), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->d_self_bt + (size_t)q.slot * e->max_self_pages, hsl.self_pages.data(), sizeof(int) * hsl.self_pages.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->d_cross_bt + (size_t)q.slot * e->max_cross_pages, hsl.cross_pages.data(), sizeof(int) * hsl.cross_pages.size(), cudaMemcpyHostToDevice, st));
+    e->h_mirror[q.slot * 4 + 0] = 1; e->h_mirror[q.slot * 4 + 1] = 0; e->h_mirror[q.slot * 4 + 2] = 0; e->h_mirror[q.slot * 4 + 3] = q.n_dec;
+  }
+  // the pageable host vectors above must outlive the async copies
+  CU(cudaStreamSynchronize(st));
+
+  auto stage_and_upload = [&](bool dec) -> int {
+    int off = 0;
+    int* h_off = dec ? h_off_d : h_off_e;
+    for (int r = 0; r < n_req; ++r) {
+      const T5GRequest& q = reqs[r];
+      const int n = dec ? q.n_dec : q.n_text;
+      h_off[r] = off;
+      if (dec) e->hslots[q.slot].dec_off = off; else e->hslots[q.slot].mem_off = off;
+      for (int i = 0; i < n; ++i) {
+        h_ids[off + i] = (int)(dec ? q.dec_ids[i] : q.text_ids[i]);
+        h_seg_of[off + i] = r; h_tslot[off + i] = q.slot; h_tidx[off + i] = i;
+        float p;
+        if (dec) {            // models/t5gemma.py:945-947: arange/max(1,est_total-1)*scale in fp32
+          p = (float)i / (float)std::max(1, est_totals[r] - 1);
+          p = p * c.progress_scale;
+        } else {              // models/t5gemma.py:609-624
+          p = (float)i / ((float)std::max(n, 2) - 1.0f);
+          p = p * c.progress_scale;
+        }
+        h_pos[off + i] = p;
+      }
+      off += n;
+      if (dec) h_last[r] = off - 1;
+    }
+    h_off[n_req] = off;
+    CU(cudaMemcpyAsync(e->p_ids, h_ids, sizeof(int) * off, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->p_seg_of, h_seg_of, sizeof(int) * off, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->p_pos, h_pos, sizeof(float) * off, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->p_tok_slot, h_tslot, sizeof(int) * off, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->p_tok_idx, h_tidx, sizeof(int) * off, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dec ? e->p_seg_off_d : e->p_seg_off_e, h_off, sizeof(int) * (n_req + 1), cudaMemcpyHostToDevice, st));
+    return T5G_OK;
+  };
+
+  // ================= encoder (HF:664-718, 426-452) =================
+  CU(cudaEventRecord(e->ev[0], st));
+  { int rc = stage_and_upload(false); if (rc) return rc; }
+  CU(launch_embed(e->enc_embed, e->p_ids, sqrtf((float)d), e->p_h, Te, d, st)); e->launches++;
+  for (int l = 0; l < c.n_enc_layers; ++l) {
+    const EncLayer& L = e->enc[l];
+    // h += post_ff(prev y) ; xn = pre_sa(h)
+    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Te, d, c.rms_eps, st));
+    else CU(launch_norm(e->p_h, e->p_y, e->enc[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st));
+    e->launches++;
+    CU(gemm(e, e->p_xn, L.wqkv, Te, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st));
+    RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Te;
+    ra.Hq = e->Hq; ra.Hkv = e->Hkv; ra.D = D; ra.inv_freq = e->inv_freq; ra.q_out = e->p_q; ra.k_out = e->p_k; ra.v_out = e->p_v; ra.block_table = nullptr;
+    CU(launch_rope_split(ra, st)); e->launches++;
+    AttnPrefillArgs aa{}; aa.q = e->p_q; aa.k = e->p_k; aa.v = e->p_v; aa.q_seg_off = e->p_seg_off_e; aa.k_seg_off = e->p_seg_off_e; aa.q_seg_of = e->p_seg_of;
+    aa.Tq = Te; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.D = D; aa.causal = 0; aa.window = c.enc_layer_sliding[l] ? c.sliding_window : 0;
+    aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
+    CU(launch_attn_prefill(aa, st)); e->launches++;
+    CU(gemm(e, e->p_att, L.wo, Te, d, QD, GE_F32, nullptr, e->p_y, d, st));
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st)); e->launches++;
+    CU(gemm(e, e->p_xn, L.wgu, Te, 2 * I, d, GE_GEGLU_BF16, nullptr, e->p_act, I, st));
+    CU(gemm(e, e->p_act, L.wd, Te, d, I, GE_F32, nullptr, e->p_y, d, st));
+  }
+  // memory = final_norm(h + post_ff(y))
+  CU(launch_norm(e->p_h, e->p_y, e->enc[c.n_enc_layers - 1].g_post_ff, e->g_enc_final, nullptr, e->p_mem_bf, e->p_memory, Te, d, c.rms_eps, st)); e->launches++;
+  CU(cudaEventRecord(e->ev[1], st));
+
+  // ================= decoder over BOS + prompt (HF:748-828; models/t5gemma.py:183-243) =================
+  // encoder-side metadata needed for the cross K/V (positions, slots) is re-derived per layer from a
+  // second staging copy kept on the device: pos_e/tok_* are overwritten by the decoder upload, so keep copies.
+  float* pos_e; int *tslot_e, *tidx_e, *seg_of_e;
+  // copies of encoder metadata (device->device) into the (unused during prefill) p_final scratch region
+  // p_final is [T,d] floats; we need 4*Te ints, d >= 8 guarantees room.
+  pos_e = e->p_final; tslot_e = (int*)(e->p_final + Tm); tidx_e = (int*)(e->p_final + 2 * (size_t)Tm); seg_of_e = (int*)(e->p_final + 3 * (size_t)Tm);
+  CU(cudaMemcpyAsync(pos_e, e->p_pos, sizeof(float) * Te, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(tslot_e, e->p_tok_slot, sizeof(int) * Te, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(tidx_e, e->p_tok_idx, sizeof(int) * Te, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(seg_of_e, e->p_seg_of, sizeof(int) * Te, cudaMemcpyDeviceToDevice, st));
+  CU(cudaStreamSynchronize(st));     // staging buffer is reused by the decoder upload
+  { int rc = stage_and_upload(true); if (rc) return rc; }
+  CU(cudaMemcpyAsync(e->p_last_rows, h_last, sizeof(int) * n_req, cudaMemcpyHostToDevice, st));
+  CU(launch_embed(e->audio_emb, e->p_ids, sqrtf((float)d), e->p_h, Td, d, st)); e->launches++;
+  for (int l = 0; l < c.n_dec_layers; ++l) {
+    const DecLayer& L = e->dec[l];
+    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Td, d, c.rms_eps, st));
+    else CU(launch_norm(e->p_h, e->p_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st));
+    e->launches++;
+    CU(gemm(e, e->p_xn, L.wqkv, Td, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st));
+    RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Td;
+    ra.Hq = e->Hq; ra.Hkv = e->Hkv; ra.D = D; ra.inv_freq = e->inv_freq; ra.q_out = e->p_q; ra.k_out = e->p_k; ra.v_out = e->p_v;
+    ra.pool = e->pool; ra.layer = l; ra.block_table = e->d_self_bt; ra.bt_stride = e->max_self_pages; ra.tok_slot = e->p_tok_slot; ra.tok_idx = e->p_tok_idx;
+    CU(launch_rope_split(ra, st)); e->launches++;
+    AttnPrefillArgs aa{}; aa.q = e->p_q; aa.k = e->p_k; aa.v = e->p_v; aa.q_seg_off = e->p_seg_off_d; aa.k_seg_off = e->p_seg_off_d; aa.q_seg_of = e->p_seg_of;
+    aa.Tq = Td; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.D = D; aa.causal = 1; aa.window = c.dec_layer_sliding[l] ? c.sliding_window : 0;
+    aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
+    CU(launch_attn_prefill(aa, st)); e->launches++;
+    CU(gemm(e, e->p_att, L.wo, Td, d, QD, GE_F32, nullptr, e->p_y, d, st));
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ca, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st)); e->launches++;
+    // cross attention: q = RoPE(q_proj(x), decoder pos); K/V of this layer computed once from memory
+    CU(gemm(e, e->p_xn, L.wq_c, Td, QD, d, GE_F32, nullptr, e->p_qkv, QD, st));
+    RopeSplitArgs rq{}; rq.qkv = e->p_qkv; rq.ld = QD; rq.q_off = 0; rq.k_off = -1; rq.v_off = -1; rq.pos = e->p_pos; rq.M = Td;
+    rq.Hq = e->Hq; rq.Hkv = e->Hkv; rq.D = D; rq.inv_freq = e->inv_freq; rq.q_out = e->p_q; rq.block_table = nullptr;
+    CU(launch_rope_split(rq, st)); e->launches++;
+    CU(gemm(e, e->p_mem_bf, L.wkv_c, Te, 2 * KD, d, GE_F32, nullptr, e->p_ckv, 2 * KD, st));
+    RopeSplitArgs rk{}; rk.qkv = e->p_ckv; rk.ld = 2 * KD; rk.q_off = -1; rk.k_off = 0; rk.v_off = KD; rk.pos = pos_e; rk.M = Te;
+    rk.Hq = e->Hq; rk.Hkv = e->Hkv; rk.D = D; rk.inv_freq = e->inv_freq; rk.k_out = e->p_ck; rk.v_out = e->p_cv;
+    rk.pool = e->pool; rk.layer = l; rk.block_table = e->d_cross_bt; rk.bt_stride = e->max_cross_pages; rk.tok_slot = tslot_e; rk.tok_idx = tidx_e;
+    CU(launch_rope_split(rk, st)); e->launches++;
+    AttnPrefillArgs ac{}; ac.q = e->p_q; ac.k = e->p_ck; ac.v = e->p_cv; ac.q_seg_off = e->p_seg_off_d; ac.k_seg_off = e->p_seg_off_e; ac.q_seg_of = e->p_seg_of;
+    ac.Tq = Td; ac.Hq = e->Hq; ac.Hkv = e->Hkv; ac.D = D; ac.causal = 0; ac.window = 0; ac.scale = c.attn_scale; ac.softcap = c.attn_softcap; ac.out = e->p_att;
+    CU(launch_attn_prefill(ac, st)); e->launches++;
+    CU(gemm(e, e->p_att, L.wo_c, Td, d, QD, GE_F32, nullptr, e->p_y, d, st));
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_ca, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st)); e->launches++;
+    CU(gemm(e, e->p_xn, L.wgu, Td, 2 * I, d, GE_GEGLU_BF16, nullptr, e->p_act, I, st));
+    CU(gemm(e, e->p_act, L.wd, Td, d, I, GE_F32, nullptr, e->p_y, d, st));
+  }
+  // h = h + post_ff(y) (kept, pre-final-norm) ; p_qkv <- final_norm(h) fp32 for teacher-forced logits
+  CU(launch_norm(e->p_h, e->p_y, e->dec[c.n_dec_layers - 1].g_post_ff, e->g_dec_final, e->p_h, nullptr, e->p_final, Td, d, c.rms_eps, st)); e->launches++;
+  // hand the last token of every request to the decode buffers: h_end buffer <- h, y <- 0
+  {
+    for (int r = 0; r < n_req; ++r) {
+      float* hdst = (e->h_end == 0 ? e->d_hA : e->d_hB) + (size_t)reqs[r].slot * d;
+      CU(cudaMemcpyAsync(hdst, e->p_h + (size_t)h_last[r] * d, sizeof(float) * d, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemsetAsync(e->d_y + (size_t)reqs[r].slot * d, 0, sizeof(float) * d, st));
+    }
+  }
+  CU(cudaEventRecord(e->ev[2], st));
+  CU(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&e->timings[0], e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&e->timings[2], e->ev[1], e->ev[2]);
+  e->timings[1] = 0.f;
+  return T5G_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode step
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
+  const T5GConfig& c = e->c;
+  const int d = e->d, I = e->I, QD = e->QD, KD = e->KD, QKV = e->QKV, D = e->D;
+  const int B = c.max_slots;
+  const bool pdl = e->use_pdl;
+  int nl = 0;
+  float* hbuf[2] = {e->d_hA, e->d_hB};
+  // batch rows are processed in groups of <= 4 by the GEMV family
+  auto gemv_all = [&](GemvArgs a, int P, int E, size_t in_stride, size_t out_stride) -> cudaError_t {
+    for (int b0 = 0; b0 < B; b0 += 4) {
+      GemvArgs g = a;
+      g.B = std::min(4, B - b0); g.slot0 = b0;
+      if (g.x) g.x += (size_t)b0 * in_stride;
+      if (g.h_in) g.h_in += (size_t)b0 * d;
+      if (g.y) g.y += (size_t)b0 * d;
+      if (g.h_out) g.h_out += (size_t)b0 * d;
+      if (g.part_o) { g.part_o += (size_t)b0 * e->Hq * g.n_splits * D; g.part_ml += (size_t)b0 * e->Hq * g.n_splits * 2; }
+      g.out += (size_t)b0 * out_stride;
+      cudaError_t er = launch_gemv(g, P, E, e->num_sms, st, pdl);
+      if (er != cudaSuccess) return er;
+      nl++;
+    }
+    return cudaSuccess;
+  };
+  GemvArgs z{}; z.eps = c.rms_eps; z.slots = e->d_slots; z.head_dim = D;
+
+  const DecLayer& Llast = e->dec[c.n_dec_layers - 1];
+  // ---- head: t1 = gelu(W1 * final_norm(h + post_ff(y)) + b1) ; logits = W2 t1 + b2 ----
+  { GemvArgs a = z; a.W = e->head_w1; a.N = d; a.K = d; a.h_in = hbuf[e->h_end]; a.y = e->d_y; a.g_post = Llast.g_post_ff; a.g_pre = e->g_dec_final;
+    a.h_out = nullptr; a.bias = e->head_b1; a.out = e->d_t1; a.out_stride = d;
+    CU(gemv_all(a, P_RES_NORM, E_BIAS_GELU, 0, d)); }
+  { GemvArgs a = z; a.W = e->head_w2; a.N = e->Vpad; a.K = d; a.x = e->d_t1; a.bias = e->head_b2; a.out = e->d_logits; a.out_stride = e->Vpad;
+    CU(gemv_all(a, P_PLAIN, E_BIAS, d, e->Vpad)); }
+  // ---- sample + stop rules + state update ----
+  { SamplerArgs s{}; s.logits = e->d_logits; s.ld = e->Vpad; s.V = e->V; s.slots = e->d_slots; s.topk_sched_pool = e->d_topk_pool;
+    s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
+    s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = B; s.host_mirror = e->d_mirror;
+    s.picks_out = e->d_picks; s.forced_pool = e->d_forced;
+    CU(launch_sampler(s, st, pdl)); nl++; }
+  // ---- 26 decoder layers at q_len = 1 ----
+  int t = 0;   // hbuf[t] holds the current residual
+  for (int l = 0; l < c.n_dec_layers; ++l) {
+    const DecLayer& L = e->dec[l];
+    { GemvArgs a = z; a.W = L.wqkv; a.N = QKV; a.K = d; a.g_pre = L.g_pre_sa; a.out = e->d_qkv; a.out_stride = QKV;
+      if (l == 0) { a.emb = e->audio_emb; a.emb_scale = sqrtf((float)d); a.h_out = hbuf[0]; t = 0; CU(gemv_all(a, P_EMBED_NORM, E_STORE, 0, QKV)); }
+      else { a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = e->dec[l - 1].g_post_ff; a.h_out = hbuf[t ^ 1]; t ^= 1; CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QKV)); } }
+    { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
+      a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
+      a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq;
+      a.part_o = e->d_part_o; a.part_ml = e->d_part_ml;
+      CU(launch_attn_decode(a, st, pdl)); nl++; }
+    { GemvArgs a = z; a.W = L.wo; a.N = d; a.K = QD; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml; a.n_splits = e->ns_self; a.out = e->d_y; a.out_stride = d;
+      CU(gemv_all(a, P_COMBINE, E_STORE, 0, d)); }
+    { GemvArgs a = z; a.W = L.wq_c; a.N = QD; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_sa; a.g_pre = L.g_pre_ca; a.h_out = hbuf[t ^ 1]; t ^= 1;
+      a.out = e->d_qc; a.out_stride = QD;
+      CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QD)); }
+    { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
+      a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
+      a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq;
+      a.part_o = e->d_part_o; a.part_ml = e->d_part_ml;
+      CU(launch_attn_decode(a, st, pdl)); nl++; }
+    { GemvArgs a = z; a.W = L.wo_c; a.N = d; a.K = QD; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml; a.n_splits = e->ns_cross; a.out = e->d_y; a.out_stride = d;
+      CU(gemv_all(a, P_COMBINE, E_STORE, 0, d)); }
+    { GemvArgs a = z; a.W = L.wgu; a.N = 2 * I; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_ca; a.g_pre = L.g_pre_ff; a.h_out = hbuf[t ^ 1]; t ^= 1;
+      a.out = e->d_act; a.out_stride = I;
+      CU(gemv_all(a, P_RES_NORM, E_GEGLU, 0, I)); }
+    { GemvArgs a = z; a.W = L.wd; a.N = d; a.K = I; a.x = e->d_act; a.out = e->d_y; a.out_stride = d;
+      CU(gemv_all(a, P_PLAIN, E_STORE, I, d)); }
+  }
+  if (t != e->h_end) { t5g_set_error("internal: residual buffer parity %d != %d", t, e->h_end); return T5G_ERR_STATE; }
+  *n_launch = nl;
+  return T5G_OK;
+}
+
+}  // namespace
+
+extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
+  T5G_CHECK(e && max_steps > 0, T5G_ERR_INVALID, "bad arguments");
+  T5G_CHECK(e->finalized, T5G_ERR_STATE, "weights not finalized");
+  T5G_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream_;
+  CU(cudaEventRecord(e->ev[3], st));
+  if (e->use_graph) {
+    if (!e->step_graph) {
+      cudaStream_t cs;
+      CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      // warm the lazily-set function attributes outside capture
+      int nl = 0;
+      cudaGraph_t g = nullptr;
+      CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+      int rc = enqueue_step(e, cs, &nl);
+      cudaError_t er = cudaStreamEndCapture(cs, &g);
+      if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cs); return rc; }
+      CU(er);
+      CU(cudaGraphInstantiate(&e->step_graph, g, 0));
+      cudaGraphDestroy(g);
+      cudaStreamDestroy(cs);
+      e->nodes_per_step = nl;
+    }
+    for (int i = 0; i < max_steps; ++i) CU(cudaGraphLaunch(e->step_graph, st));
+    e->launches += (int64_t)e->nodes_per_step * max_steps;
+  } else {
+    for (int i = 0; i < max_steps; ++i) { int nl = 0; int rc = enqueue_step(e, st, &nl); if (rc) return rc; e->launches += nl; }
+  }
+  CU(cudaEventRecord(e->ev[4], st));
+  return T5G_OK;
+}
+
+extern "C" int t5g_poll(T5GEngine* e, T5GSlotState* states, void* stream_) {
+  T5G_CHECK(e && states, T5G_ERR_INVALID, "bad arguments");
+  T5G_CUDA(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize((cudaStream_t)stream_));
+  if (cudaEventQuery(e->ev[4]) == cudaSuccess) cudaEventElapsedTime(&e->timings[3], e->ev[3], e->ev[4]);
+  cudaGetLastError();
+  for (int s = 0; s < e->c.max_slots; ++s) {
+    states[s].active = e->h_mirror[s * 4 + 0]; states[s].finished = e->h_mirror[s * 4 + 1];
+    states[s].n_generated = e->h_mirror[s * 4 + 2]; states[s].cur_len = e->h_mirror[s * 4 + 3];
+  }
+  return T5G_OK;
+}
+
+extern "C" int t5g_read_tokens(T5GEngine* e, int slot, int32_t* out, int max_tokens, int* n_out, void* stream_) {
+  T5G_CHECK(e && out && n_out && slot >= 0 && slot < e->c.max_slots, T5G_ERR_INVALID, "bad arguments");
+  CU(cudaStreamSynchronize((cudaStream_t)stream_));
+  const int n = std::min(max_tokens, e->h_mirror[slot * 4 + 2]);
+  memcpy(out, e->h_tokens + (size_t)slot * e->c.max_dec_len, sizeof(int) * n);
+  *n_out = n;
+  return T5G_OK;
+}
+
+extern "C" int t5g_read_picks(T5GEngine* e, int slot, int32_t* out, int max_tokens, int* n_out, void* stream_) {
+  T5G_CHECK(e && out && n_out && slot >= 0 && slot < e->c.max_slots, T5G_ERR_INVALID, "bad arguments");
+  CU(cudaStreamSynchronize((cudaStream_t)stream_));
+  const int n = std::min(max_tokens, e->h_mirror[slot * 4 + 2]);
+  memcpy(out, e->h_picks + (size_t)slot * e->c.max_dec_len, sizeof(int) * n);
+  *n_out = n;
+  return T5G_OK;
+}
+
+extern "C" int t5g_release_slot(T5GEngine* e, int slot) {
+  T5G_CHECK(e && slot >= 0 && slot < e->c.max_slots, T5G_ERR_INVALID, "bad slot");
+  T5G_CUDA(cudaSetDevice(e->device));
+  HostSlot& hs = e->hslots[slot];
+  free_slot_pages(e, hs);
+  hs.in_use = false;
+  SlotDev sd; memset(&sd, 0, sizeof(sd));
+  e->h_slots[slot] = sd;
+  CU(cudaMemcpy(e->d_slots + slot, &sd, sizeof(sd), cudaMemcpyHostToDevice));
+  for (int i = 0; i < 4; ++i) e->h_mirror[slot * 4 + i] = 0;
+  return T5G_OK;
+}
+
+extern "C" int t5g_read_memory(T5GEngine* e, int slot, float* out, void* stream_) {
+  T5G_CHECK(e && out && slot >= 0 && slot < e->c.max_slots, T5G_ERR_INVALID, "bad arguments");
+  const HostSlot& hs = e->hslots[slot];
+  T5G_CHECK(hs.in_use && hs.prefill_id == e->prefill_counter && hs.mem_off >= 0, T5G_ERR_STATE, "slot %d was not part of the last prefill", slot);
+  CU(cudaStreamSynchronize((cudaStream_t)stream_));
+  CU(cudaMemcpy(out, e->p_memory + (size_t)hs.mem_off * e->d, sizeof(float) * (size_t)hs.n_text * e->d, cudaMemcpyDeviceToHost));
+  return T5G_OK;
+}
+
+extern "C" int t5g_read_last_hidden(T5GEngine* e, int slot, float* out, void* stream_) {
+  T5G_CHECK(e && out && slot >= 0 && slot < e->c.max_slots, T5G_ERR_INVALID, "bad arguments");
+  const HostSlot& hs = e->hslots[slot];
+  T5G_CHECK(hs.in_use && hs.prefill_id == e->prefill_counter, T5G_ERR_STATE, "slot %d was not part of the last prefill", slot);
+  CU(cudaStreamSynchronize((cudaStream_t)stream_));
+  CU(cudaMemcpy(out, e->p_final + (size_t)(hs.dec_off + hs.n_dec - 1) * e->d, sizeof(float) * e->d, cudaMemcpyDeviceToHost));
+  return T5G_OK;
+}
+
+extern "C" int t5g_read_logits(T5GEngine* e, int slot, float* out, void* stream_) {
+  T5G_CHECK(e && out && slot >= 0 && slot < e->c.max_slots, T5G_ERR_INVALID, "bad arguments");
+  CU(cudaStreamSynchronize((cudaStream_t)stream_));
+  CU(cudaMemcpy(out, e->d_logits + (size_t)slot * e->Vpad, sizeof(float) * e->V, cudaMemcpyDeviceToHost));
+  return T5G_OK;
+}
+
+extern "C" int t5g_prefill_logits(T5GEngine* e, int slot, float* out, void* stream_) {
+  T5G_CHECK(e && out && slot >= 0 && slot < e->c.max_slots, T5G_ERR_INVALID, "bad arguments");
+  const HostSlot& hs = e->hslots[slot];
+  T5G_CHECK(hs.in_use && hs.prefill_id == e->prefill_counter, T5G_ERR_STATE, "slot %d was not part of the last prefill", slot);
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int d = e->d;
+  for (int t0 = 0; t0 < hs.n_dec; t0 += e->logits_chunk) {
+    const int n = std::min(e->logits_chunk, hs.n_dec - t0);
+    const float* src = e->p_final + (size_t)(hs.dec_off + t0) * d;
+    CU(launch_f32_to_bf16(src, e->p_xn, (size_t)n * d, st)); e->launches++;
+    CU(gemm(e, e->p_xn, e->head_w1, n, d, d, GE_BIAS_GELU_BF16, e->head_b1, e->p_act, d, st));
+    CU(gemm(e, e->p_act, e->head_w2, n, e->Vpad, d, GE_BIAS_F32, e->head_b2, e->p_logits, e->Vpad, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy2D(out + (size_t)t0 * e->V, sizeof(float) * e->V, e->p_logits, sizeof(float) * e->Vpad, sizeof(float) * e->V, n, cudaMemcpyDeviceToHost));
+  }
+  return T5G_OK;
+}
+
+extern "C" int t5g_sample(T5GEngine* e, float* logits, const T5GSampleRow* rows, int n_rows, int32_t* out_tokens,
+                          int32_t* out_argmax, void* stream_) {
+  T5G_CHECK(e && logits && rows && out_tokens && n_rows > 0 && n_rows <= 4096, T5G_ERR_INVALID, "bad arguments");
+  T5G_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream_;
+  const T5GConfig& c = e->c;
+  std::vector<SlotDev> sd(n_rows);
+  std::vector<float> us(n_rows);
+  for (int i = 0; i < n_rows; ++i) {
+    const T5GSampleRow& r = rows[i];
+    const bool minp = r.sampling.min_p > 0.f && r.sampling.min_p < 1.f;
+    T5G_CHECK(r.sampling.temperature > 0.f, T5G_ERR_INVALID, "row %d: temperature must be > 0", i);
+    T5G_CHECK(minp || r.sampling.top_k > 0 || r.sampling.top_p >= 1.0f, T5G_ERR_UNSUPPORTED, "row %d: top_p<1 without top_k>0 not implemented", i);
+    T5G_CHECK(r.sampling.top_k <= 1024, T5G_ERR_UNSUPPORTED, "row %d: top_k > 1024 not supported", i);
+    SlotDev& s = sd[i]; memset(&s, 0, sizeof(s));
+    s.active = 1; s.n_generated = r.cur_num_gen; s.cur_len = r.current_length; s.prompt_offset = r.prompt_offset; s.target_total = r.target_total;
+    s.est_total = std::max(r.target_total + 1, 1); s.n_text = r.n_text;
+    s.budget_limit = (int)std::floor((double)r.target_total - (double)r.prompt_offset + (double)c.encodec_sr * (double)c.extra_cutoff);
+    s.top_k = r.sampling.top_k; s.top_p = r.sampling.top_p; s.min_p = r.sampling.min_p; s.temperature = r.sampling.temperature;
+    s.uniforms = e->d_sample_u + i; s.n_uniforms = 1; s.topk_sched_off = -1;
+    // the kernel indexes uniforms by n_generated (clamped to n_uniforms-1 = 0)
+    us[i] = r.u;
+  }
+  int *d_tok = nullptr, *d_amax = nullptr;
+  CU(cudaMalloc(&d_tok, sizeof(int) * n_rows * 2));
+  d_amax = d_tok + n_rows;
+  CU(cudaMemcpyAsync(e->d_sample_u, us.data(), sizeof(float) * n_rows, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(e->d_sample_slots, sd.data(), sizeof(SlotDev) * n_rows, cudaMemcpyHostToDevice, st));
+  SamplerArgs s{}; s.logits = logits; s.ld = e->V; s.V = e->V; s.slots = e->d_sample_slots; s.topk_sched_pool = e->d_topk_pool;
+  s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
+  s.tokens_out = d_tok; s.tokens_stride = 1; s.flat_tokens = 1; s.argmax_out = d_amax; s.rows = n_rows; s.host_mirror = nullptr;
+  cudaError_t er = launch_sampler(s, st, false);
+  e->launches++;
+  if (er == cudaSuccess) er = cudaMemcpyAsync(out_tokens, d_tok, sizeof(int) * n_rows, cudaMemcpyDeviceToHost, st);
+  if (er == cudaSuccess && out_argmax) er = cudaMemcpyAsync(out_argmax, d_amax, sizeof(int) * n_rows, cudaMemcpyDeviceToHost, st);
+  if (er == cudaSuccess) er = cudaStreamSynchronize(st);
+  cudaFree(d_tok);
+  CU(er);
+  return T5G_OK;
+}
+
+extern "C" int64_t t5g_launch_count(const T5GEngine* e) { return e ? e->launches : 0; }
+
+extern "C" int64_t t5g_weight_bytes_per_step(const T5GEngine* e) {
+  if (!e) return 0;
+  const int64_t d = e->d, I = e->I, QD = e->QD, QKV = e->QKV;
+  // decoder layers without the cross K/V projections, six norm gains per layer (bf16 in the
+  // reference's accounting), final norm, head (weights + biases), one embedding row
+  int64_t per_layer = QKV * d + d * QD + QD * d + d * QD + 2 * I * d + d * I + 6 * d;
+  int64_t params = per_layer * e->c.n_dec_layers + d + (d * d + d) + ((int64_t)e->V * d + e->V) + d;
+  return params * 2;
+}
+
+extern "C" int64_t t5g_kv_bytes_per_token(const T5GEngine* e) {
+  if (!e) return 0;
+  return (int64_t)e->c.n_dec_layers * 2 * e->KD * 2;
+}
+
+extern "C" int t5g_get_timings(T5GEngine* e, float* out) {
+  T5G_CHECK(e && out, T5G_ERR_INVALID, "bad arguments");
+  for (int i = 0; i < 4; ++i) out[i] = e->timings[i];
+  return T5G_OK;
+}
+
+extern "C" int t5g_debug_gemm(T5GEngine* e, const void* x, const void* w, float* out, int M, int N, int K, int impl, void* stream_) {
+  T5G_CHECK(e && x && w && out, T5G_ERR_INVALID, "bad arguments");
+  T5G_CUDA(cudaSetDevice(e->device));
+  GemmArgs g{(const bf16*)x, (const bf16*)w, M, N, K, GE_F32, nullptr, out, N};
+  e->launches++;
+  CU(impl == 1 ? launch_gemm_tc(g, (cudaStream_t)stream_) : launch_gemm_simt(g, (cudaStream_t)stream_));
+  return T5G_OK;
+}
+
+extern "C" int t5g_debug_gemv(T5GEngine* e, const float* x, const void* w, float* out, int B, int N, int K, void* stream_) {
+  T5G_CHECK(e && x && w && out && B >= 1 && B <= 4, T5G_ERR_INVALID, "bad arguments");
+  T5G_CUDA(cudaSetDevice(e->device));
+  GemvArgs a{}; a.W = (const bf16*)w; a.N = N; a.K = K; a.B = B; a.x = x; a.out = out; a.out_stride = N; a.slots = nullptr;
+  e->launches++;
+  CU(launch_gemv(a, P_PLAIN, E_STORE, e->num_sms, (cudaStream_t)stream_, false));
+  return T5G_OK;
+}

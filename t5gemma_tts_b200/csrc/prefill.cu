@@ -1,0 +1,232 @@
+// Prefill-side glue kernels: embedding gather, RMSNorm sandwich, RoPE split + paged KV append,
+// baseline SIMT GEMM (bring-up / cross-check for the tcgen05 GEMM), weight packing.
+#include "kernels.h"
+
+namespace {
+
+__global__ void embed_kernel(const bf16* __restrict__ table, const int* __restrict__ ids, float scale,
+                             float* __restrict__ h, int M, int d) {
+  const int t = blockIdx.x;
+  const bf16* row = table + (size_t)ids[t] * d;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) h[(size_t)t * d + k] = __bfloat162float(row[k]) * scale;
+}
+
+// one CTA per token: h_out = h_in + rmsnorm(y)*g_post ; xn/xf = rmsnorm(h_out)*g_pre  (HF:66-74 in fp32)
+__global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ h_in, const float* __restrict__ y,
+                                                   const float* __restrict__ g_post, const float* __restrict__ g_pre,
+                                                   float* __restrict__ h_out, bf16* __restrict__ xn,
+                                                   float* __restrict__ xf, int d, float eps) {
+  __shared__ float red[32];
+  extern __shared__ float hs[];
+  const size_t base = (size_t)blockIdx.x * d;
+  float rinv_y = 0.f;
+  if (y) {
+    float ys = 0.f;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) { float v = y[base + k]; ys = fmaf(v, v, ys); }
+    ys = block_sum(ys, red);
+    rinv_y = rsqrtf(ys / (float)d + eps);
+  }
+  float ss = 0.f;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    float hv = h_in[base + k];
+    if (y) hv += y[base + k] * rinv_y * g_post[k];
+    hs[k] = hv;
+    if (h_out) h_out[base + k] = hv;
+    ss = fmaf(hv, hv, ss);
+  }
+  if (!g_pre) return;
+  ss = block_sum(ss, red);
+  const float rinv = rsqrtf(ss / (float)d + eps);
+  for (int k = threadIdx.x; k < d; k += blockDim.x) {
+    float v = hs[k] * rinv * g_pre[k];
+    if (xn) xn[base + k] = __float2bfloat16(v);
+    if (xf) xf[base + k] = v;
+  }
+}
+
+// one CTA per token; threads over (head, j<D/2)
+__global__ void rope_split_kernel(RopeSplitArgs a) {
+  const int t = blockIdx.x;
+  const int D = a.D, half = D / 2;
+  const float pos = a.pos ? a.pos[t] : 0.f;
+  const float* row = a.qkv + (size_t)t * a.ld;
+  int slot = -1, idx = 0, page = 0, off = 0;
+  if (a.block_table) {
+    slot = a.tok_slot[t]; idx = a.tok_idx[t];
+    page = a.block_table[(size_t)slot * a.bt_stride + idx / a.pool.page_tokens];
+    off = idx % a.pool.page_tokens;
+  }
+  const int nq = a.q_off >= 0 ? a.Hq * half : 0, nk = a.k_off >= 0 ? a.Hkv * half : 0;
+  for (int i = threadIdx.x; i < nq + nk; i += blockDim.x) {
+    const bool isq = i < nq;
+    const int ii = isq ? i : i - nq;
+    const int hd = ii / half, j = ii - hd * half;
+    float s = 0.f, c = 1.f;
+    if (a.pos) sincosf(pos * a.inv_freq[j], &s, &c);
+    const float* src = row + (isq ? a.q_off : a.k_off) + hd * D;
+    const float x1 = src[j], x2 = src[j + half];
+    const float r1 = x1 * c - x2 * s, r2 = x2 * c + x1 * s;
+    if (isq) {
+      bf16* dst = a.q_out + (size_t)t * a.Hq * D + hd * D;
+      dst[j] = __float2bfloat16(r1); dst[j + half] = __float2bfloat16(r2);
+    } else {
+      if (a.k_out) {
+        bf16* dst = a.k_out + (size_t)t * a.Hkv * D + hd * D;
+        dst[j] = __float2bfloat16(r1); dst[j + half] = __float2bfloat16(r2);
+      }
+      if (a.block_table) {
+        bf16* dst = a.pool.ptr(a.layer, 0, page) + ((size_t)hd * a.pool.page_tokens + off) * D;
+        dst[j] = __float2bfloat16(r1); dst[j + half] = __float2bfloat16(r2);
+      }
+    }
+  }
+  if (a.v_off >= 0) {
+    for (int i = threadIdx.x; i < a.Hkv * D; i += blockDim.x) {
+      const int hd = i / D, j = i - hd * D;
+      const bf16 v = __float2bfloat16(row[a.v_off + i]);
+      if (a.v_out) a.v_out[(size_t)t * a.Hkv * D + i] = v;
+      if (a.block_table) a.pool.ptr(a.layer, 1, page)[((size_t)hd * a.pool.page_tokens + off) * D + j] = v;
+    }
+  }
+}
+
+// ---- baseline GEMM: 64x64 tile, BK=16, 256 threads, 4x4 micro-tile, fp32 FMA ---------------------
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+__device__ __forceinline__ void gemm_store(const GemmArgs& a, int m, int n, float v, float v_pair) {
+  switch (a.epilogue) {
+    case GE_F32: reinterpret_cast<float*>(a.out)[(size_t)m * a.ldo + n] = v; break;
+    case GE_BF16: reinterpret_cast<bf16*>(a.out)[(size_t)m * a.ldo + n] = __float2bfloat16(v); break;
+    case GE_BIAS_F32: reinterpret_cast<float*>(a.out)[(size_t)m * a.ldo + n] = v + a.bias[n]; break;
+    case GE_BIAS_GELU_BF16:
+      reinterpret_cast<bf16*>(a.out)[(size_t)m * a.ldo + n] = __float2bfloat16(gelu_erf_f(v + a.bias[n])); break;
+    case GE_GEGLU_BF16:   // n even = gate row, v_pair = up row
+      reinterpret_cast<bf16*>(a.out)[(size_t)m * a.ldo + (n >> 1)] = __float2bfloat16(gelu_tanh_f(v) * v_pair); break;
+  }
+}
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a) {
+  __shared__ float As[SG_BK][SG_BM + 1];
+  __shared__ float Ws[SG_BK][SG_BN + 1];
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16x16 threads, each 4x4
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < a.K; k0 += SG_BK) {
+    for (int i = threadIdx.x; i < SG_BM * SG_BK; i += 256) {
+      int r = i / SG_BK, c = i % SG_BK;
+      int m = m0 + r, k = k0 + c;
+      As[c][r] = (m < a.M && k < a.K) ? __bfloat162float(a.A[(size_t)m * a.K + k]) : 0.f;
+      int n = n0 + r;
+      Ws[c][r] = (n < a.N && k < a.K) ? __bfloat162float(a.W[(size_t)n * a.K + k]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float av[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = As[k][ty * 4 + i]; wv[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.M) continue;
+    if (a.epilogue == GE_GEGLU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 4; j += 2) {
+        const int n = n0 + tx * 4 + j;
+        if (n + 1 < a.N) gemm_store(a, m, n, acc[i][j], acc[i][j + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n < a.N) gemm_store(a, m, n, acc[i][j], 0.f);
+      }
+    }
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ rows,
+                                   float* __restrict__ dst, int d) {
+  const size_t s = (size_t)rows[blockIdx.x] * d, o = (size_t)blockIdx.x * d;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) dst[o + k] = src[s + k];
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+
+__device__ __forceinline__ float load_as_f32(const void* p, int dtype, size_t i) {
+  if (dtype == 0) return reinterpret_cast<const float*>(p)[i];
+  if (dtype == 1) return __bfloat162float(reinterpret_cast<const bf16*>(p)[i]);
+  return __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+
+__global__ void pack_kernel(const void* __restrict__ src, int src_dtype, void* __restrict__ dst, int dst_is_bf16,
+                            long long rows, long long cols, long long row_off, long long row_mul, int add_one) {
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    float v = load_as_f32(src, src_dtype, (size_t)i);
+    if (add_one) v += 1.0f;
+    const size_t o = (size_t)(row_off + r * row_mul) * cols + c;
+    if (dst_is_bf16) reinterpret_cast<bf16*>(dst)[o] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(dst)[o] = v;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_embed(const bf16* table, const int* ids, float scale, float* h, int M, int d, cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  embed_kernel<<<M, 256, 0, st>>>(table, ids, scale, h, M, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, const float* g_pre, float* h_out,
+                        bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  norm_kernel<<<M, 256, d * sizeof(float), st>>>(h_in, y, g_post, g_pre, h_out, xn, xf, d, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rope_split(const RopeSplitArgs& a, cudaStream_t st) {
+  if (a.M <= 0) return cudaSuccess;
+  rope_split_kernel<<<a.M, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
+  if (a.M <= 0) return cudaSuccess;
+  dim3 grid((a.N + SG_BN - 1) / SG_BN, (a.M + SG_BM - 1) / SG_BM);
+  gemm_simt_kernel<<<grid, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const float* src, const int* rows, float* dst, int n, int d, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  gather_rows_kernel<<<n, 256, 0, st>>>(src, rows, dst, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  f32_to_bf16_kernel<<<grid, 256, 0, st>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const void* src, int src_dtype, void* dst, int dst_is_bf16, int64_t rows, int64_t cols,
+                        int64_t row_off, int64_t row_mul, int add_one, cudaStream_t st) {
+  const int64_t n = rows * cols;
+  if (n == 0) return cudaSuccess;
+  int grid = (int)((n + 255) / 256 < 8192 ? (n + 255) / 256 : 8192);
+  pack_kernel<<<grid, 256, 0, st>>>(src, src_dtype, dst, dst_is_bf16, rows, cols, row_off, row_mul, add_one);
+  return cudaGetLastError();
+}

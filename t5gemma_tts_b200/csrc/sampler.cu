@@ -1,0 +1,317 @@
+// Fused sampling step S: eos edits -> temperature -> (min-p | top-k -> top-p) -> inverse-CDF draw with an
+// explicit uniform -> stop rules -> per-slot state update.  One CTA per batch row, no host sync.
+// Replaces sample_helper (models/t5gemma.py:971-1055) + topk_sampling/top_k_top_p_filtering
+// (models/utils.py:53-122): ~15 ATen launches and 2-3 .item() syncs per token in the reference.
+//
+// Bit-exactness contract (oracle/sampler_oracle.py): every floating-point op that decides the outcome is
+// an individually rounded fp32 op (__fadd_rn/__fmul_rn/__fdiv_rn: never contracted into fma), exp is the
+// fixed polynomial det_exp(), and sums run in the oracle's stated order.  Top-k uses an exact radix
+// select over order-preserving integer keys; survivors are ordered (value desc, index asc).
+#include "kernels.h"
+
+namespace {
+
+constexpr int SAMP_THREADS = 1024;
+constexpr int CAND_CAP = 2048;       // max survivors handled on chip (k + ties)
+constexpr int CHUNK = 256;           // oracle's full-vocabulary summation chunk
+constexpr int MAX_CHUNKS = 1024;
+
+__device__ __forceinline__ float det_exp(float x) {
+  if (x < -86.0f) return 0.f;
+  const float LOG2E = __int_as_float(0x3fb8aa3b), LN2_HI = __int_as_float(0x3f318000),
+              LN2_LO = __int_as_float(0xb95e8083);
+  const float n = rintf(__fmul_rn(x, LOG2E));
+  float r = __fsub_rn(x, __fmul_rn(n, LN2_HI));
+  r = __fsub_rn(r, __fmul_rn(n, LN2_LO));
+  float p = __int_as_float(0x39506967);
+  p = __fadd_rn(__fmul_rn(p, r), __int_as_float(0x3ab743ce));
+  p = __fadd_rn(__fmul_rn(p, r), __int_as_float(0x3c088908));
+  p = __fadd_rn(__fmul_rn(p, r), __int_as_float(0x3d2aa9c1));
+  p = __fadd_rn(__fmul_rn(p, r), __int_as_float(0x3e2aaaaa));
+  p = __fadd_rn(__fmul_rn(p, r), __int_as_float(0x3f000000));
+  float y = __fmul_rn(p, __fmul_rn(r, r));
+  y = __fadd_rn(y, r);
+  y = __fadd_rn(y, 1.0f);
+  return __fmul_rn(y, __int_as_float(((int)n + 127) << 23));
+}
+
+__device__ __forceinline__ unsigned key_of(float z) {
+  unsigned u = (z == 0.f) ? 0u : __float_as_uint(z);      // -0 == +0
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float val_of(unsigned key) {
+  unsigned u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+  return __uint_as_float(u);
+}
+
+struct Shared {
+  unsigned hist[256];
+  unsigned long long cand[CAND_CAP];
+  float e[CAND_CAP];
+  float csum[MAX_CHUNKS];
+  float redv[32]; int redi[32];
+  unsigned prefix; int kth; unsigned n_cand; int overflow;
+  float zmax; int amax; int n_keep; float total;
+};
+
+__global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  Shared& S = *reinterpret_cast<Shared*>(smraw);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  SlotDev& sl = a.slots[row];
+  if (!sl.active) return;
+  float* lg = a.logits + (size_t)row * a.ld;
+  const int V = a.V, eos = a.eos;
+
+  // (1) in-place eos edits (models/t5gemma.py:986-997)
+  const int n_gen = sl.n_generated, cur_len = sl.cur_len;
+  const int eff_len = max(0, cur_len - sl.prompt_offset);
+  if (tid == 0) {
+    if (eff_len == 0) lg[eos] = -1e9f;
+    if (n_gen <= a.encodec_sr / 5) lg[eos] = -10000.0f;
+    S.n_cand = 0; S.overflow = 0;
+  }
+  __syncthreads();
+
+  // (2) argmax of the adjusted logits (first index on ties)
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  for (int i = tid; i < V; i += SAMP_THREADS) {
+    float v = lg[i];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) { S.redv[warp] = bv; S.redi[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    bv = S.redv[lane]; bi = S.redi[lane];
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { S.amax = bi; S.zmax = bv; }
+  }
+  __syncthreads();
+  const float T = sl.temperature;
+  const bool scaled = (T != 1.0f);
+  auto zof = [&](int i) -> float { float v = lg[i]; return scaled ? __fdiv_rn(v, T) : v; };
+  const float zmax = scaled ? __fdiv_rn(S.zmax, T) : S.zmax;
+
+  int top_k = sl.top_k;
+  if (sl.topk_sched_off >= 0 && sl.n_topk_sched > 0)
+    top_k = a.topk_sched_pool[sl.topk_sched_off + min(sl.n_topk_sched - 1, n_gen)];
+  float top_p = sl.top_p;
+  const float min_p = sl.min_p;
+  const int nchunk = (V + CHUNK - 1) / CHUNK;
+  bool have_csum = false;
+  bool filtered = false;
+
+  // (3) min-p (models/utils.py:72-80): full softmax with the oracle's chunked sum
+  if (min_p > 0.f && min_p < 1.f) {
+    for (int c = tid; c < nchunk; c += SAMP_THREADS) {
+      float s = 0.f;
+      const int hi = min(V, (c + 1) * CHUNK);
+      for (int i = c * CHUNK; i < hi; ++i) s = __fadd_rn(s, det_exp(__fsub_rn(zof(i), zmax)));
+      S.csum[c] = s;
+    }
+    __syncthreads();
+    if (tid == 0) { float s = 0.f; for (int c = 0; c < nchunk; ++c) s = __fadd_rn(s, S.csum[c]); S.total = s; }
+    __syncthreads();
+    have_csum = true;
+    const float tot = S.total;
+    for (int i = tid; i < V; i += SAMP_THREADS) {
+      const float z = zof(i);
+      const float pr = __fdiv_rn(det_exp(__fsub_rn(z, zmax)), tot);
+      if (!(pr < min_p)) {
+        unsigned slot = atomicAdd(&S.n_cand, 1u);
+        if (slot < CAND_CAP) S.cand[slot] = ((unsigned long long)key_of(z) << 32) | (0xffffffffu - (unsigned)i);
+        else S.overflow = 1;
+      }
+    }
+    __syncthreads();
+    if (S.n_cand > 0) { filtered = true; top_k = 0; top_p = 1.0f; }
+  }
+
+  // (4) top-k: exact k-th largest by MSB-first radix select, ties kept (models/utils.py:82-86)
+  if (!filtered && top_k > 0) {
+    int k = min(max(top_k, 1), V);
+    unsigned prefix = 0, mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += SAMP_THREADS) S.hist[i] = 0;
+      __syncthreads();
+      for (int i0 = 0; i0 < V; i0 += SAMP_THREADS) {
+        const int i = i0 + tid;
+        const bool ok = i < V;
+        unsigned key = ok ? key_of(zof(i)) : 0u;
+        const bool match = ok && ((key & mask) == prefix);
+        const unsigned digit = (key >> shift) & 0xffu;
+        // warp-aggregated histogram update
+        const unsigned act = __ballot_sync(0xffffffffu, match);
+        if (match) {
+          const unsigned peers = __match_any_sync(act, digit);
+          if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&S.hist[digit], (unsigned)__popc(peers));
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = k; int d = 255;
+        for (; d > 0; --d) { if ((int)S.hist[d] >= rem) break; rem -= (int)S.hist[d]; }
+        S.prefix = prefix | ((unsigned)d << shift); S.kth = rem;
+      }
+      __syncthreads();
+      prefix = S.prefix; k = S.kth; mask |= (0xffu << shift);
+      __syncthreads();
+    }
+    const unsigned thr_key = prefix;
+    for (int i = tid; i < V; i += SAMP_THREADS) {
+      const unsigned key = key_of(zof(i));
+      if (key >= thr_key) {
+        unsigned slot = atomicAdd(&S.n_cand, 1u);
+        if (slot < CAND_CAP) S.cand[slot] = ((unsigned long long)key << 32) | (0xffffffffu - (unsigned)i);
+        else S.overflow = 1;
+      }
+    }
+    __syncthreads();
+    filtered = true;
+  }
+
+  int token = 0;
+  if (filtered) {
+    // sort survivors (value desc, index asc): bitonic on the 64-bit composite, descending
+    const int n = min((int)S.n_cand, CAND_CAP);
+    int np2 = 1; while (np2 < n) np2 <<= 1;
+    for (int i = n + tid; i < np2; i += SAMP_THREADS) S.cand[i] = 0ull;
+    __syncthreads();
+    for (int size = 2; size <= np2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < np2; i += SAMP_THREADS) {
+          const int j = i ^ stride;
+          if (j > i) {
+            const bool desc = ((i & size) == 0);
+            unsigned long long x = S.cand[i], y = S.cand[j];
+            if ((x < y) == desc) { S.cand[i] = y; S.cand[j] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    const float z0 = val_of((unsigned)(S.cand[0] >> 32));
+    for (int i = tid; i < n; i += SAMP_THREADS)
+      S.e[i] = det_exp(__fsub_rn(val_of((unsigned)(S.cand[i] >> 32)), z0));
+    __syncthreads();
+    if (tid == 0) {
+      int n_keep = n;
+      if (top_p < 1.0f) {          // (5) nucleus on the top-k-filtered distribution, shift-right rule
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, S.e[i]);
+        float cum = 0.f;
+        n_keep = 1;
+        for (int i = 0; i + 1 < n; ++i) {
+          cum = __fadd_rn(cum, __fdiv_rn(S.e[i], s));
+          if (cum > top_p) break;   // token i+1 removed (cum through i exceeds p); cum is monotone
+          n_keep = i + 2;
+        }
+      }
+      // (6) inverse-CDF draw over the kept prefix
+      const float u = sl.uniforms ? sl.uniforms[min(n_gen, max(sl.n_uniforms - 1, 0))] : 0.5f;
+      float s2 = 0.f;
+      for (int i = 0; i < n_keep; ++i) s2 = __fadd_rn(s2, S.e[i]);
+      float c = 0.f; int pick = n_keep - 1;
+      for (int i = 0; i < n_keep; ++i) {
+        c = __fadd_rn(c, __fdiv_rn(S.e[i], s2));
+        if (u < c) { pick = i; break; }
+      }
+      S.n_keep = (int)(0xffffffffu - (unsigned)(S.cand[pick] & 0xffffffffull));
+    }
+    __syncthreads();
+    token = S.n_keep;
+  } else {
+    // unfiltered: whole vocabulary in index order, chunked sums, target t = u*s
+    if (!have_csum) {
+      for (int c = tid; c < nchunk; c += SAMP_THREADS) {
+        float s = 0.f;
+        const int hi = min(V, (c + 1) * CHUNK);
+        for (int i = c * CHUNK; i < hi; ++i) s = __fadd_rn(s, det_exp(__fsub_rn(zof(i), zmax)));
+        S.csum[c] = s;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      float s = 0.f;
+      for (int c = 0; c < nchunk; ++c) s = __fadd_rn(s, S.csum[c]);
+      const float u = sl.uniforms ? sl.uniforms[min(n_gen, max(sl.n_uniforms - 1, 0))] : 0.5f;
+      const float t = __fmul_rn(u, s);
+      float cc = 0.f, base = 0.f; int cidx = -1;
+      for (int c = 0; c < nchunk; ++c) { base = cc; cc = __fadd_rn(cc, S.csum[c]); if (t < cc) { cidx = c; break; } }
+      int pick = V - 1;
+      if (cidx >= 0) {
+        const int hi = min(V, (cidx + 1) * CHUNK);
+        float run = base; pick = hi - 1;
+        for (int i = cidx * CHUNK; i < hi; ++i) {
+          run = __fadd_rn(run, det_exp(__fsub_rn(zof(i), zmax)));
+          if (t < run) { pick = i; break; }
+        }
+      }
+      S.n_keep = pick;
+    }
+    __syncthreads();
+    token = S.n_keep;
+  }
+
+  // (7) stop rules + state update (models/t5gemma.py:1020-1048, 1075-1099)
+  if (tid == 0) {
+    const int amax = S.amax;
+    if (a.picks_out && !a.flat_tokens) a.picks_out[(size_t)row * a.tokens_stride + n_gen] = token;
+    if (a.forced_pool && n_gen < sl.n_forced) token = a.forced_pool[(size_t)row * a.tokens_stride + n_gen];
+    bool force = (token == eos) || (amax == eos);
+    if (a.text_guard > 0) force = force || (eff_len > max(1, sl.n_text) * a.text_guard);
+    const bool budget = n_gen > sl.budget_limit;
+    if (force || budget) token = eos;
+    if (sl.max_new_tokens > 0 && n_gen + 1 >= sl.max_new_tokens) token = eos;
+    if (a.tokens_out) a.tokens_out[(size_t)row * a.tokens_stride + (a.flat_tokens ? 0 : n_gen)] = token;
+    if (a.argmax_out) a.argmax_out[row] = amax;
+    if (S.overflow) sl.error |= 1;
+    sl.n_generated = n_gen + 1;
+    const int new_len = cur_len + 1;
+    sl.cur_len = new_len;
+    sl.last_token = token;
+    if (token == eos) { sl.active = 0; sl.finished = 1; }
+    else {
+      // python float64 arithmetic, then fp32 (models/t5gemma.py:1087-1094)
+      double p = (double)(new_len - 1) / (double)max(1, sl.est_total - 1) * (double)a.progress_scale;
+      p = fmin(p, (double)a.progress_scale);
+      sl.pos = (float)p;
+    }
+    if (a.host_mirror) {
+      volatile int* hm = a.host_mirror + row * 4;
+      hm[0] = sl.active; hm[1] = sl.finished; hm[2] = n_gen + 1; hm[3] = new_len;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st, bool pdl) {
+  if (a.V > MAX_CHUNKS * CHUNK) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(a.rows);
+  cfg.blockDim = dim3(SAMP_THREADS);
+  cfg.dynamicSmemBytes = sizeof(Shared);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, sampler_kernel, a);
+}

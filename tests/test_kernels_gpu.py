@@ -1,0 +1,43 @@
+"""Kernel-level numerics against plain torch fp32 references of the same op."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from tests.gpu_util import engine_for
+from t5gemma_tts_b200 import lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,N,K", [(1, 4096, 2304), (1, 2304, 9216), (2, 2304, 2048), (4, 1000, 2304), (3, 65, 64)])
+def test_gemv_vs_torch(B, N, K):
+    eng = engine_for("tinyA_eager")
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + N)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    x = torch.randn(B, K, device="cuda", generator=g)
+    out = torch.empty(B, N, device="cuda")
+    torch.cuda.synchronize()
+    L.check(eng.lib, eng.lib.t5g_debug_gemv(eng._h, C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()),
+                                            C.c_void_p(out.data_ptr()), B, N, K, None))
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double().t()
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err        # fp32 accumulation of exact bf16*fp32 products
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 256, 128), (152, 4096, 2304), (7, 100, 64), (300, 2304, 9216)])
+def test_gemm_simt_vs_torch(M, N, K):
+    eng = engine_for("tinyA_eager")
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    out = torch.empty(M, N, device="cuda")
+    torch.cuda.synchronize()
+    L.check(eng.lib, eng.lib.t5g_debug_gemm(eng._h, C.c_void_p(a.data_ptr()), C.c_void_p(w.data_ptr()),
+                                            C.c_void_p(out.data_ptr()), M, N, K, 0, None))
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().t()
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err

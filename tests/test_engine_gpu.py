@@ -1,7 +1,7 @@
 """GPU parity tests: the CUDA engine (through the C ABI) against the committed reference outputs
 (tests/golden) and the CPU oracle.  Tolerances:
   * vs the fp32 reference fixtures: max-abs-err / abs-max <= 2e-2 (north_star's bf16 tolerance)
-  * vs the oracle evaluated with bf16-rounded weights: <= 3e-3 (kernel logic; activations stay fp32 on the
+  * vs the oracle evaluated with bf16-rounded weights: <= 1.5e-2 (kernel logic; bf16 K/V cache and prefill GEMM inputs; activations stay fp32 on the
     decode path, bf16 on the prefill GEMM inputs)
   * greedy agreement, teacher-forced along the reference sequence: >= 99 % of steps
 """
@@ -19,7 +19,7 @@ CASES = [("tinyA_eager", "tinyA_eager_prompt"), ("tinyA_eager", "tinyA_eager_nop
          ("tinyA_sdpa", "tinyA_sdpa_prompt"), ("tinyA_sdpa", "tinyA_sdpa_noprompt"),
          ("tinyB_eager", "tinyB_eager_prompt")]
 TOL_REF = 2e-2
-TOL_BF16W = 3e-3
+TOL_BF16W = 1.5e-2
 
 
 def _request(c, **kw):
@@ -109,7 +109,7 @@ def test_inference_tts_errors():
     x = torch.randint(2, 500, (2, 5)).cuda()
     with pytest.raises(AssertionError):
         eng.inference_tts(x, torch.tensor([5, 5]), torch.zeros(2, 0, 1, dtype=torch.long), torch.tensor([10, 10]))
-    old = eng.args.n_codebooks
+    old = getattr(eng.args, "n_codebooks", 1)
     eng.args.n_codebooks = 2
     with pytest.raises(ValueError):
         eng.inference_tts(x[:1], torch.tensor([5]), torch.zeros(1, 0, 1, dtype=torch.long), torch.tensor([10]))

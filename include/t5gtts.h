@@ -171,6 +171,10 @@ const char* t5g_last_error(void);
 int t5g_abi_version(void);
 
 /* Kernel-level entry points used by tests/ and the roofline micro-benchmarks. */
+/* With T5G_TRACE=1 in the environment at t5g_create, every kernel of the decode step records
+ * (min over CTAs of the time after its dependency wait, max over CTAs of its exit time) in globaltimer ns;
+ * this returns the records of the last executed step in launch order. */
+int t5g_debug_trace(T5GEngine* eng, uint64_t* begin_ns, uint64_t* end_ns, int max_entries, int* n_out);
 int t5g_debug_gemm(T5GEngine* eng, const void* x_bf16 /* dev [M,K] */, const void* w_bf16 /* dev [N,K] */,
                    float* out /* dev [M,N] */, int M, int N, int K, int impl /* 0 = simt, 1 = tcgen05 */, void* stream);
 int t5g_debug_gemv(T5GEngine* eng, const float* x /* dev [B,K] */, const void* w_bf16 /* dev [N,K] */,

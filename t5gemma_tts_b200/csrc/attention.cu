@@ -9,11 +9,13 @@
 //     cross) over contiguous K/V.
 // The G = Hq/Hkv query heads of a KV group are processed together so K/V bytes are read once.
 #include "kernels.h"
+#include <cooperative_groups.h>
 
 namespace {
 
 template <int D> struct Geo {
-  static constexpr int LPT = (D / 8 < 8) ? D / 8 : 8;   // lanes per token
+  static constexpr int LPT = (D / 8 < 16) ? D / 8 : 16; // lanes per token (16 for D=256: 16 dims per lane keeps
+                                                        // the q/acc/k/v slices at ~100 registers)
   static constexpr int DPL = D / LPT;                   // dims per lane (multiple of 8)
   static constexpr int TPW = 32 / LPT;                  // tokens per warp iteration
   static constexpr int NV = DPL / 8;                    // 16-byte loads per lane per row
@@ -59,69 +61,99 @@ __device__ __forceinline__ void group_update(GroupState<G, Geo<D>::DPL>& st, con
   }
 }
 
-// merges the per-group states of a CTA through shared memory; result for (g,d): num/den relative to M
+// merges the TPW token groups of a warp with xor shuffles over the group-index bits of the lane id
 template <int G, int D>
-__device__ __forceinline__ void cta_merge(const GroupState<G, Geo<D>::DPL>& st, float* sm_o, float* sm_ml,
-                                          int lane, int warp) {
-  constexpr int LPT = Geo<D>::LPT, DPL = Geo<D>::DPL, TPW = Geo<D>::TPW;
-  const int grp = warp * TPW + lane / LPT, l8 = lane % LPT;
+__device__ __forceinline__ void warp_merge(GroupState<G, Geo<D>::DPL>& st) {
+  constexpr int LPT = Geo<D>::LPT, DPL = Geo<D>::DPL;
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
-    if (l8 == 0) { sm_ml[(grp * G + g) * 2] = st.m[g]; sm_ml[(grp * G + g) * 2 + 1] = st.l[g]; }
+  for (int o = LPT; o < 32; o <<= 1) {
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) sm_o[(size_t)(grp * G + g) * D + l8 * DPL + i] = st.acc[g][i];
+    for (int g = 0; g < G; ++g) {
+      const float mo = __shfl_xor_sync(0xffffffffu, st.m[g], o);
+      const float lo_ = __shfl_xor_sync(0xffffffffu, st.l[g], o);
+      const float mn = fmaxf(st.m[g], mo);
+      const float w0 = (st.m[g] == -INFINITY) ? 0.f : __expf(st.m[g] - mn);
+      const float w1 = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+      st.l[g] = st.l[g] * w0 + lo_ * w1;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) {
+        const float ao = __shfl_xor_sync(0xffffffffu, st.acc[g][i], o);
+        st.acc[g][i] = st.acc[g][i] * w0 + ao * w1;
+      }
+      st.m[g] = mn;
+    }
   }
 }
 
+constexpr int ATD_WARPS = 8;
+
+// grid (Hkv, NS, B), thread-block cluster (1, NS, 1): the NS split CTAs of one (request, kv head) exchange
+// their partial softmax states through distributed shared memory instead of a global round trip.
 template <int G, int D>
-__global__ void __launch_bounds__(ATT_WARPS * 32) attn_decode_kernel(AttnDecodeArgs a) {
+__global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeArgs a) {
   constexpr int LPT = Geo<D>::LPT, DPL = Geo<D>::DPL, TPW = Geo<D>::TPW, NV = Geo<D>::NV;
-  constexpr int NGRP = ATT_WARPS * TPW;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ float qs[G][D];
   __shared__ float cs[D / 2], sn[D / 2];
   __shared__ float knew[D], vnew[D];
-  __shared__ __align__(16) float sm_o[NGRP * G * D];
-  __shared__ float sm_ml[NGRP * G * 2];
+  __shared__ __align__(16) float w_o[ATD_WARPS][G][D];
+  __shared__ float w_ml[ATD_WARPS][G][2];
+  __shared__ __align__(16) float c_o[G][D];      // this CTA's partial, read by the cluster peers
+  __shared__ float c_ml[G][2];
 
   pdl_launch_dependents();
   pdl_wait();
+  trace_begin(a.trace);
   const int hk = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
+  const int NS = a.n_splits;
   const SlotDev& sl = a.slots[b];
-  if (!sl.active) return;
+  if (!sl.active) return;                          // uniform over the whole cluster (same b)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.is_cross ? sl.n_text : sl.cur_len;
   const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
-  int chunk = (L - lo + a.n_splits - 1) / a.n_splits;
+  int chunk = (L - lo + NS - 1) / NS;
   chunk = (chunk + TPW - 1) / TPW * TPW;
   const int t_begin = lo + split * chunk, t_end = min(L, t_begin + chunk);
   const int PT = a.pool.page_tokens;
   const int* bt = a.block_table + (size_t)b * a.bt_stride;
-
-  // RoPE tables for this request's position (fp32 angles from a FLOAT position, HF:150-161)
-  const float pos = sl.pos;
-  for (int i = tid; i < D / 2; i += blockDim.x) {
-    float s, c;
-    sincosf(pos * a.inv_freq[i], &s, &c);
-    cs[i] = c; sn[i] = s;
-  }
-  __syncthreads();
-  for (int i = tid; i < G * D / 2; i += blockDim.x) {
-    int g = i / (D / 2), j = i - g * (D / 2);
-    const float* qp = a.q + (size_t)b * a.q_stride + (size_t)(hk * G + g) * D;
-    float x1 = qp[j], x2 = qp[j + D / 2];
-    qs[g][j] = x1 * cs[j] - x2 * sn[j];
-    qs[g][j + D / 2] = x2 * cs[j] + x1 * sn[j];
-  }
   const bool has_new = (!a.is_cross) && (t_end == L) && (t_end > t_begin);
+
+  // RoPE table of this request's position (fp32 angles from a FLOAT position, HF:150-161)
+  if (a.rope_cs) {
+    for (int i = tid; i < D / 2; i += blockDim.x) { cs[i] = a.rope_cs[(size_t)b * D + i]; sn[i] = a.rope_cs[(size_t)b * D + D / 2 + i]; }
+  } else {
+    const float pos = sl.pos;
+    for (int i = tid; i < D / 2; i += blockDim.x) {
+      float s, c;
+      sincosf(pos * a.inv_freq[i], &s, &c);
+      cs[i] = c; sn[i] = s;
+    }
+  }
+  // raw q (and the new k/v) are fetched in the same round trip as the table
+  for (int i = tid; i < G * D; i += blockDim.x) {
+    const int g = i / D, j = i - g * D;
+    qs[g][j] = a.q[(size_t)b * a.q_stride + (size_t)(hk * G + g) * D + j];
+  }
   if (has_new) {
     const float* kp = a.kv_new + (size_t)b * a.kv_stride + (size_t)hk * D;
     const float* vp = kp + (size_t)a.Hkv * D;
+    for (int j = tid; j < D; j += blockDim.x) { knew[j] = kp[j]; vnew[j] = __bfloat162float(__float2bfloat16(vp[j])); }
+  }
+  __syncthreads();
+  // rotate in place: element pairs (j, j+D/2)
+  for (int i = tid; i < G * D / 2; i += blockDim.x) {
+    const int g = i / (D / 2), j = i - g * (D / 2);
+    const float x1 = qs[g][j], x2 = qs[g][j + D / 2];
+    qs[g][j] = x1 * cs[j] - x2 * sn[j];
+    qs[g][j + D / 2] = x2 * cs[j] + x1 * sn[j];
+  }
+  if (has_new) {
     for (int j = tid; j < D / 2; j += blockDim.x) {
-      float x1 = kp[j], x2 = kp[j + D / 2];
+      const float x1 = knew[j], x2 = knew[j + D / 2];
       knew[j] = __bfloat162float(__float2bfloat16(x1 * cs[j] - x2 * sn[j]));
       knew[j + D / 2] = __bfloat162float(__float2bfloat16(x2 * cs[j] + x1 * sn[j]));
     }
-    for (int j = tid; j < D; j += blockDim.x) vnew[j] = __bfloat162float(__float2bfloat16(vp[j]));
   }
   __syncthreads();
   if (has_new) {   // append to the page (K post-RoPE), visible to later steps
@@ -140,7 +172,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_decode_kernel(AttnDecodeA
 
   GroupState<G, DPL> st;
   st.init();
-  for (int t0 = t_begin + warp * TPW; t0 < t_end; t0 += ATT_WARPS * TPW) {
+  for (int t0 = t_begin + warp * TPW; t0 < t_end; t0 += ATD_WARPS * TPW) {
     const int t = t0 + grp;
     const bool valid = t < t_end;
     float kf[DPL], vf[DPL];
@@ -165,30 +197,55 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_decode_kernel(AttnDecodeA
     // all lanes execute the shuffles; invalid groups contribute nothing
     group_update<G, D>(st, qreg, kf, vf, a.scale, a.softcap, valid);
   }
-  cta_merge<G, D>(st, sm_o, sm_ml, lane, warp);
+  warp_merge<G, D>(st);
+  if (grp == 0) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (l8 == 0) { w_ml[warp][g][0] = st.m[g]; w_ml[warp][g][1] = st.l[g]; }
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) w_o[warp][g][l8 * DPL + i] = st.acc[g][i];
+    }
+  }
   __syncthreads();
-  const int NS = a.n_splits;
+  // CTA-level merge of the warps -> c_o / c_ml (unnormalised, relative to the CTA max)
   for (int i = tid; i < G * D; i += blockDim.x) {
     const int g = i / D, d = i - g * D;
     float M = -INFINITY;
-    for (int r = 0; r < NGRP; ++r) M = fmaxf(M, sm_ml[(r * G + g) * 2]);
+#pragma unroll
+    for (int w = 0; w < ATD_WARPS; ++w) M = fmaxf(M, w_ml[w][g][0]);
     float num = 0.f, den = 0.f;
     if (M > -INFINITY) {
-      for (int r = 0; r < NGRP; ++r) {
-        float m = sm_ml[(r * G + g) * 2];
-        if (m == -INFINITY) continue;
-        float w = __expf(m - M);
-        num = fmaf(w, sm_o[(size_t)(r * G + g) * D + d], num);
-        den = fmaf(w, sm_ml[(r * G + g) * 2 + 1], den);
+#pragma unroll
+      for (int w = 0; w < ATD_WARPS; ++w) {
+        const float m = w_ml[w][g][0];
+        const float wt = (m == -INFINITY) ? 0.f : __expf(m - M);
+        num = fmaf(wt, w_o[w][g][d], num);
+        den = fmaf(wt, w_ml[w][g][1], den);
       }
     }
-    const int head = hk * G + g;
-    a.part_o[((size_t)(b * a.Hq + head) * NS + split) * D + d] = num;
-    if (d == 0) {
-      float* ml = a.part_ml + ((size_t)(b * a.Hq + head) * NS + split) * 2;
-      ml[0] = M; ml[1] = den;
-    }
+    c_o[g][d] = num;
+    if (d == 0) { c_ml[g][0] = M; c_ml[g][1] = den; }
   }
+  cluster.sync();
+  // ---- distributed final merge over the cluster: rank `split` finalises dims [split*D/NS, (split+1)*D/NS) ----
+  const int dslice = D / NS;
+  for (int i = tid; i < G * dslice; i += blockDim.x) {
+    const int g = i / dslice, d = split * dslice + (i - g * dslice);
+    float M = -INFINITY;
+    for (int r = 0; r < NS; ++r) M = fmaxf(M, cluster.map_shared_rank(&c_ml[0][0], r)[g * 2]);
+    float num = 0.f, den = 0.f;
+    for (int r = 0; r < NS; ++r) {
+      const float* rml = cluster.map_shared_rank(&c_ml[0][0], r);
+      const float m = rml[g * 2];
+      if (m == -INFINITY) continue;
+      const float wt = __expf(m - M);
+      num = fmaf(wt, cluster.map_shared_rank(&c_o[0][0], r)[g * D + d], num);
+      den = fmaf(wt, rml[g * 2 + 1], den);
+    }
+    a.out[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = den > 0.f ? num / den : 0.f;
+  }
+  cluster.sync();                                  // peers may still be reading this CTA's shared memory
+  trace_end(a.trace);
 }
 
 // ---- prefill: one warp per (query token, kv head) ----------------------------------------------
@@ -233,25 +290,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_prefill_kernel(AttnPrefil
     }
     group_update<G, D>(st, qreg, kf, vf, a.scale, a.softcap, valid);
   }
-  // merge the TPW groups of this warp with xor shuffles over the group index bits
-#pragma unroll
-  for (int o = LPT; o < 32; o <<= 1) {
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float mo = __shfl_xor_sync(0xffffffffu, st.m[g], o);
-      float lo_ = __shfl_xor_sync(0xffffffffu, st.l[g], o);
-      float mn = fmaxf(st.m[g], mo);
-      float w0 = (st.m[g] == -INFINITY) ? 0.f : __expf(st.m[g] - mn);
-      float w1 = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
-      st.l[g] = st.l[g] * w0 + lo_ * w1;
-#pragma unroll
-      for (int i = 0; i < DPL; ++i) {
-        float ao = __shfl_xor_sync(0xffffffffu, st.acc[g][i], o);
-        st.acc[g][i] = st.acc[g][i] * w0 + ao * w1;
-      }
-      st.m[g] = mn;
-    }
-  }
+  warp_merge<G, D>(st);
   if (grp == 0) {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -267,14 +306,16 @@ template <int G, int D>
 cudaError_t launch_decode_gd(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.Hkv, a.n_splits, a.B);
-  cfg.blockDim = dim3(ATT_WARPS * 32);
+  cfg.blockDim = dim3(ATD_WARPS * 32);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = a.n_splits; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D>, a);
 }
 
@@ -305,6 +346,7 @@ cudaError_t launch_prefill_gd(const AttnPrefillArgs& a, cudaStream_t st) {
 
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   const int G = a.Hq / a.Hkv;
+  if (a.n_splits < 1 || a.n_splits > 8 || (a.n_splits & (a.n_splits - 1)) || a.D % a.n_splits) return cudaErrorInvalidValue;
   DISPATCH_GD(G, a.D, launch_decode_gd, a, st, pdl);
   return cudaErrorInvalidValue;
 }

@@ -56,6 +56,17 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+// block-wide sum of four values at once (one barrier pair)
+__device__ __forceinline__ void block_sum4(float& a, float& b, float& c, float& d, float* red /* >= 128 floats */) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) { red[w] = a; red[32 + w] = b; red[64 + w] = c; red[96 + w] = d; }
+  __syncthreads();
+  a = warp_sum(lane < nw ? red[lane] : 0.f); b = warp_sum(lane < nw ? red[32 + lane] : 0.f);
+  c = warp_sum(lane < nw ? red[64 + lane] : 0.f); d = warp_sum(lane < nw ? red[96 + lane] : 0.f);
+}
+
 // 8 bf16 packed in a uint4 -> 8 floats (bf16 -> fp32 is a 16-bit shift)
 __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
   f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
@@ -64,12 +75,33 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
   f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 
-// streaming 128-bit weight load: read-only path, do not allocate in L1
-__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+// streaming 128-bit weight load: read-only path, no L1 allocation, L2 evict-first (the 4.85 GB/step weight
+// stream must not evict the KV pages and activations that the rest of the step re-reads from L2)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream(const void* p, uint64_t pol) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
   return r;
+}
+
+#define T5G_TRACE_STRIDE 1024
+// optional in-step tracing (T5G_TRACE=1): per kernel, min over CTAs of the time after griddepcontrol.wait and
+// max over CTAs of the exit time, in %globaltimer nanoseconds
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_begin(unsigned long long* tr) {
+  if (tr && threadIdx.x == 0) atomicMin(tr, globaltimer_ns());
+}
+__device__ __forceinline__ void trace_end(unsigned long long* tr) {
+  if (tr && threadIdx.x == 0) atomicMax(tr + T5G_TRACE_STRIDE, globaltimer_ns());
 }
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {

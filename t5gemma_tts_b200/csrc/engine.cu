@@ -82,8 +82,10 @@ struct T5GEngine {
   uint64_t prefill_counter = 0;
   // decode workspaces (B = max_slots)
   float *d_hA = nullptr, *d_hB = nullptr, *d_y = nullptr, *d_qkv = nullptr, *d_qc = nullptr, *d_act = nullptr,
-        *d_t1 = nullptr, *d_logits = nullptr, *d_part_o = nullptr, *d_part_ml = nullptr;
+        *d_t1 = nullptr, *d_logits = nullptr, *d_rope = nullptr;
   float* d_sample_u = nullptr; SlotDev* d_sample_slots = nullptr;   // t5g_sample scratch
+  float* d_attn = nullptr;                                          // attention output [B,QD]
+  unsigned long long* d_trace = nullptr; bool use_trace = false;    // [2][T5G_TRACE_STRIDE] begin/end timestamps
   int ns_self = 8, ns_cross = 2;
   int h_end = 0;                                               // which h buffer holds the residual at step end
   cudaGraphExec_t step_graph = nullptr; cudaStream_t graph_built_for = nullptr; int nodes_per_step = 0;
@@ -219,6 +221,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_PDL")) e->use_pdl = atoi(s) != 0;
   if (const char* s = getenv("T5G_GRAPH")) e->use_graph = atoi(s) != 0;
   if (const char* s = getenv("T5G_GEMM")) e->gemm_impl = atoi(s);
+  if (const char* s = getenv("T5G_TRACE")) e->use_trace = atoi(s) != 0;
   *out = e;   // so that the caller can destroy on failure
   T5G_CUDA(cudaStreamCreateWithFlags(&e->load_stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev) T5G_CUDA(cudaEventCreate(&ev));
@@ -290,14 +293,18 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
 
   // ---- decode workspaces ----
   e->h_end = (cfg->n_dec_layers - 1) & 1;
-  e->ns_self = std::max(1, std::min(16, (2 * e->num_sms) / (e->Hkv * B)));
-  e->ns_cross = std::max(1, std::min(4, e->num_sms / (e->Hkv * B)));
-  const int NS = std::max(e->ns_self, e->ns_cross);
+  {
+    int want = (2 * e->num_sms) / (e->Hkv * B);
+    e->ns_self = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
+    while (D % e->ns_self) e->ns_self >>= 1;
+    e->ns_cross = std::min(2, e->ns_self);
+  }
   DM(e->d_hA, (size_t)B * d); DM(e->d_hB, (size_t)B * d); DM(e->d_y, (size_t)B * d); DM(e->d_qkv, (size_t)B * QKV);
   DM(e->d_qc, (size_t)B * QD); DM(e->d_act, (size_t)B * I); DM(e->d_t1, (size_t)B * d); DM(e->d_logits, (size_t)B * e->Vpad);
-  DM(e->d_part_o, (size_t)B * e->Hq * NS * D); DM(e->d_part_ml, (size_t)B * e->Hq * NS * 2);
+  DM(e->d_rope, (size_t)B * D);
   T5G_CUDA(cudaMemset(e->d_y, 0, sizeof(float) * (size_t)B * d));
   DM(e->d_sample_u, 4096); DM(e->d_sample_slots, 4096);
+  DM(e->d_attn, (size_t)B * QD); DM(e->d_trace, 2 * T5G_TRACE_STRIDE);
   T5G_CUDA(cudaDeviceSynchronize());
   return T5G_OK;
 }
@@ -612,6 +619,11 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
   const bool pdl = e->use_pdl;
   int nl = 0;
   float* hbuf[2] = {e->d_hA, e->d_hB};
+  int kidx = 0;                                   // kernel sequence number inside the step (tracing)
+  auto next_trace = [&]() -> unsigned long long* {
+    if (!e->use_trace || kidx >= T5G_TRACE_STRIDE) return nullptr;
+    return e->d_trace + (kidx++);
+  };
   // batch rows are processed in groups of <= 4 by the GEMV family
   auto gemv_all = [&](GemvArgs a, int P, int E, size_t in_stride, size_t out_stride) -> cudaError_t {
     for (int b0 = 0; b0 < B; b0 += 4) {
@@ -621,15 +633,19 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
       if (g.h_in) g.h_in += (size_t)b0 * d;
       if (g.y) g.y += (size_t)b0 * d;
       if (g.h_out) g.h_out += (size_t)b0 * d;
-      if (g.part_o) { g.part_o += (size_t)b0 * e->Hq * g.n_splits * D; g.part_ml += (size_t)b0 * e->Hq * g.n_splits * 2; }
       g.out += (size_t)b0 * out_stride;
+      g.trace = next_trace();
       cudaError_t er = launch_gemv(g, P, E, e->num_sms, st, pdl);
       if (er != cudaSuccess) return er;
       nl++;
     }
     return cudaSuccess;
   };
-  GemvArgs z{}; z.eps = c.rms_eps; z.slots = e->d_slots; z.head_dim = D;
+  GemvArgs z{}; z.eps = c.rms_eps; z.slots = e->d_slots;
+  if (e->use_trace) {
+    CU(cudaMemsetAsync(e->d_trace, 0xFF, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
+    CU(cudaMemsetAsync(e->d_trace + T5G_TRACE_STRIDE, 0, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
+  }
 
   const DecLayer& Llast = e->dec[c.n_dec_layers - 1];
   // ---- head: t1 = gelu(W1 * final_norm(h + post_ff(y)) + b1) ; logits = W2 t1 + b2 ----
@@ -642,7 +658,8 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
   { SamplerArgs s{}; s.logits = e->d_logits; s.ld = e->Vpad; s.V = e->V; s.slots = e->d_slots; s.topk_sched_pool = e->d_topk_pool;
     s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
     s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = B; s.host_mirror = e->d_mirror;
-    s.picks_out = e->d_picks; s.forced_pool = e->d_forced;
+    s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
+    s.trace = next_trace();
     CU(launch_sampler(s, st, pdl)); nl++; }
   // ---- 26 decoder layers at q_len = 1 ----
   int t = 0;   // hbuf[t] holds the current residual
@@ -653,21 +670,21 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
       else { a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = e->dec[l - 1].g_post_ff; a.h_out = hbuf[t ^ 1]; t ^= 1; CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QKV)); } }
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
-      a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq;
-      a.part_o = e->d_part_o; a.part_ml = e->d_part_ml;
+      a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
+      a.out = e->d_attn; a.trace = next_trace();
       CU(launch_attn_decode(a, st, pdl)); nl++; }
-    { GemvArgs a = z; a.W = L.wo; a.N = d; a.K = QD; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml; a.n_splits = e->ns_self; a.out = e->d_y; a.out_stride = d;
-      CU(gemv_all(a, P_COMBINE, E_STORE, 0, d)); }
+    { GemvArgs a = z; a.W = L.wo; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
+      CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
     { GemvArgs a = z; a.W = L.wq_c; a.N = QD; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_sa; a.g_pre = L.g_pre_ca; a.h_out = hbuf[t ^ 1]; t ^= 1;
       a.out = e->d_qc; a.out_stride = QD;
       CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QD)); }
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
-      a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq;
-      a.part_o = e->d_part_o; a.part_ml = e->d_part_ml;
+      a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
+      a.out = e->d_attn; a.trace = next_trace();
       CU(launch_attn_decode(a, st, pdl)); nl++; }
-    { GemvArgs a = z; a.W = L.wo_c; a.N = d; a.K = QD; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml; a.n_splits = e->ns_cross; a.out = e->d_y; a.out_stride = d;
-      CU(gemv_all(a, P_COMBINE, E_STORE, 0, d)); }
+    { GemvArgs a = z; a.W = L.wo_c; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
+      CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
     { GemvArgs a = z; a.W = L.wgu; a.N = 2 * I; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_ca; a.g_pre = L.g_pre_ff; a.h_out = hbuf[t ^ 1]; t ^= 1;
       a.out = e->d_act; a.out_stride = I;
       CU(gemv_all(a, P_RES_NORM, E_GEGLU, 0, I)); }
@@ -864,6 +881,18 @@ extern "C" int t5g_get_timings(T5GEngine* e, float* out) {
   return T5G_OK;
 }
 
+extern "C" int t5g_debug_trace(T5GEngine* e, uint64_t* begin_ns, uint64_t* end_ns, int max_entries, int* n_out) {
+  T5G_CHECK(e && begin_ns && end_ns && n_out, T5G_ERR_INVALID, "bad arguments");
+  T5G_CHECK(e->use_trace, T5G_ERR_STATE, "tracing is off (set T5G_TRACE=1 before creating the engine)");
+  T5G_CUDA(cudaSetDevice(e->device));
+  CU(cudaDeviceSynchronize());
+  const int n = std::min(std::min(max_entries, e->nodes_per_step > 0 ? e->nodes_per_step : T5G_TRACE_STRIDE), T5G_TRACE_STRIDE);
+  CU(cudaMemcpy(begin_ns, e->d_trace, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(end_ns, e->d_trace + T5G_TRACE_STRIDE, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+  *n_out = n;
+  return T5G_OK;
+}
+
 extern "C" int t5g_debug_gemm(T5GEngine* e, const void* x, const void* w, float* out, int M, int N, int K, int impl, void* stream_) {
   T5G_CHECK(e && x && w && out, T5G_ERR_INVALID, "bad arguments");
   T5G_CUDA(cudaSetDevice(e->device));
@@ -878,6 +907,6 @@ extern "C" int t5g_debug_gemv(T5GEngine* e, const float* x, const void* w, float
   T5G_CUDA(cudaSetDevice(e->device));
   GemvArgs a{}; a.W = (const bf16*)w; a.N = N; a.K = K; a.B = B; a.x = x; a.out = out; a.out_stride = N; a.slots = nullptr;
   e->launches++;
-  CU(launch_gemv(a, P_PLAIN, E_STORE, e->num_sms, (cudaStream_t)stream_, false));
+  CU(launch_gemv(a, P_PLAIN, E_STORE, e->num_sms, (cudaStream_t)stream_, e->use_pdl));
   return T5G_OK;
 }

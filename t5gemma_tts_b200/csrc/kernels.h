@@ -3,7 +3,7 @@
 #include "common.cuh"
 
 // ---------------- GEMV family (gemv.cu) ----------------
-enum { P_PLAIN = 0, P_NORM = 1, P_RES_NORM = 2, P_EMBED_NORM = 3, P_COMBINE = 4 };
+enum { P_PLAIN = 0, P_NORM = 1, P_RES_NORM = 2, P_EMBED_NORM = 3 };
 enum { E_STORE = 0, E_GEGLU = 1, E_BIAS_GELU = 2, E_BIAS = 3 };
 
 struct GemvArgs {
@@ -16,11 +16,11 @@ struct GemvArgs {
   const float* g_pre;                // (1+w) pre-norm gain
   float* h_out;                      // updated residual (written by CTA 0), may be null
   const bf16* emb; float emb_scale;  // P_EMBED_NORM: audio embedding table, sqrt(hidden)
-  const float* part_o; const float* part_ml; int n_splits; int head_dim;   // P_COMBINE
   float eps;
   const float* bias;
   float* out; int out_stride;
   const SlotDev* slots; int slot0;   // optional activity gating / last_token source
+  unsigned long long* trace;         // optional [2]: begin/end timestamps
 };
 cudaError_t launch_gemv(const GemvArgs& a, int P, int E, int num_sms, cudaStream_t st, bool pdl);
 
@@ -41,11 +41,13 @@ struct AttnDecodeArgs {
   const float* kv_new; int kv_stride;      // self: raw k at kv_new[b*kv_stride + 0..KD), v at +KD ; null for cross
   const SlotDev* slots;
   int B, Hq, Hkv, D;
-  int n_splits;
+  int n_splits;                            // split-KV CTAs per (request, kv head) = cluster size (1,2,4,8)
   int is_cross;                            // 1: length = n_text, no causal/window, no append
   int window;                              // >0: sliding window (self only)
   float scale, softcap; const float* inv_freq;   // inv_freq [D/2] fp32 (HF:143-145), host-computed
-  float* part_o; float* part_ml;           // [B,Hq,NS,D], [B,Hq,NS,2]
+  const float* rope_cs;                    // optional [B][D]: cos[D/2] | sin[D/2] of the row's position (written by the sampler)
+  float* out;                              // [B, Hq*D] final (normalised) attention output
+  unsigned long long* trace;
 };
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
 
@@ -101,6 +103,8 @@ struct SamplerArgs {
   int* tokens_out; int tokens_stride; // [slot][tokens_stride], entry n_generated (flat_tokens: entry 0)
   int flat_tokens;
   int* host_mirror;                   // optional mapped-host [rows][4]: active, finished, n_generated, cur_len
+  float* rope_out; const float* inv_freq; int head_dim;   // optional: cos|sin table of the new position per row
+  unsigned long long* trace;
   int* argmax_out;                    // optional [rows]
   int* picks_out;                     // optional [slot][tokens_stride]: engine's own sampled id per step
   const int* forced_pool;             // optional [slot][tokens_stride]: teacher-forced ids

@@ -44,7 +44,13 @@ __device__ __forceinline__ float val_of(unsigned key) {
   return __uint_as_float(u);
 }
 
+constexpr int HI_CAP = 73728;        // vocabularies up to this size use the shared-memory fast path
+
 struct Shared {
+  unsigned short hi16[HI_CAP];       // top 16 bits of every order-preserving key (one global pass)
+  unsigned tmax[SAMP_THREADS];       // per-thread maxima (lower-bound selection for 32 < k <= 1024)
+  unsigned redk[32];
+  unsigned lb; int n_surv;
   unsigned hist[256];
   unsigned long long cand[CAND_CAP];
   float e[CAND_CAP];
@@ -59,6 +65,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
   Shared& S = *reinterpret_cast<Shared*>(smraw);
   pdl_launch_dependents();
   pdl_wait();
+  trace_begin(a.trace);
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   SlotDev& sl = a.slots[row];
   if (!sl.active) return;
@@ -75,11 +82,34 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
   }
   __syncthreads();
 
-  // (2) argmax of the adjusted logits (first index on ties)
+  // (2) one pipelined global pass: argmax of the adjusted logits (first index on ties), and -- for the
+  //     top-k fast path -- the top 16 bits of every key into shared memory + per-thread max key
+  const float T = sl.temperature;
+  const bool scaled = (T != 1.0f);
+  auto zof = [&](int i) -> float { float v = lg[i]; return scaled ? __fdiv_rn(v, T) : v; };
+  const bool use_hi = V <= HI_CAP;
   float bv = -INFINITY; int bi = 0x7fffffff;
-  for (int i = tid; i < V; i += SAMP_THREADS) {
-    float v = lg[i];
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  unsigned mk = 0u;
+  for (int i0 = tid; i0 < V; i0 += SAMP_THREADS * 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int i = i0 + j * SAMP_THREADS; v[j] = (i < V) ? lg[i] : -INFINITY; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + j * SAMP_THREADS;
+      if (i < V) {
+        if (v[j] > bv || (v[j] == bv && i < bi)) { bv = v[j]; bi = i; }
+        const unsigned key = key_of(scaled ? __fdiv_rn(v[j], T) : v[j]);
+        mk = max(mk, key);
+        if (use_hi) S.hi16[i] = (unsigned short)(key >> 16);
+      }
+    }
+  }
+  S.tmax[tid] = mk;
+  {
+    unsigned wk = mk;
+    for (int o = 16; o > 0; o >>= 1) wk = max(wk, __shfl_xor_sync(0xffffffffu, wk, o));
+    if (lane == 0) S.redk[warp] = wk;
   }
   for (int o = 16; o > 0; o >>= 1) {
     float ov = __shfl_xor_sync(0xffffffffu, bv, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
@@ -96,9 +126,6 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
     if (lane == 0) { S.amax = bi; S.zmax = bv; }
   }
   __syncthreads();
-  const float T = sl.temperature;
-  const bool scaled = (T != 1.0f);
-  auto zof = [&](int i) -> float { float v = lg[i]; return scaled ? __fdiv_rn(v, T) : v; };
   const float zmax = scaled ? __fdiv_rn(S.zmax, T) : S.zmax;
 
   int top_k = sl.top_k;
@@ -136,7 +163,84 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
     if (S.n_cand > 0) { filtered = true; top_k = 0; top_p = 1.0f; }
   }
 
-  // (4) top-k: exact k-th largest by MSB-first radix select, ties kept (models/utils.py:82-86)
+  // (4) top-k, ties kept (models/utils.py:82-86).
+  // Fast path: a lower bound LB on the k-th largest key is the k-th largest of 32 warp maxima (k <= 32) or
+  // of the 1024 thread maxima; every element whose top-16 key bits reach LB's is a candidate (a superset
+  // of the top-k and of all ties at the k-th value).  Candidates are re-read exactly, sorted (value desc,
+  // index asc) and cut at the k-th value.  Falls back to the exact radix select if the superset overflows.
+  bool fast_done = false;
+  if (!filtered && top_k > 0 && use_hi) {
+    const int k = min(max(top_k, 1), V);
+    if (k <= 32) {
+      if (warp == 0) {
+        unsigned x = S.redk[lane];
+        // bitonic sort of 32 keys across the warp, descending
+        for (int size = 2; size <= 32; size <<= 1)
+          for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned y = __shfl_xor_sync(0xffffffffu, x, stride);
+            const bool up = ((lane & size) == 0);              // this block sorts descending
+            const bool lower = ((lane & stride) == 0);
+            const unsigned mx = max(x, y), mn = min(x, y);
+            x = (up == lower) ? mx : mn;
+          }
+        if (lane == k - 1) S.lb = x;
+      }
+    } else {
+      for (int size = 2; size <= SAMP_THREADS; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          __syncthreads();
+          const int j = tid ^ stride;
+          if (j > tid) {
+            const bool desc = ((tid & size) == 0);
+            const unsigned x = S.tmax[tid], y = S.tmax[j];
+            if ((x < y) == desc) { S.tmax[tid] = y; S.tmax[j] = x; }
+          }
+        }
+      __syncthreads();
+      if (tid == 0) S.lb = S.tmax[k - 1];
+    }
+    __syncthreads();
+    const unsigned short thr16 = (unsigned short)(S.lb >> 16);
+    for (int i = tid; i < V; i += SAMP_THREADS) {
+      if (S.hi16[i] >= thr16) {
+        const unsigned slot = atomicAdd(&S.n_cand, 1u);
+        if (slot < CAND_CAP) S.cand[slot] = ((unsigned long long)key_of(zof(i)) << 32) | (0xffffffffu - (unsigned)i);
+        else S.overflow = 1;
+      }
+    }
+    __syncthreads();
+    if (!S.overflow) {
+      const int n = (int)S.n_cand;
+      int np2 = 1; while (np2 < n) np2 <<= 1;
+      for (int i = n + tid; i < np2; i += SAMP_THREADS) S.cand[i] = 0ull;
+      __syncthreads();
+      for (int size = 2; size <= np2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int i = tid; i < np2; i += SAMP_THREADS) {
+            const int j = i ^ stride;
+            if (j > i) {
+              const bool desc = ((i & size) == 0);
+              unsigned long long x = S.cand[i], y = S.cand[j];
+              if ((x < y) == desc) { S.cand[i] = y; S.cand[j] = x; }
+            }
+          }
+          __syncthreads();
+        }
+      const unsigned thr_key = (unsigned)(S.cand[k - 1] >> 32);
+      for (int i = tid; i < n; i += SAMP_THREADS) {
+        const bool in = (unsigned)(S.cand[i] >> 32) >= thr_key;
+        const bool next_in = (i + 1 < n) && ((unsigned)(S.cand[i + 1] >> 32) >= thr_key);
+        if (in && !next_in) S.n_surv = i + 1;
+      }
+      __syncthreads();
+      fast_done = true;
+      filtered = true;
+    } else {
+      __syncthreads();
+      if (tid == 0) { S.n_cand = 0; S.overflow = 0; }
+      __syncthreads();
+    }
+  }
   if (!filtered && top_k > 0) {
     int k = min(max(top_k, 1), V);
     unsigned prefix = 0, mask = 0;
@@ -182,21 +286,26 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
   int token = 0;
   if (filtered) {
     // sort survivors (value desc, index asc): bitonic on the 64-bit composite, descending
-    const int n = min((int)S.n_cand, CAND_CAP);
-    int np2 = 1; while (np2 < n) np2 <<= 1;
-    for (int i = n + tid; i < np2; i += SAMP_THREADS) S.cand[i] = 0ull;
-    __syncthreads();
-    for (int size = 2; size <= np2; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i = tid; i < np2; i += SAMP_THREADS) {
-          const int j = i ^ stride;
-          if (j > i) {
-            const bool desc = ((i & size) == 0);
-            unsigned long long x = S.cand[i], y = S.cand[j];
-            if ((x < y) == desc) { S.cand[i] = y; S.cand[j] = x; }
+    int n;
+    if (fast_done) {
+      n = S.n_surv;
+    } else {
+      n = min((int)S.n_cand, CAND_CAP);
+      int np2 = 1; while (np2 < n) np2 <<= 1;
+      for (int i = n + tid; i < np2; i += SAMP_THREADS) S.cand[i] = 0ull;
+      __syncthreads();
+      for (int size = 2; size <= np2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+          for (int i = tid; i < np2; i += SAMP_THREADS) {
+            const int j = i ^ stride;
+            if (j > i) {
+              const bool desc = ((i & size) == 0);
+              unsigned long long x = S.cand[i], y = S.cand[j];
+              if ((x < y) == desc) { S.cand[i] = y; S.cand[j] = x; }
+            }
           }
+          __syncthreads();
         }
-        __syncthreads();
       }
     }
     const float z0 = val_of((unsigned)(S.cand[0] >> 32));
@@ -290,7 +399,21 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
       volatile int* hm = a.host_mirror + row * 4;
       hm[0] = sl.active; hm[1] = sl.finished; hm[2] = n_gen + 1; hm[3] = new_len;
     }
+    S.total = sl.pos;
   }
+  if (a.rope_out) {
+    // cos/sin of the new token's PM-RoPE angle, once per step instead of once per attention kernel
+    __syncthreads();
+    const float pos = S.total;
+    const int half = a.head_dim / 2;
+    for (int i = tid; i < half; i += SAMP_THREADS) {
+      float sn, cs;
+      sincosf(pos * a.inv_freq[i], &sn, &cs);
+      a.rope_out[(size_t)row * a.head_dim + i] = cs;
+      a.rope_out[(size_t)row * a.head_dim + half + i] = sn;
+    }
+  }
+  trace_end(a.trace);
 }
 
 }  // namespace

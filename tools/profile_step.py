@@ -1,0 +1,51 @@
+"""Short driver for ncu: 2b-2b random-init engine, one prefill, then a few decode steps (bs=1, config[1] shape)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import engine_config, make_inputs  # noqa: E402
+from t5gemma_tts_b200 import T5GemmaVoiceEngine, GenerationRequest  # noqa: E402
+from t5gemma_tts_b200.random_init import iter_random_state_dict  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=6)
+ap.add_argument("--ctx", type=int, default=150)
+a = ap.parse_args()
+cfg = engine_config()
+eng = T5GemmaVoiceEngine(cfg)
+eng.load_state_dict(iter_random_state_dict(cfg, seed=0, device="cuda"))
+x, xl, y, tgt = make_inputs(1234, cfg)
+rq = GenerationRequest(text_ids=x[0].numpy(), prompt_ids=y[0, : a.ctx + 1, 0].numpy(), target_total=int(tgt[0]),
+                       prompt_frames=a.ctx + 1, top_k=30, top_p=0.9, temperature=0.8)
+eng.prefill([rq], [0])
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+eng.decode(a.steps)
+eng.poll()
+e0.record()
+eng.decode(a.steps)
+e1.record()
+eng.poll()
+print("ms/step", e0.elapsed_time(e1) / a.steps, "launches", eng.launch_count())
+if os.environ.get("T5G_TRACE") == "1":
+    import ctypes as C
+    import numpy as np
+    from t5gemma_tts_b200 import lib as L
+    eng.decode(1); eng.poll()
+    b = np.zeros(1024, dtype=np.uint64); e_ = np.zeros(1024, dtype=np.uint64); n = C.c_int(0)
+    L.check(eng.lib, eng.lib.t5g_debug_trace(eng._h, b.ctypes.data_as(C.POINTER(C.c_uint64)), e_.ctypes.data_as(C.POINTER(C.c_uint64)), 1024, C.byref(n)))
+    n = n.value
+    b, e_ = b[:n].astype(np.int64), e_[:n].astype(np.int64)
+    t0 = b[0]
+    names = ["head1", "head2", "sampler"] + ["qkv", "sattn", "o", "qc", "cattn", "oc", "gu", "down"] * 26
+    print("step span us", (e_.max() - t0) / 1000.0)
+    agg = {}
+    for i in range(n):
+        nm = names[i] if i < len(names) else str(i)
+        dur = (e_[i] - b[i]) / 1000.0                     # post-wait body duration
+        gap = (b[i] - e_[i - 1]) / 1000.0 if i else 0.0   # previous kernel's exit -> this kernel past its wait
+        a = agg.setdefault(nm, [0, 0.0, 0.0]); a[0] += 1; a[1] += dur; a[2] += gap
+    for nm, (c, d, g) in agg.items():
+        print(f"{nm:8s} n={c:3d} body avg {d/c:7.2f} us   gap avg {g/c:6.2f} us   total {(d+g):8.1f} us")

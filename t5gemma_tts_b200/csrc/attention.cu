@@ -102,6 +102,11 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   __shared__ __align__(16) float c_o[G][D];      // this CTA's partial, read by the cluster peers
   __shared__ float c_ml[G][2];
 
+  {
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, n = gridDim.x * gridDim.y * gridDim.z;
+    l2_prefetch_range(a.pf[0], cta, n);
+    l2_prefetch_range(a.pf[1], cta, n);
+  }
   pdl_launch_dependents();
   pdl_wait();
   trace_begin(a.trace);

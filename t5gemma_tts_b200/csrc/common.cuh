@@ -90,6 +90,18 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p, uint64_t pol) {
 }
 
 #define T5G_TRACE_STRIDE 1024
+// Asynchronous L2 prefetch of an upcoming kernel's weight range (prefetch.global.L2 per line): issued by the
+// kernels of the decode step in their pre-dependency section so that HBM keeps streaming weights into the
+// 126 MB L2 while latency-bound kernels (attention, small projections) leave it idle.
+struct PrefetchRange { const void* ptr; unsigned long long bytes; };
+__device__ __forceinline__ void l2_prefetch_range(const PrefetchRange& r, int cta, int n_ctas) {
+  if (!r.ptr || r.bytes == 0) return;
+  const unsigned long long n = (r.bytes + 127) / 128;            // one prefetch per 128-byte line
+  for (unsigned long long i = (unsigned long long)cta * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)n_ctas * blockDim.x)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)r.ptr + i * 128) : "memory");
+}
+
 // optional in-step tracing (T5G_TRACE=1): per kernel, min over CTAs of the time after griddepcontrol.wait and
 // max over CTAs of the exit time, in %globaltimer nanoseconds
 __device__ __forceinline__ unsigned long long globaltimer_ns() {

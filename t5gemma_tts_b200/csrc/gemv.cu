@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(GV_THREADS, (NB == 1) ? 2 : 1) gemv_kernel(Gem
       }
     }
   }
+  l2_prefetch_range(a.pf[0], blockIdx.x, gridDim.x);
+  l2_prefetch_range(a.pf[1], blockIdx.x, gridDim.x);
   // RMSNorm gains are weights: fetch them before the dependency resolves as well
   float gpre[NP], gpost[NP];
   if (P == P_NORM || P == P_RES_NORM || P == P_EMBED_NORM) {

@@ -21,6 +21,7 @@ struct GemvArgs {
   float* out; int out_stride;
   const SlotDev* slots; int slot0;   // optional activity gating / last_token source
   unsigned long long* trace;         // optional [2]: begin/end timestamps
+  PrefetchRange pf[2];               // upcoming weights to pull into L2 (see l2_prefetch_range)
 };
 cudaError_t launch_gemv(const GemvArgs& a, int P, int E, int num_sms, cudaStream_t st, bool pdl);
 
@@ -47,6 +48,7 @@ struct AttnDecodeArgs {
   float scale, softcap; const float* inv_freq;   // inv_freq [D/2] fp32 (HF:143-145), host-computed
   const float* rope_cs;                    // optional [B][D]: cos[D/2] | sin[D/2] of the row's position (written by the sampler)
   float* out;                              // [B, Hq*D] final (normalised) attention output
+  PrefetchRange pf[2];
   unsigned long long* trace;
 };
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
@@ -105,6 +107,7 @@ struct SamplerArgs {
   int* host_mirror;                   // optional mapped-host [rows][4]: active, finished, n_generated, cur_len
   float* rope_out; const float* inv_freq; int head_dim;   // optional: cos|sin table of the new position per row
   unsigned long long* trace;
+  PrefetchRange pf[4];
   int* argmax_out;                    // optional [rows]
   int* picks_out;                     // optional [slot][tokens_stride]: engine's own sampled id per step
   const int* forced_pool;             // optional [slot][tokens_stride]: teacher-forced ids

@@ -63,6 +63,7 @@ struct Shared {
 __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   Shared& S = *reinterpret_cast<Shared*>(smraw);
+  for (int i = 0; i < 4; ++i) l2_prefetch_range(a.pf[i], blockIdx.x, gridDim.x);
   pdl_launch_dependents();
   pdl_wait();
   trace_begin(a.trace);

@@ -247,7 +247,9 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
       num = fmaf(wt, cluster.map_shared_rank(&c_o[0][0], r)[g * D + d], num);
       den = fmaf(wt, rml[g * 2 + 1], den);
     }
-    a.out[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = den > 0.f ? num / den : 0.f;
+    const float o = den > 0.f ? num / den : 0.f;
+    if (a.out) a.out[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = o;
+    if (a.out_bf) a.out_bf[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = __float2bfloat16(o);
   }
   cluster.sync();                                  // peers may still be reading this CTA's shared memory
   trace_end(a.trace);

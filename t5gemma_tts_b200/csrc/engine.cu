@@ -48,7 +48,7 @@ struct T5GEngine {
   int d, I, Hq, Hkv, D, QD, KD, QKV, V, Vpad, PT;
   int max_self_pages, max_cross_pages, n_pages;
   bool use_pdl = true, use_graph = true, use_l2pf = false;   // L2 weight prefetch: measured net-negative (profiles/), opt-in
-  int gemm_impl = 0;                       // 0 simt, 1 tcgen05
+  int gemm_impl = 1;                       // 1 tcgen05/TMEM/TMA (default), 0 = SIMT cross-check kernel
   cudaStream_t load_stream = nullptr;
   std::vector<void*> allocs;               // every cudaMalloc of this engine
   size_t bytes_allocated = 0;
@@ -85,6 +85,7 @@ struct T5GEngine {
         *d_t1 = nullptr, *d_logits = nullptr, *d_rope = nullptr;
   float* d_sample_u = nullptr; SlotDev* d_sample_slots = nullptr;   // t5g_sample scratch
   float* d_attn = nullptr;                                          // attention output [B,QD]
+  bf16 *d_xn = nullptr, *d_attn_bf = nullptr, *d_act_bf = nullptr, *d_t1_bf = nullptr;   // batched (tensor-core) decode step
   unsigned long long* d_trace = nullptr; bool use_trace = false;    // [2][T5G_TRACE_STRIDE] begin/end timestamps
   int ns_self = 8, ns_cross = 2;
   int h_end = 0;                                               // which h buffer holds the residual at step end
@@ -186,7 +187,7 @@ cudaError_t gemm(T5GEngine* e, const bf16* A, const bf16* W, int M, int N, int K
                  void* out, int ldo, cudaStream_t st) {
   GemmArgs g{A, W, M, N, K, epi, bias, out, ldo};
   e->launches++;
-  if (e->gemm_impl == 1) return launch_gemm_tc(g, st);
+  if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms);
   return launch_gemm_simt(g, st);
 }
 
@@ -304,8 +305,11 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   DM(e->d_qc, (size_t)B * QD); DM(e->d_act, (size_t)B * I); DM(e->d_t1, (size_t)B * d); DM(e->d_logits, (size_t)B * e->Vpad);
   DM(e->d_rope, (size_t)B * D);
   T5G_CUDA(cudaMemset(e->d_y, 0, sizeof(float) * (size_t)B * d));
+  T5G_CUDA(cudaMemset(e->d_hA, 0, sizeof(float) * (size_t)B * d));
+  T5G_CUDA(cudaMemset(e->d_hB, 0, sizeof(float) * (size_t)B * d));
   DM(e->d_sample_u, 4096); DM(e->d_sample_slots, 4096);
   DM(e->d_attn, (size_t)B * QD); DM(e->d_trace, 2 * T5G_TRACE_STRIDE);
+  DM(e->d_xn, (size_t)B * d); DM(e->d_attn_bf, (size_t)B * QD); DM(e->d_act_bf, (size_t)B * I); DM(e->d_t1_bf, (size_t)B * d);
   T5G_CUDA(cudaDeviceSynchronize());
   return T5G_OK;
 }
@@ -595,7 +599,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   // hand the last token of every request to the decode buffers: h_end buffer <- h, y <- 0
   {
     for (int r = 0; r < n_req; ++r) {
-      float* hdst = (e->h_end == 0 ? e->d_hA : e->d_hB) + (size_t)reqs[r].slot * d;
+      float* hdst = ((e->c.max_slots > 4 || e->h_end == 0) ? e->d_hA : e->d_hB) + (size_t)reqs[r].slot * d;
       CU(cudaMemcpyAsync(hdst, e->p_h + (size_t)h_last[r] * d, sizeof(float) * d, cudaMemcpyDeviceToDevice, st));
       CU(cudaMemsetAsync(e->d_y + (size_t)reqs[r].slot * d, 0, sizeof(float) * d, st));
     }
@@ -710,6 +714,60 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
   return T5G_OK;
 }
 
+
+// Batched decode step (B > 4 rows): the projections become skinny tensor-core GEMMs with M = B (weights are
+// streamed once for the whole batch); attention and sampling are the same kernels as the bs=1 path.
+int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
+  const T5GConfig& c = e->c;
+  const int d = e->d, I = e->I, QD = e->QD, QKV = e->QKV, D = e->D;
+  const int B = c.max_slots;
+  int nl = 0;
+  auto G = [&](const bf16* A, const bf16* W, int N, int K, int epi, const float* bias, void* out, int ldo) -> cudaError_t {
+    GemmArgs g{A, W, B, N, K, epi, bias, out, ldo};
+    nl += 2;                                           // kernel (+ memset when split-K)
+    if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms);
+    return launch_gemm_simt(g, st);
+  };
+  float* h = e->d_hA;
+  const DecLayer& Llast = e->dec[c.n_dec_layers - 1];
+  // head: h += post_ff(y) ; xn = final_norm(h)
+  CU(launch_norm(h, e->d_y, Llast.g_post_ff, e->g_dec_final, h, e->d_xn, nullptr, B, d, c.rms_eps, st)); nl++;
+  CU(G(e->d_xn, e->head_w1, d, d, GE_BIAS_GELU_BF16, e->head_b1, e->d_t1_bf, d));
+  CU(G(e->d_t1_bf, e->head_w2, e->Vpad, d, GE_BIAS_F32, e->head_b2, e->d_logits, e->Vpad));
+  { SamplerArgs s{}; s.logits = e->d_logits; s.ld = e->Vpad; s.V = e->V; s.slots = e->d_slots; s.topk_sched_pool = e->d_topk_pool;
+    s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
+    s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = B; s.host_mirror = e->d_mirror;
+    s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
+    CU(launch_sampler(s, st, false)); nl++; }
+  CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st)); nl++;
+  for (int l = 0; l < c.n_dec_layers; ++l) {
+    const DecLayer& L = e->dec[l];
+    if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st));
+    else CU(launch_norm(h, e->d_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, h, e->d_xn, nullptr, B, d, c.rms_eps, st));
+    nl++;
+    CU(G(e->d_xn, L.wqkv, QKV, d, GE_F32, nullptr, e->d_qkv, QKV));
+    { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
+      a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
+      a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
+      a.out = nullptr; a.out_bf = e->d_attn_bf;
+      CU(launch_attn_decode(a, st, false)); nl++; }
+    CU(G(e->d_attn_bf, L.wo, d, QD, GE_F32, nullptr, e->d_y, d));
+    CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st)); nl++;
+    CU(G(e->d_xn, L.wq_c, QD, d, GE_F32, nullptr, e->d_qc, QD));
+    { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
+      a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
+      a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
+      a.out = nullptr; a.out_bf = e->d_attn_bf;
+      CU(launch_attn_decode(a, st, false)); nl++; }
+    CU(G(e->d_attn_bf, L.wo_c, d, QD, GE_F32, nullptr, e->d_y, d));
+    CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st)); nl++;
+    CU(G(e->d_xn, L.wgu, 2 * I, d, GE_GEGLU_BF16, nullptr, e->d_act_bf, I));
+    CU(G(e->d_act_bf, L.wd, d, I, GE_F32, nullptr, e->d_y, d));
+  }
+  *n_launch = nl;
+  return T5G_OK;
+}
+
 }  // namespace
 
 extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
@@ -726,7 +784,7 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
       int nl = 0;
       cudaGraph_t g = nullptr;
       CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
-      int rc = enqueue_step(e, cs, &nl);
+      int rc = (e->c.max_slots > 4) ? enqueue_step_batched(e, cs, &nl) : enqueue_step(e, cs, &nl);
       cudaError_t er = cudaStreamEndCapture(cs, &g);
       if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cs); return rc; }
       CU(er);
@@ -738,7 +796,12 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
     for (int i = 0; i < max_steps; ++i) CU(cudaGraphLaunch(e->step_graph, st));
     e->launches += (int64_t)e->nodes_per_step * max_steps;
   } else {
-    for (int i = 0; i < max_steps; ++i) { int nl = 0; int rc = enqueue_step(e, st, &nl); if (rc) return rc; e->launches += nl; }
+    for (int i = 0; i < max_steps; ++i) {
+      int nl = 0;
+      int rc = (e->c.max_slots > 4) ? enqueue_step_batched(e, st, &nl) : enqueue_step(e, st, &nl);
+      if (rc) return rc;
+      e->launches += nl;
+    }
   }
   CU(cudaEventRecord(e->ev[4], st));
   return T5G_OK;
@@ -912,7 +975,7 @@ extern "C" int t5g_debug_gemm(T5GEngine* e, const void* x, const void* w, float*
   T5G_CUDA(cudaSetDevice(e->device));
   GemmArgs g{(const bf16*)x, (const bf16*)w, M, N, K, GE_F32, nullptr, out, N};
   e->launches++;
-  CU(impl == 1 ? launch_gemm_tc(g, (cudaStream_t)stream_) : launch_gemm_simt(g, (cudaStream_t)stream_));
+  CU(impl == 1 ? launch_gemm_tc(g, (cudaStream_t)stream_, e->num_sms) : launch_gemm_simt(g, (cudaStream_t)stream_));
   return T5G_OK;
 }
 

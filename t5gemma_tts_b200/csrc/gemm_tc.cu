@@ -1,3 +1,274 @@
-// tcgen05 / TMEM / TMA GEMM (placeholder until the kernel lands; never silently falls back).
+// Dense projections on the 5th-generation tensor cores: C[M,N] = A[M,K] * W[N,K]^T, bf16 in, fp32 accumulate.
+// Used for the encoder/decoder prefill GEMMs (M = packed tokens) and for batched decode (M = batch rows).
+//
+// Formulation ("swap-AB"): the WEIGHT tile is the tcgen05 A operand (UMMA M = 128 output features = the 128
+// TMEM lanes) and the ACTIVATION tile is the B operand (UMMA N = 16..256 tokens = TMEM columns), so one
+// kernel covers 8-row batched decode up to 8192-token prefill without padding the token dimension to 128.
+// Both operands are K-major in global memory exactly as stored ([N,K] weights, [M,K] activations): TMA
+// (cp.async.bulk.tensor.2d, 128-byte swizzle) stages 64-element K-slabs through an mbarrier ring, one elected
+// thread issues tcgen05.mma (kind::f16, fp32 accumulators in TMEM), tcgen05.commit releases ring slots and
+// signals the epilogue warps, which read the accumulators with tcgen05.ld (32 lanes x 32 bit, 16 columns per
+// instruction) and apply the fused epilogue (bias / exact GELU / GeGLU / bf16 cast).  When the output grid is
+// smaller than the machine (weight-streaming regime) K is split across CTAs and fp32 partials are reduced with
+// red.global.add.f32 into a zeroed output.
 #include "kernels.h"
-cudaError_t launch_gemm_tc(const GemmArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+
+#include <cuda.h>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace {
+
+constexpr int TC_BM = 128;          // output features per tile (UMMA M)
+constexpr int TC_BK = 64;           // K elements per stage (one 128-byte swizzle atom of bf16)
+constexpr int TC_THREADS = 192;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "LAB_DONE:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO=1 [16,30), SBO = 1024 B >> 4 [32,46), version 1 [46,48), layout SWIZZLE_128B = 2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcParams {
+  int M, N, K;
+  int epilogue; const float* bias;
+  void* out; int ldo;
+  int k_blocks_per_split;     // K-slabs handled by one CTA (blockIdx.z selects the split)
+  int split_k;
+};
+
+template <int TOKT, int NSTAGE>
+struct __align__(1024) TcSmem {
+  unsigned char w[NSTAGE][TC_BM * 128];       // weight tiles: 128 rows x 128 B (swizzled by TMA)
+  unsigned char x[NSTAGE][TOKT * 128];        // activation tiles: TOKT rows x 128 B
+  uint64_t full[NSTAGE], empty[NSTAGE], acc_full;
+  uint32_t tmem_base;
+};
+
+template <int TOKT, int NSTAGE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  // dynamic shared memory is only guaranteed 16-byte aligned: realign to the 1024 B the swizzle atom needs
+  TcSmem<TOKT, NSTAGE>& S = *reinterpret_cast<TcSmem<TOKT, NSTAGE>*>(
+      (reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+  constexpr int TMEM_COLS = TOKT < 32 ? 32 : TOKT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f0 = blockIdx.x * TC_BM, t0 = blockIdx.y * TOKT;
+  const int kb_total = p.K / TC_BK;
+  const int kb0 = blockIdx.z * p.k_blocks_per_split;
+  const int nkb = min(p.k_blocks_per_split, kb_total - kb0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
+    mbar_init(&S.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = S.tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      constexpr uint32_t STAGE_BYTES = TC_BM * 128 + TOKT * 128;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % NSTAGE;
+        if (i >= NSTAGE) mbar_wait(&S.empty[s], ((i / NSTAGE) - 1) & 1);
+        mbar_expect_tx(&S.full[s], STAGE_BYTES);
+        const int kc = (kb0 + i) * TC_BK;
+        tma_load_2d(S.w[s], &map_w, kc, f0, &S.full[s]);
+        tma_load_2d(S.x[s], &map_x, kc, t0, &S.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TOKT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % NSTAGE;
+        mbar_wait(&S.full[s], (i / NSTAGE) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t wa = smem_u32(S.w[s]), xa = smem_u32(S.x[s]);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {       // UMMA K = 16 bf16 = 32 bytes inside the swizzle atom
+          const uint64_t da = umma_desc_sw128(wa + k * 32), db = umma_desc_sw128(xa + k * 32);
+          umma_bf16(tmem_d, da, db, idesc, (i | k) ? 1u : 0u);
+        }
+        umma_commit(&S.empty[s]);                     // frees the slot once these MMAs have read it
+      }
+      umma_commit(&S.acc_full);                       // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> global =====
+    const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    const int f = f0 + q * 32 + lane;                 // output feature of this thread
+    if (nkb > 0) {
+      mbar_wait(&S.acc_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < TOKT; c += 16) {
+        if (t0 + c >= p.M) break;                     // warp-uniform
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int t = t0 + c + j;
+          float val = v[j];
+          if (p.epilogue == GE_GEGLU_BF16) {
+            const float other = __shfl_xor_sync(0xffffffffu, val, 1);       // up value lives in the odd lane
+            if (t < p.M && f < p.N && !(lane & 1))
+              reinterpret_cast<bf16*>(p.out)[(size_t)t * p.ldo + (f >> 1)] = __float2bfloat16(gelu_tanh_f(val) * other);
+            continue;
+          }
+          if (t >= p.M || f >= p.N) continue;
+          if (p.split_k > 1) { atomicAdd(reinterpret_cast<float*>(p.out) + (size_t)t * p.ldo + f, val); continue; }
+          switch (p.epilogue) {
+            case GE_F32: reinterpret_cast<float*>(p.out)[(size_t)t * p.ldo + f] = val; break;
+            case GE_BF16: reinterpret_cast<bf16*>(p.out)[(size_t)t * p.ldo + f] = __float2bfloat16(val); break;
+            case GE_BIAS_F32: reinterpret_cast<float*>(p.out)[(size_t)t * p.ldo + f] = val + bias; break;
+            case GE_BIAS_GELU_BF16:
+              reinterpret_cast<bf16*>(p.out)[(size_t)t * p.ldo + f] = __float2bfloat16(gelu_erf_f(val + bias)); break;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side: tensor maps -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+bool make_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int TOKT, int NSTAGE>
+cudaError_t launch_tc(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<TOKT, NSTAGE>;
+  const size_t smem = sizeof(TcSmem<TOKT, NSTAGE>) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, TC_THREADS, smem, st>>>(mw, mx, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmArgs& a) {
+  return a.K % TC_BK == 0 && a.K >= TC_BK && a.M >= 1 && a.N >= 1 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a.W) & 15) == 0 && (a.epilogue != GE_GEGLU_BF16 || a.N % 2 == 0);
+}
+
+cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms) {
+  if (a.M <= 0) return cudaSuccess;
+  if (!gemm_tc_supported(a)) return cudaErrorNotSupported;
+  const int tokt = a.M <= 16 ? 16 : a.M <= 32 ? 32 : a.M <= 64 ? 64 : a.M <= 128 ? 128 : 256;
+  CUtensorMap mw, mx;
+  if (!make_map(&mw, a.W, a.N, a.K, TC_BM) || !make_map(&mx, a.A, a.M, a.K, tokt)) return cudaErrorNotSupported;
+  const int kb_total = a.K / TC_BK;
+  const int tiles = ((a.N + TC_BM - 1) / TC_BM) * ((a.M + tokt - 1) / tokt);
+  int split = 1;
+  if (a.epilogue == GE_F32 && tiles < num_sms) {          // weight-streaming regime: fill the machine along K
+    split = num_sms / tiles;
+    split = std::min(split, std::max(1, kb_total / 4));
+    split = std::max(split, 1);
+  }
+  const int kbps = (kb_total + split - 1) / split;
+  split = (kb_total + kbps - 1) / kbps;
+  TcParams p{a.M, a.N, a.K, a.epilogue, a.bias, a.out, a.ldo, kbps, split};
+  if (split > 1) {
+    cudaError_t e = cudaMemsetAsync(a.out, 0, sizeof(float) * ((size_t)(a.M - 1) * a.ldo + a.N), st);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((a.N + TC_BM - 1) / TC_BM, (a.M + tokt - 1) / tokt, split);
+  switch (tokt) {
+    case 16: return launch_tc<16, 8>(mw, mx, p, grid, st);
+    case 32: return launch_tc<32, 8>(mw, mx, p, grid, st);
+    case 64: return launch_tc<64, 6>(mw, mx, p, grid, st);
+    case 128: return launch_tc<128, 5>(mw, mx, p, grid, st);
+    default: return launch_tc<256, 4>(mw, mx, p, grid, st);
+  }
+}

@@ -47,7 +47,8 @@ struct AttnDecodeArgs {
   int window;                              // >0: sliding window (self only)
   float scale, softcap; const float* inv_freq;   // inv_freq [D/2] fp32 (HF:143-145), host-computed
   const float* rope_cs;                    // optional [B][D]: cos[D/2] | sin[D/2] of the row's position (written by the sampler)
-  float* out;                              // [B, Hq*D] final (normalised) attention output
+  float* out;                              // [B, Hq*D] final (normalised) attention output (fp32), or
+  bf16* out_bf;                            // bf16 copy for the tensor-core o_proj of the batched path (either may be null)
   PrefetchRange pf[2];
   unsigned long long* trace;
 };
@@ -86,7 +87,10 @@ struct GemmArgs {
   void* out; int ldo;     // GE_GEGLU: N counts interleaved rows, out is [M, N/2]
 };
 cudaError_t launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
-cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st);   // tcgen05/TMEM/TMA path (gemm_tc.cu)
+cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms);   // tcgen05/TMEM/TMA path (gemm_tc.cu)
+bool gemm_tc_supported(const GemmArgs& a);
+// h[b] = table[slots[b].last_token] * scale for every row (batched decode step)
+cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float scale, float* h, int B, int d, cudaStream_t st);
 cudaError_t launch_gather_rows(const float* src, const int* rows, float* dst, int n, int d, cudaStream_t st);
 cudaError_t launch_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st);
 

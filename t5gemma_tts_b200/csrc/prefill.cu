@@ -11,6 +11,14 @@ __global__ void embed_kernel(const bf16* __restrict__ table, const int* __restri
   for (int k = threadIdx.x; k < d; k += blockDim.x) h[(size_t)t * d + k] = __bfloat162float(row[k]) * scale;
 }
 
+__global__ void embed_slots_kernel(const bf16* __restrict__ table, const SlotDev* __restrict__ slots, float scale,
+                                   float* __restrict__ h, int d) {
+  const int b = blockIdx.x;
+  if (!slots[b].active) return;
+  const bf16* row = table + (size_t)slots[b].last_token * d;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) h[(size_t)b * d + k] = __bfloat162float(row[k]) * scale;
+}
+
 // one CTA per token: h_out = h_in + rmsnorm(y)*g_post ; xn/xf = rmsnorm(h_out)*g_pre  (HF:66-74 in fp32)
 __global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ h_in, const float* __restrict__ y,
                                                    const float* __restrict__ g_post, const float* __restrict__ g_pre,
@@ -186,6 +194,12 @@ __global__ void pack_kernel(const void* __restrict__ src, int src_dtype, void* _
 cudaError_t launch_embed(const bf16* table, const int* ids, float scale, float* h, int M, int d, cudaStream_t st) {
   if (M <= 0) return cudaSuccess;
   embed_kernel<<<M, 256, 0, st>>>(table, ids, scale, h, M, d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float scale, float* h, int B, int d, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  embed_slots_kernel<<<B, 256, 0, st>>>(table, slots, scale, h, d);
   return cudaGetLastError();
 }
 

@@ -41,3 +41,21 @@ def test_gemm_simt_vs_torch(M, N, K):
     ref = a.double() @ w.double().t()
     err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 128, 64), (5, 100, 128), (64, 2304, 2304), (64, 18432, 2304), (152, 4096, 2304),
+                                   (1000, 2304, 9216), (33, 65664, 256)])
+def test_gemm_tcgen05_vs_torch(M, N, K):
+    """tcgen05/TMEM/TMA GEMM (incl. TMA out-of-bounds tiles and the split-K reduction) vs torch."""
+    eng = engine_for("tinyA_eager")
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    torch.cuda.synchronize()
+    L.check(eng.lib, eng.lib.t5g_debug_gemm(eng._h, C.c_void_p(a.data_ptr()), C.c_void_p(w.data_ptr()),
+                                            C.c_void_p(out.data_ptr()), M, N, K, 1, None))
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().t()
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err

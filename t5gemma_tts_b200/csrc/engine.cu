@@ -725,7 +725,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
   auto G = [&](const bf16* A, const bf16* W, int N, int K, int epi, const float* bias, void* out, int ldo) -> cudaError_t {
     GemmArgs g{A, W, B, N, K, epi, bias, out, ldo};
     nl += 2;                                           // kernel (+ memset when split-K)
-    if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms);
+    if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms, false);
     return launch_gemm_simt(g, st);
   };
   float* h = e->d_hA;

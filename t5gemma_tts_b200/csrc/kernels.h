@@ -87,7 +87,7 @@ struct GemmArgs {
   void* out; int ldo;     // GE_GEGLU: N counts interleaved rows, out is [M, N/2]
 };
 cudaError_t launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
-cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms);   // tcgen05/TMEM/TMA path (gemm_tc.cu)
+cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool pdl = false);   // tcgen05/TMEM/TMA path (gemm_tc.cu)
 bool gemm_tc_supported(const GemmArgs& a);
 // h[b] = table[slots[b].last_token] * scale for every row (batched decode step)
 cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float scale, float* h, int B, int d, cudaStream_t st);

@@ -41,6 +41,7 @@ __device__ __forceinline__ void group_update(GroupState<G, Geo<D>::DPL>& st, con
                                              const float* kf, const float* vf, float scale, float softcap,
                                              bool valid) {
   constexpr int LPT = Geo<D>::LPT, DPL = Geo<D>::DPL;
+  const float inv_softcap = softcap > 0.f ? 1.f / softcap : 0.f;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     float dot = 0.f;
@@ -49,7 +50,10 @@ __device__ __forceinline__ void group_update(GroupState<G, Geo<D>::DPL>& st, con
 #pragma unroll
     for (int o = LPT >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
     float s = dot * scale;
-    if (softcap > 0.f) s = softcap * tanhf(s / softcap);
+    if (softcap > 0.f) {                     // softcap*tanh(s/softcap), tanh(x) = 1 - 2/(exp(2x)+1)
+      const float e2 = __expf(2.f * s * inv_softcap);
+      s = softcap * (1.f - __fdividef(2.f, e2 + 1.f));
+    }
     if (!valid) s = -INFINITY;
     const float mn = fmaxf(st.m[g], s);
     const float corr = (st.m[g] == -INFINITY) ? 0.f : __expf(st.m[g] - mn);
@@ -86,9 +90,13 @@ __device__ __forceinline__ void warp_merge(GroupState<G, Geo<D>::DPL>& st) {
 }
 
 constexpr int ATD_WARPS = 8;
+constexpr int ATD_MAX_NS = 8;
+constexpr int ATD_BT_CACHE = 256;      // block-table entries staged in shared memory (covers 4096 tokens at 16/page)
 
 // grid (Hkv, NS, B), thread-block cluster (1, NS, 1): the NS split CTAs of one (request, kv head) exchange
-// their partial softmax states through distributed shared memory instead of a global round trip.
+// their partial softmax states through distributed shared memory instead of a global round trip: every CTA
+// PUSHES the slice of its partial that rank r will finalise into rank r's receive buffer, one cluster barrier,
+// then every rank merges locally.
 template <int G, int D>
 __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeArgs a) {
   constexpr int LPT = Geo<D>::LPT, DPL = Geo<D>::DPL, TPW = Geo<D>::TPW, NV = Geo<D>::NV;
@@ -97,10 +105,12 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   __shared__ float qs[G][D];
   __shared__ float cs[D / 2], sn[D / 2];
   __shared__ float knew[D], vnew[D];
+  __shared__ int bt_s[ATD_BT_CACHE];
   __shared__ __align__(16) float w_o[ATD_WARPS][G][D];
   __shared__ float w_ml[ATD_WARPS][G][2];
-  __shared__ __align__(16) float c_o[G][D];      // this CTA's partial, read by the cluster peers
-  __shared__ float c_ml[G][2];
+  __shared__ __align__(16) float recv_o[ATD_MAX_NS][G][D / 1];   // [src rank][g][dslice] (only D/NS used per rank)
+  __shared__ float recv_ml[ATD_MAX_NS][G][2];
+  __shared__ float w_wt[ATD_WARPS][G], c_ml[G][2], f_wt[ATD_MAX_NS][G];
 
   {
     const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, n = gridDim.x * gridDim.y * gridDim.z;
@@ -112,39 +122,41 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   trace_begin(a.trace);
   const int hk = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
   const int NS = a.n_splits;
-  const SlotDev& sl = a.slots[b];
-  if (!sl.active) return;                          // uniform over the whole cluster (same b)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = a.is_cross ? sl.n_text : sl.cur_len;
-  const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
-  int chunk = (L - lo + NS - 1) / NS;
-  chunk = (chunk + TPW - 1) / TPW * TPW;
-  const int t_begin = lo + split * chunk, t_end = min(L, t_begin + chunk);
   const int PT = a.pool.page_tokens;
   const int* bt = a.block_table + (size_t)b * a.bt_stride;
-  const bool has_new = (!a.is_cross) && (t_end == L) && (t_end > t_begin);
-
-  // RoPE table of this request's position (fp32 angles from a FLOAT position, HF:150-161)
+  // ---- one round trip: slot state, RoPE table, raw q, new k/v and the block-table row are all independent ----
+  const SlotDev& sl = a.slots[b];
+  const int active = sl.active;
+  const int L = a.is_cross ? sl.n_text : sl.cur_len;
+  const float pos = sl.pos;
   if (a.rope_cs) {
     for (int i = tid; i < D / 2; i += blockDim.x) { cs[i] = a.rope_cs[(size_t)b * D + i]; sn[i] = a.rope_cs[(size_t)b * D + D / 2 + i]; }
-  } else {
-    const float pos = sl.pos;
+  }
+  for (int i = tid; i < G * D; i += blockDim.x) {
+    const int g = i / D, j = i - g * D;
+    qs[g][j] = a.q[(size_t)b * a.q_stride + (size_t)(hk * G + g) * D + j];
+  }
+  if (!a.is_cross) {
+    const float* kp = a.kv_new + (size_t)b * a.kv_stride + (size_t)hk * D;
+    const float* vp = kp + (size_t)a.Hkv * D;
+    for (int j = tid; j < D; j += blockDim.x) { knew[j] = kp[j]; vnew[j] = __bfloat162float(__float2bfloat16(vp[j])); }
+  }
+  for (int i = tid; i < ATD_BT_CACHE && i < a.bt_stride; i += blockDim.x) bt_s[i] = bt[i];
+  if (!active) return;                             // uniform over the whole cluster (same b)
+  cluster.barrier_arrive();                        // "this CTA is running": waited on before the first remote store
+  if (!a.rope_cs) {
     for (int i = tid; i < D / 2; i += blockDim.x) {
       float s, c;
       sincosf(pos * a.inv_freq[i], &s, &c);
       cs[i] = c; sn[i] = s;
     }
   }
-  // raw q (and the new k/v) are fetched in the same round trip as the table
-  for (int i = tid; i < G * D; i += blockDim.x) {
-    const int g = i / D, j = i - g * D;
-    qs[g][j] = a.q[(size_t)b * a.q_stride + (size_t)(hk * G + g) * D + j];
-  }
-  if (has_new) {
-    const float* kp = a.kv_new + (size_t)b * a.kv_stride + (size_t)hk * D;
-    const float* vp = kp + (size_t)a.Hkv * D;
-    for (int j = tid; j < D; j += blockDim.x) { knew[j] = kp[j]; vnew[j] = __bfloat162float(__float2bfloat16(vp[j])); }
-  }
+  const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
+  int chunk = (L - lo + NS - 1) / NS;
+  chunk = (chunk + TPW - 1) / TPW * TPW;
+  const int t_begin = lo + split * chunk, t_end = min(L, t_begin + chunk);
+  const bool has_new = (!a.is_cross) && (t_end == L) && (t_end > t_begin);
   __syncthreads();
   // rotate in place: element pairs (j, j+D/2)
   for (int i = tid; i < G * D / 2; i += blockDim.x) {
@@ -161,8 +173,9 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
     }
   }
   __syncthreads();
+  auto page_of = [&](int t) -> int { const int pi = t / PT; return pi < ATD_BT_CACHE ? bt_s[pi] : bt[pi]; };
   if (has_new) {   // append to the page (K post-RoPE), visible to later steps
-    const int t = L - 1, page = bt[t / PT], off = t % PT;
+    const int t = L - 1, page = page_of(t), off = t % PT;
     bf16* kd = a.pool.ptr(a.layer, 0, page) + ((size_t)hk * PT + off) * D;
     bf16* vd = a.pool.ptr(a.layer, 1, page) + ((size_t)hk * PT + off) * D;
     for (int j = tid; j < D; j += blockDim.x) { kd[j] = __float2bfloat16(knew[j]); vd[j] = __float2bfloat16(vnew[j]); }
@@ -177,30 +190,40 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
 
   GroupState<G, DPL> st;
   st.init();
-  for (int t0 = t_begin + warp * TPW; t0 < t_end; t0 += ATD_WARPS * TPW) {
-    const int t = t0 + grp;
-    const bool valid = t < t_end;
-    float kf[DPL], vf[DPL];
-    if (valid) {
-      if (has_new && t == L - 1) {
+  // two token groups per iteration: both K/V row loads are in flight before either is consumed
+  for (int t0 = t_begin + warp * TPW; t0 < t_end; t0 += 2 * ATD_WARPS * TPW) {
+    uint4 ku[2][NV], vu[2][NV];
+    bool valid[2], fresh[2];
 #pragma unroll
-        for (int i = 0; i < DPL; ++i) { kf[i] = knew[l8 * DPL + i]; vf[i] = vnew[l8 * DPL + i]; }
-      } else {
-        const int page = bt[t / PT], off = t % PT;
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * ATD_WARPS * TPW + grp;
+      valid[u] = t < t_end;
+      fresh[u] = valid[u] && has_new && t == L - 1;
+      if (valid[u] && !fresh[u]) {
+        const int page = page_of(t), off = t % PT;
         const bf16* kp = a.pool.ptr(a.layer, 0, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
         const bf16* vp = a.pool.ptr(a.layer, 1, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
-        uint4 ku[NV], vu[NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) { ku[i] = *reinterpret_cast<const uint4*>(kp + i * 8); vu[i] = *reinterpret_cast<const uint4*>(vp + i * 8); }
-#pragma unroll
-        for (int i = 0; i < NV; ++i) { bf16x8_to_f32(ku[i], kf + i * 8); bf16x8_to_f32(vu[i], vf + i * 8); }
+        for (int i = 0; i < NV; ++i) { ku[u][i] = *reinterpret_cast<const uint4*>(kp + i * 8); vu[u][i] = *reinterpret_cast<const uint4*>(vp + i * 8); }
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < DPL; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
     }
-    // all lanes execute the shuffles; invalid groups contribute nothing
-    group_update<G, D>(st, qreg, kf, vf, a.scale, a.softcap, valid);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (t0 + u * ATD_WARPS * TPW >= t_end) break;      // warp-uniform
+      float kf[DPL], vf[DPL];
+      if (fresh[u]) {
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) { kf[i] = knew[l8 * DPL + i]; vf[i] = vnew[l8 * DPL + i]; }
+      } else if (valid[u]) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { bf16x8_to_f32(ku[u][i], kf + i * 8); bf16x8_to_f32(vu[u][i], vf + i * 8); }
+      } else {
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
+      }
+      // all lanes execute the shuffles; invalid groups contribute nothing
+      group_update<G, D>(st, qreg, kf, vf, a.scale, a.softcap, valid[u]);
+    }
   }
   warp_merge<G, D>(st);
   if (grp == 0) {
@@ -212,46 +235,63 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
     }
   }
   __syncthreads();
-  // CTA-level merge of the warps -> c_o / c_ml (unnormalised, relative to the CTA max)
+  // CTA-level merge of the warps, pushed straight into the receive buffer of the rank that owns each dim slice.
+  // Per-warp merge weights are computed once (G*WARPS exps) instead of once per output element.
+  const int dslice = D / NS;
+  if (tid < G) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < ATD_WARPS; ++w) M = fmaxf(M, w_ml[w][tid][0]);
+    float den = 0.f;
+#pragma unroll
+    for (int w = 0; w < ATD_WARPS; ++w) {
+      const float m = w_ml[w][tid][0];
+      const float wt = (m == -INFINITY) ? 0.f : __expf(m - M);
+      den = fmaf(wt, w_ml[w][tid][1], den);
+      w_wt[w][tid] = wt;
+    }
+    c_ml[tid][0] = M; c_ml[tid][1] = den;
+  }
+  __syncthreads();
+  cluster.barrier_wait();                                // every peer has started: its shared memory may be written
   for (int i = tid; i < G * D; i += blockDim.x) {
     const int g = i / D, d = i - g * D;
-    float M = -INFINITY;
+    float num = 0.f;
 #pragma unroll
-    for (int w = 0; w < ATD_WARPS; ++w) M = fmaxf(M, w_ml[w][g][0]);
-    float num = 0.f, den = 0.f;
-    if (M > -INFINITY) {
-#pragma unroll
-      for (int w = 0; w < ATD_WARPS; ++w) {
-        const float m = w_ml[w][g][0];
-        const float wt = (m == -INFINITY) ? 0.f : __expf(m - M);
-        num = fmaf(wt, w_o[w][g][d], num);
-        den = fmaf(wt, w_ml[w][g][1], den);
-      }
-    }
-    c_o[g][d] = num;
-    if (d == 0) { c_ml[g][0] = M; c_ml[g][1] = den; }
+    for (int w = 0; w < ATD_WARPS; ++w) num = fmaf(w_wt[w][g], w_o[w][g][d], num);
+    const int dst = d / dslice;                          // rank that finalises this dim
+    float* ro = cluster.map_shared_rank(&recv_o[0][0][0], dst);
+    ro[((size_t)split * G + g) * D + (d - dst * dslice)] = num;
   }
-  cluster.sync();
-  // ---- distributed final merge over the cluster: rank `split` finalises dims [split*D/NS, (split+1)*D/NS) ----
-  const int dslice = D / NS;
-  for (int i = tid; i < G * dslice; i += blockDim.x) {
-    const int g = i / dslice, d = split * dslice + (i - g * dslice);
+  if (tid < G * NS) {                                    // (m, l) of this CTA to every rank
+    const int g = tid % G, dst = tid / G;
+    float* rm = cluster.map_shared_rank(&recv_ml[0][0][0], dst);
+    rm[(split * G + g) * 2] = c_ml[g][0]; rm[(split * G + g) * 2 + 1] = c_ml[g][1];
+  }
+  cluster.sync();                                        // all pushes have landed
+  // ---- local final merge: rank `split` owns dims [split*dslice, (split+1)*dslice) of every head of the group ----
+  if (tid < G) {
     float M = -INFINITY;
-    for (int r = 0; r < NS; ++r) M = fmaxf(M, cluster.map_shared_rank(&c_ml[0][0], r)[g * 2]);
-    float num = 0.f, den = 0.f;
+    for (int r = 0; r < NS; ++r) M = fmaxf(M, recv_ml[r][tid][0]);
+    float den = 0.f;
     for (int r = 0; r < NS; ++r) {
-      const float* rml = cluster.map_shared_rank(&c_ml[0][0], r);
-      const float m = rml[g * 2];
-      if (m == -INFINITY) continue;
-      const float wt = __expf(m - M);
-      num = fmaf(wt, cluster.map_shared_rank(&c_o[0][0], r)[g * D + d], num);
-      den = fmaf(wt, rml[g * 2 + 1], den);
+      const float m = recv_ml[r][tid][0];
+      const float wt = (m == -INFINITY) ? 0.f : __expf(m - M);
+      den = fmaf(wt, recv_ml[r][tid][1], den);
+      f_wt[r][tid] = wt;
     }
-    const float o = den > 0.f ? num / den : 0.f;
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    for (int r = 0; r < NS; ++r) f_wt[r][tid] *= inv;
+  }
+  __syncthreads();
+  for (int i = tid; i < G * dslice; i += blockDim.x) {
+    const int g = i / dslice, dd = i - g * dslice;
+    float o = 0.f;
+    for (int r = 0; r < NS; ++r) o = fmaf(f_wt[r][g], recv_o[r][g][dd], o);
+    const int d = split * dslice + dd;
     if (a.out) a.out[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = o;
     if (a.out_bf) a.out_bf[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = __float2bfloat16(o);
   }
-  cluster.sync();                                  // peers may still be reading this CTA's shared memory
   trace_end(a.trace);
 }
 

@@ -177,6 +177,10 @@ int t5g_abi_version(void);
 int t5g_debug_trace(T5GEngine* eng, uint64_t* begin_ns, uint64_t* end_ns, int max_entries, int* n_out);
 int t5g_debug_gemm(T5GEngine* eng, const void* x_bf16 /* dev [M,K] */, const void* w_bf16 /* dev [N,K] */,
                    float* out /* dev [M,N] */, int M, int N, int K, int impl /* 0 = simt, 1 = tcgen05 */, void* stream);
+/* Launches the decode step's dominant kernel (gate|up projection: post-norm + residual + pre-norm prologue, GeGLU
+ * epilogue; gemv_kernel<1,P_RES_NORM,E_GEGLU>) on caller-provided interleaved weights [2*inter, hidden] (device,
+ * bf16) using the engine's own decode buffers of row 0.  Used by bench.py to time that kernel live. */
+int t5g_debug_gemv_gateup(T5GEngine* eng, const void* w_bf16, void* stream);
 int t5g_debug_gemv(T5GEngine* eng, const float* x /* dev [B,K] */, const void* w_bf16 /* dev [N,K] */,
                    float* out /* dev [B,N] */, int B, int N, int K, void* stream);
 

@@ -979,6 +979,17 @@ extern "C" int t5g_debug_gemm(T5GEngine* e, const void* x, const void* w, float*
   return T5G_OK;
 }
 
+extern "C" int t5g_debug_gemv_gateup(T5GEngine* e, const void* w, void* stream_) {
+  T5G_CHECK(e && w && e->finalized, T5G_ERR_INVALID, "bad arguments / weights not finalized");
+  T5G_CUDA(cudaSetDevice(e->device));
+  const DecLayer& L = e->dec[0];
+  GemvArgs a{}; a.W = (const bf16*)w; a.N = 2 * e->I; a.K = e->d; a.B = 1; a.h_in = e->d_hA; a.y = e->d_y; a.g_post = L.g_post_ca;
+  a.g_pre = L.g_pre_ff; a.h_out = nullptr; a.eps = e->c.rms_eps; a.out = e->d_act; a.out_stride = e->I; a.slots = nullptr;
+  e->launches++;
+  CU(launch_gemv(a, P_RES_NORM, E_GEGLU, e->num_sms, (cudaStream_t)stream_, e->use_pdl));
+  return T5G_OK;
+}
+
 extern "C" int t5g_debug_gemv(T5GEngine* e, const float* x, const void* w, float* out, int B, int N, int K, void* stream_) {
   T5G_CHECK(e && x && w && out && B >= 1 && B <= 4, T5G_ERR_INVALID, "bad arguments");
   T5G_CUDA(cudaSetDevice(e->device));

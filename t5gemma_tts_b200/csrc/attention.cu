@@ -125,26 +125,46 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int PT = a.pool.page_tokens;
   const int* bt = a.block_table + (size_t)b * a.bt_stride;
-  // ---- one round trip: slot state, RoPE table, raw q, new k/v and the block-table row are all independent ----
+  // ---- one round trip: slot state, RoPE table, raw q, new k/v and the block-table row are all independent:
+  //      every load is issued into registers before the first shared-memory store (stores wait on their loads) ----
   const SlotDev& sl = a.slots[b];
   const int active = sl.active;
   const int L = a.is_cross ? sl.n_text : sl.cur_len;
   const float pos = sl.pos;
-  if (a.rope_cs) {
-    for (int i = tid; i < D / 2; i += blockDim.x) { cs[i] = a.rope_cs[(size_t)b * D + i]; sn[i] = a.rope_cs[(size_t)b * D + D / 2 + i]; }
+  constexpr int NT = ATD_WARPS * 32;
+  constexpr int QPT = (G * D + NT - 1) / NT, KPT = (D + NT - 1) / NT, RPT = (D / 2 + NT - 1) / NT;
+  float rq[QPT], rk[KPT], rv[KPT], rc[RPT], rs[RPT];
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) {
+    const int i = tid + u * NT;
+    rq[u] = (i < G * D) ? a.q[(size_t)b * a.q_stride + (size_t)(hk * G) * D + i] : 0.f;
   }
-  for (int i = tid; i < G * D; i += blockDim.x) {
-    const int g = i / D, j = i - g * D;
-    qs[g][j] = a.q[(size_t)b * a.q_stride + (size_t)(hk * G + g) * D + j];
+#pragma unroll
+  for (int u = 0; u < KPT; ++u) {
+    const int j = tid + u * NT;
+    const bool ok = !a.is_cross && j < D;
+    rk[u] = ok ? a.kv_new[(size_t)b * a.kv_stride + (size_t)hk * D + j] : 0.f;
+    rv[u] = ok ? a.kv_new[(size_t)b * a.kv_stride + (size_t)(a.Hkv + hk) * D + j] : 0.f;
   }
-  if (!a.is_cross) {
-    const float* kp = a.kv_new + (size_t)b * a.kv_stride + (size_t)hk * D;
-    const float* vp = kp + (size_t)a.Hkv * D;
-    for (int j = tid; j < D; j += blockDim.x) { knew[j] = kp[j]; vnew[j] = __bfloat162float(__float2bfloat16(vp[j])); }
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int i = tid + u * NT;
+    const bool ok = a.rope_cs && i < D / 2;
+    rc[u] = ok ? a.rope_cs[(size_t)b * D + i] : 1.f;
+    rs[u] = ok ? a.rope_cs[(size_t)b * D + D / 2 + i] : 0.f;
   }
-  for (int i = tid; i < ATD_BT_CACHE && i < a.bt_stride; i += blockDim.x) bt_s[i] = bt[i];
+  const int bt_v = (tid < ATD_BT_CACHE && tid < a.bt_stride) ? bt[tid] : 0;
   if (!active) return;                             // uniform over the whole cluster (same b)
-  cluster.barrier_arrive();                        // "this CTA is running": waited on before the first remote store
+#pragma unroll
+  for (int u = 0; u < QPT; ++u) { const int i = tid + u * NT; if (i < G * D) qs[i / D][i % D] = rq[u]; }
+#pragma unroll
+  for (int u = 0; u < KPT; ++u) {
+    const int j = tid + u * NT;
+    if (j < D) { knew[j] = rk[u]; vnew[j] = __bfloat162float(__float2bfloat16(rv[u])); }
+  }
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) { const int i = tid + u * NT; if (i < D / 2) { cs[i] = rc[u]; sn[i] = rs[u]; } }
+  if (tid < ATD_BT_CACHE) bt_s[tid] = bt_v;
   if (!a.rope_cs) {
     for (int i = tid; i < D / 2; i += blockDim.x) {
       float s, c;
@@ -158,6 +178,7 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   const int t_begin = lo + split * chunk, t_end = min(L, t_begin + chunk);
   const bool has_new = (!a.is_cross) && (t_end == L) && (t_end > t_begin);
   __syncthreads();
+  cluster.barrier_arrive();                        // "this CTA is running": waited on before the first remote store
   // rotate in place: element pairs (j, j+D/2)
   for (int i = tid; i < G * D / 2; i += blockDim.x) {
     const int g = i / (D / 2), j = i - g * (D / 2);

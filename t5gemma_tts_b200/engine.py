@@ -111,6 +111,23 @@ class T5GemmaVoiceEngine:
         eng.load_state_dict(state_dict)
         return eng
 
+    @classmethod
+    def from_pretrained(cls, model_dir: str, device="cuda:0", **sizing) -> "T5GemmaVoiceEngine":
+        """HF-format directory (config.json + safetensors) as written by scripts/export_t5gemma_voice_hf.py;
+        replaces AutoModelForSeq2SeqLM.from_pretrained(dir, trust_remote_code=True) (inference_commandline_hf.py:102-107)."""
+        from . import checkpoint as ck
+        ref_cfg = ck.load_hf_config(model_dir)
+        eng = cls(EngineConfig.from_reference(ref_cfg, **sizing), ref_config=ref_cfg, device=device)
+        eng.load_state_dict(ck.iter_hf_tensors(model_dir, device="cpu"))
+        return eng
+
+    @classmethod
+    def from_pth(cls, path: str, device="cuda:0", t5_config_dict=None, **sizing) -> "T5GemmaVoiceEngine":
+        """Training bundle {model, args} as loaded by inference_commandline.py:121-156."""
+        from . import checkpoint as ck
+        ref_cfg, sd = ck.load_pth_bundle(path, t5_config_dict)
+        return cls.from_state_dict(ref_cfg, sd, device=device, **sizing)
+
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
         """Reference state_dict keys.  Tensors may live on CPU or on this GPU."""
         items = state_dict.items() if hasattr(state_dict, "items") else state_dict   # dict or (name, tensor) iterable

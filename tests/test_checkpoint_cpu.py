@@ -1,0 +1,69 @@
+"""Checkpoint readers (HF safetensors dir / .pth bundle) on synthetic checkpoints built from the golden fixture."""
+import argparse
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import fixtures
+from t5gemma_tts_b200 import checkpoint as ck
+from t5gemma_tts_b200.config import EngineConfig
+
+
+def _write_hf_dir(tmp_path, shards=1):
+    from safetensors.torch import save_file
+    _, sd, meta = fixtures.load_model_fixture("tinyA_eager")
+    d = tmp_path / "hf"
+    d.mkdir()
+    cfg = dict(meta, model_type="t5gemma_voice", eos=103, eog=101, empty_token=100, y_sep_token=104)
+    (d / "config.json").write_text(json.dumps(cfg))
+    sd = {k: v.contiguous() for k, v in sd.items()}
+    if shards == 1:
+        save_file(sd, str(d / "model.safetensors"))
+    else:
+        keys = sorted(sd)
+        half = len(keys) // 2
+        wm = {}
+        for i, ks in enumerate((keys[:half], keys[half:])):
+            fn = f"model-{i+1:05d}-of-00002.safetensors"
+            save_file({k: sd[k] for k in ks}, str(d / fn))
+            wm.update({k: fn for k in ks})
+        (d / "model.safetensors.index.json").write_text(json.dumps({"weight_map": wm}))
+    return str(d), sd
+
+
+@pytest.mark.parametrize("shards", [1, 2])
+def test_hf_dir_roundtrip(tmp_path, shards):
+    d, sd = _write_hf_dir(tmp_path, shards)
+    cfg = ck.load_hf_config(d)
+    ec = EngineConfig.from_reference(cfg)
+    assert ec.hidden == 64 and ec.stop_token == 103 and ec.attn_softcap == 50.0
+    got = dict(ck.iter_hf_tensors(d))
+    assert set(got) == set(sd)
+    for k in sd:
+        assert torch.equal(got[k], sd[k])
+
+
+def test_hf_dir_errors(tmp_path):
+    d = tmp_path / "x"
+    d.mkdir()
+    (d / "config.json").write_text(json.dumps({"audio_vocab_size": 100}))
+    with pytest.raises(ValueError):
+        ck.load_hf_config(str(d))
+    (d / "config.json").write_text(json.dumps({"t5_config_dict": {}}))
+    with pytest.raises(FileNotFoundError):
+        list(ck.iter_hf_tensors(str(d)))
+
+
+def test_pth_bundle(tmp_path):
+    _, sd, meta = fixtures.load_model_fixture("tinyA_eager")
+    args = argparse.Namespace(audio_vocab_size=100, n_special=5, n_codebooks=1, encodec_sr=50, progress_scale=2000.0,
+                              extra_cutoff=5, attn_implementation="eager", eos=103, eog=101, empty_token=100,
+                              y_sep_token=104)
+    p = tmp_path / "bundle.pth"
+    torch.save({"model": sd, "args": args}, str(p))
+    cfg, sd2 = ck.load_pth_bundle(str(p), t5_config_dict=meta["t5_config_dict"])
+    ec = EngineConfig.from_reference(cfg)
+    assert ec.n_audio_tokens == 105 and ec.stop_token == 103 and ec.n_dec_layers == 3
+    assert set(sd2) == set(sd)

@@ -194,3 +194,28 @@ def test_batched_tensor_core_step_matches_reference():
         assert float((picks[:-1] == c["gen"][0, 0][:-1]).mean()) >= 0.99
         eng.release(s)
     assert st[1].active == 0 and st[1].n_generated == 0      # untouched rows stay idle
+
+
+def test_from_pretrained_hf_dir(tmp_path):
+    """HF-format directory (config.json + sharded safetensors) -> engine -> same prefill logits as the fixture."""
+    import json
+    from safetensors.torch import save_file
+    from t5gemma_tts_b200 import T5GemmaVoiceEngine
+    _, sd, meta = fixtures.load_model_fixture("tinyB_eager")
+    d = tmp_path / "hf"
+    d.mkdir()
+    (d / "config.json").write_text(json.dumps(dict(meta, model_type="t5gemma_voice")))
+    keys = sorted(sd)
+    wm = {}
+    for i, ks in enumerate((keys[: len(keys) // 2], keys[len(keys) // 2:])):
+        fn = f"model-{i + 1:05d}-of-00002.safetensors"
+        save_file({k: sd[k].contiguous() for k in ks}, str(d / fn))
+        wm.update({k: fn for k in ks})
+    (d / "model.safetensors.index.json").write_text(json.dumps({"weight_map": wm}))
+    eng = T5GemmaVoiceEngine.from_pretrained(str(d), max_slots=1, max_text_len=64, max_dec_len=512, max_prefill_tokens=512)
+    c = fixtures.load_case("tinyB_eager_prompt")
+    eng.prefill([_request(c, top_k=1)], [0])
+    npre = c["y"].shape[1] + 1
+    assert rel_err(eng.prefill_logits(0, npre), c["tf_logits"][:npre]) <= TOL_REF
+    assert eng.config.audio_vocab_size == 200          # reference-facing config passes through
+    eng.close()

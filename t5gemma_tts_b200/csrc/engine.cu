@@ -299,6 +299,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
     int want = (2 * e->num_sms) / (e->Hkv * B);
     e->ns_self = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
     while (D % e->ns_self) e->ns_self >>= 1;
+    if (B >= 16 && e->ns_self < 2 && D % 2 == 0) e->ns_self = 2;       // ragged batches: finer split balances long rows
     e->ns_cross = std::min(2, e->ns_self);
   }
   DM(e->d_hA, (size_t)B * d); DM(e->d_hB, (size_t)B * d); DM(e->d_y, (size_t)B * d); DM(e->d_qkv, (size_t)B * QKV);
@@ -722,45 +723,48 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
   const int d = e->d, I = e->I, QD = e->QD, QKV = e->QKV, D = e->D;
   const int B = c.max_slots;
   int nl = 0;
+  const bool pdl = e->use_pdl;
+  int mask = 31; if (const char* m = getenv("T5G_PDL_MASK")) mask = atoi(m);
+  const bool pdl_norm = pdl && (mask & 1), pdl_gemm = pdl && (mask & 2), pdl_attn = pdl && (mask & 4), pdl_samp = pdl && (mask & 8), pdl_emb = pdl && (mask & 16);
   auto G = [&](const bf16* A, const bf16* W, int N, int K, int epi, const float* bias, void* out, int ldo) -> cudaError_t {
     GemmArgs g{A, W, B, N, K, epi, bias, out, ldo};
     nl += 2;                                           // kernel (+ memset when split-K)
-    if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms, false);
+    if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms, pdl_gemm);
     return launch_gemm_simt(g, st);
   };
   float* h = e->d_hA;
   const DecLayer& Llast = e->dec[c.n_dec_layers - 1];
   // head: h += post_ff(y) ; xn = final_norm(h)
-  CU(launch_norm(h, e->d_y, Llast.g_post_ff, e->g_dec_final, h, e->d_xn, nullptr, B, d, c.rms_eps, st)); nl++;
+  CU(launch_norm(h, e->d_y, Llast.g_post_ff, e->g_dec_final, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm)); nl++;
   CU(G(e->d_xn, e->head_w1, d, d, GE_BIAS_GELU_BF16, e->head_b1, e->d_t1_bf, d));
   CU(G(e->d_t1_bf, e->head_w2, e->Vpad, d, GE_BIAS_F32, e->head_b2, e->d_logits, e->Vpad));
   { SamplerArgs s{}; s.logits = e->d_logits; s.ld = e->Vpad; s.V = e->V; s.slots = e->d_slots; s.topk_sched_pool = e->d_topk_pool;
     s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
     s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = B; s.host_mirror = e->d_mirror;
     s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
-    CU(launch_sampler(s, st, false)); nl++; }
-  CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st)); nl++;
+    CU(launch_sampler(s, st, pdl_samp)); nl++; }
+  CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st, pdl_emb)); nl++;
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
-    if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st));
-    else CU(launch_norm(h, e->d_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, h, e->d_xn, nullptr, B, d, c.rms_eps, st));
+    if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm));
+    else CU(launch_norm(h, e->d_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm));
     nl++;
     CU(G(e->d_xn, L.wqkv, QKV, d, GE_F32, nullptr, e->d_qkv, QKV));
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
       a.out = nullptr; a.out_bf = e->d_attn_bf;
-      CU(launch_attn_decode(a, st, false)); nl++; }
+      CU(launch_attn_decode(a, st, pdl_attn)); nl++; }
     CU(G(e->d_attn_bf, L.wo, d, QD, GE_F32, nullptr, e->d_y, d));
-    CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st)); nl++;
+    CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm)); nl++;
     CU(G(e->d_xn, L.wq_c, QD, d, GE_F32, nullptr, e->d_qc, QD));
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
       a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
       a.out = nullptr; a.out_bf = e->d_attn_bf;
-      CU(launch_attn_decode(a, st, false)); nl++; }
+      CU(launch_attn_decode(a, st, pdl_attn)); nl++; }
     CU(G(e->d_attn_bf, L.wo_c, d, QD, GE_F32, nullptr, e->d_y, d));
-    CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st)); nl++;
+    CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm)); nl++;
     CU(G(e->d_xn, L.wgu, 2 * I, d, GE_GEGLU_BF16, nullptr, e->d_act_bf, I));
     CU(G(e->d_act_bf, L.wd, d, I, GE_F32, nullptr, e->d_y, d));
   }

@@ -59,7 +59,7 @@ cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pd
 cudaError_t launch_embed(const bf16* table, const int* ids, float scale, float* h, int M, int d, cudaStream_t st);
 // h_out = h_in + rmsnorm(y)*g_post (if y) ; xn = bf16(rmsnorm(h_out)*g_pre) (if xn) ; hf32 = fp32 normed (if xf)
 cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, const float* g_pre, float* h_out,
-                        bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st);
+                        bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st, bool pdl = false);
 // qkv fp32 [M, ld] -> RoPE(q,k) at pos[M]; q_out bf16 [M,Hq*D]; k_out/v_out bf16 [M,Hkv*D]; optional page append
 struct RopeSplitArgs {
   const float* qkv; int ld; int q_off, k_off, v_off;   // column offsets (negative = absent)
@@ -90,7 +90,7 @@ cudaError_t launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool pdl = false);   // tcgen05/TMEM/TMA path (gemm_tc.cu)
 bool gemm_tc_supported(const GemmArgs& a);
 // h[b] = table[slots[b].last_token] * scale for every row (batched decode step)
-cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float scale, float* h, int B, int d, cudaStream_t st);
+cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float scale, float* h, int B, int d, cudaStream_t st, bool pdl = false);
 cudaError_t launch_gather_rows(const float* src, const int* rows, float* dst, int n, int d, cudaStream_t st);
 cudaError_t launch_f32_to_bf16(const float* src, bf16* dst, size_t n, cudaStream_t st);
 

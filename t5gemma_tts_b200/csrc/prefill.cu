@@ -11,44 +11,78 @@ __global__ void embed_kernel(const bf16* __restrict__ table, const int* __restri
   for (int k = threadIdx.x; k < d; k += blockDim.x) h[(size_t)t * d + k] = __bfloat162float(row[k]) * scale;
 }
 
-__global__ void embed_slots_kernel(const bf16* __restrict__ table, const SlotDev* __restrict__ slots, float scale,
-                                   float* __restrict__ h, int d) {
+// (slots are written by the sampler of the same step: no __restrict__/read-only path under PDL)
+__global__ void embed_slots_kernel(const bf16* __restrict__ table, const SlotDev* slots, float scale,
+                                   float* h, int d) {
   const int b = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (!slots[b].active) return;
   const bf16* row = table + (size_t)slots[b].last_token * d;
   for (int k = threadIdx.x; k < d; k += blockDim.x) h[(size_t)b * d + k] = __bfloat162float(row[k]) * scale;
 }
 
-// one CTA per token: h_out = h_in + rmsnorm(y)*g_post ; xn/xf = rmsnorm(h_out)*g_pre  (HF:66-74 in fp32)
-__global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ h_in, const float* __restrict__ y,
-                                                   const float* __restrict__ g_post, const float* __restrict__ g_pre,
-                                                   float* __restrict__ h_out, bf16* __restrict__ xn,
-                                                   float* __restrict__ xf, int d, float eps) {
-  __shared__ float red[32];
-  extern __shared__ float hs[];
+// one CTA per token: h_out = h_in + rmsnorm(y)*g_post ; xn/xf = rmsnorm(h_out)*g_pre  (HF:66-74 in fp32).
+// Single reduction pass: with r = rsqrt(mean(y^2)+eps), sum(h + y r g)^2 = S2 + 2 r S3 + r^2 S4; all loads are
+// 128-bit and issued before the reduction; the gains are fetched before griddepcontrol.wait (PDL).
+constexpr int NK_THREADS = 128;
+constexpr int NK_MAXV = 8;                       // float4 per thread: d <= 128*4*8 = 4096
+// (activations are read with ld.global.cg: under PDL this kernel is launched while its producer is still running, so
+// they must not come from the non-coherent read-only path)
+__global__ void __launch_bounds__(NK_THREADS) norm_kernel(const float* h_in, const float* y,
+                                                          const float* __restrict__ g_post, const float* __restrict__ g_pre,
+                                                          float* h_out, bf16* xn, float* xf, int d, float eps) {
+  __shared__ float red[128];
   const size_t base = (size_t)blockIdx.x * d;
-  float rinv_y = 0.f;
-  if (y) {
-    float ys = 0.f;
-    for (int k = threadIdx.x; k < d; k += blockDim.x) { float v = y[base + k]; ys = fmaf(v, v, ys); }
-    ys = block_sum(ys, red);
-    rinv_y = rsqrtf(ys / (float)d + eps);
+  const int nv = d >> 2;
+  float4 gp[NK_MAXV], gq[NK_MAXV];
+#pragma unroll
+  for (int u = 0; u < NK_MAXV; ++u) {
+    const int i = threadIdx.x + u * NK_THREADS;
+    gp[u] = (g_pre && i < nv) ? reinterpret_cast<const float4*>(g_pre)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    gq[u] = (y && i < nv) ? reinterpret_cast<const float4*>(g_post)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  float ss = 0.f;
-  for (int k = threadIdx.x; k < d; k += blockDim.x) {
-    float hv = h_in[base + k];
-    if (y) hv += y[base + k] * rinv_y * g_post[k];
-    hs[k] = hv;
-    if (h_out) h_out[base + k] = hv;
-    ss = fmaf(hv, hv, ss);
+  pdl_launch_dependents();
+  pdl_wait();
+  float4 hv[NK_MAXV], yv[NK_MAXV];
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+#pragma unroll
+  for (int u = 0; u < NK_MAXV; ++u) {
+    const int i = threadIdx.x + u * NK_THREADS;
+    hv[u] = (i < nv) ? __ldcg(reinterpret_cast<const float4*>(h_in + base) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    yv[u] = (y && i < nv) ? __ldcg(reinterpret_cast<const float4*>(y + base) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (!g_pre) return;
-  ss = block_sum(ss, red);
+#pragma unroll
+  for (int u = 0; u < NK_MAXV; ++u) {
+    const float hh[4] = {hv[u].x, hv[u].y, hv[u].z, hv[u].w};
+    const float yy[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+    const float gg[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float yg = yy[j] * gg[j];
+      s1 = fmaf(yy[j], yy[j], s1); s2 = fmaf(hh[j], hh[j], s2); s3 = fmaf(hh[j], yg, s3); s4 = fmaf(yg, yg, s4);
+    }
+    yv[u] = make_float4(yy[0] * gg[0], yy[1] * gg[1], yy[2] * gg[2], yy[3] * gg[3]);     // y*g_post
+  }
+  block_sum4(s1, s2, s3, s4, red);
+  const float ry = y ? rsqrtf(s1 / (float)d + eps) : 0.f;
+  const float ss = s2 + 2.f * ry * s3 + ry * ry * s4;
   const float rinv = rsqrtf(ss / (float)d + eps);
-  for (int k = threadIdx.x; k < d; k += blockDim.x) {
-    float v = hs[k] * rinv * g_pre[k];
-    if (xn) xn[base + k] = __float2bfloat16(v);
-    if (xf) xf[base + k] = v;
+#pragma unroll
+  for (int u = 0; u < NK_MAXV; ++u) {
+    const int i = threadIdx.x + u * NK_THREADS;
+    if (i >= nv) continue;
+    float4 hn = make_float4(fmaf(yv[u].x, ry, hv[u].x), fmaf(yv[u].y, ry, hv[u].y), fmaf(yv[u].z, ry, hv[u].z), fmaf(yv[u].w, ry, hv[u].w));
+    if (h_out) reinterpret_cast<float4*>(h_out + base)[i] = hn;
+    if (g_pre) {
+      const float4 o = make_float4(hn.x * rinv * gp[u].x, hn.y * rinv * gp[u].y, hn.z * rinv * gp[u].z, hn.w * rinv * gp[u].w);
+      if (xf) reinterpret_cast<float4*>(xf + base)[i] = o;
+      if (xn) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk; pk.x = *reinterpret_cast<unsigned*>(&lo); pk.y = *reinterpret_cast<unsigned*>(&hi);
+        reinterpret_cast<uint2*>(xn + base)[i] = pk;
+      }
+    }
   }
 }
 
@@ -197,17 +231,35 @@ cudaError_t launch_embed(const bf16* table, const int* ids, float scale, float* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float scale, float* h, int B, int d, cudaStream_t st) {
+cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float scale, float* h, int B, int d, cudaStream_t st, bool pdl) {
   if (B <= 0) return cudaSuccess;
-  embed_slots_kernel<<<B, 256, 0, st>>>(table, slots, scale, h, d);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(B);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, embed_slots_kernel, table, slots, scale, h, d);
 }
 
 cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, const float* g_pre, float* h_out,
-                        bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st) {
+                        bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st, bool pdl) {
   if (M <= 0) return cudaSuccess;
-  norm_kernel<<<M, 256, d * sizeof(float), st>>>(h_in, y, g_post, g_pre, h_out, xn, xf, d, eps);
-  return cudaGetLastError();
+  if (d % 4 != 0 || d > NK_THREADS * 4 * NK_MAXV) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(M);
+  cfg.blockDim = dim3(NK_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, norm_kernel, h_in, y, g_post, g_pre, h_out, xn, xf, d, eps);
 }
 
 cudaError_t launch_rope_split(const RopeSplitArgs& a, cudaStream_t st) {

@@ -89,7 +89,6 @@ __device__ __forceinline__ void warp_merge(GroupState<G, Geo<D>::DPL>& st) {
   }
 }
 
-constexpr int ATD_WARPS = 8;
 constexpr int ATD_MAX_NS = 8;
 constexpr int ATD_BT_CACHE = 256;      // block-table entries staged in shared memory (covers 4096 tokens at 16/page)
 
@@ -97,7 +96,7 @@ constexpr int ATD_BT_CACHE = 256;      // block-table entries staged in shared m
 // their partial softmax states through distributed shared memory instead of a global round trip: every CTA
 // PUSHES the slice of its partial that rank r will finalise into rank r's receive buffer, one cluster barrier,
 // then every rank merges locally.
-template <int G, int D>
+template <int G, int D, int ATD_WARPS>
 __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeArgs a) {
   constexpr int LPT = Geo<D>::LPT, DPL = Geo<D>::DPL, TPW = Geo<D>::TPW, NV = Geo<D>::NV;
   namespace cg = cooperative_groups;
@@ -372,9 +371,11 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_prefill_kernel(AttnPrefil
 
 template <int G, int D>
 cudaError_t launch_decode_gd(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
+  // 8 warps per CTA for latency (bs<=4: few CTAs, long token loops); 4 warps for batches so that 3 CTAs fit per SM
+  const bool wide = a.B <= 4;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.Hkv, a.n_splits, a.B);
-  cfg.blockDim = dim3(ATD_WARPS * 32);
+  cfg.blockDim = dim3((wide ? 8 : 4) * 32);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -384,7 +385,8 @@ cudaError_t launch_decode_gd(const AttnDecodeArgs& a, cudaStream_t st, bool pdl)
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D>, a);
+  if (wide) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D, 8>, a);
+  return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D, 4>, a);
 }
 
 template <int G, int D>

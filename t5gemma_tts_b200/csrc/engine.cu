@@ -299,7 +299,6 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
     int want = (2 * e->num_sms) / (e->Hkv * B);
     e->ns_self = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
     while (D % e->ns_self) e->ns_self >>= 1;
-    if (B >= 16 && e->ns_self < 2 && D % 2 == 0) e->ns_self = 2;       // ragged batches: finer split balances long rows
     e->ns_cross = std::min(2, e->ns_self);
   }
   DM(e->d_hA, (size_t)B * d); DM(e->d_hB, (size_t)B * d); DM(e->d_y, (size_t)B * d); DM(e->d_qkv, (size_t)B * QKV);

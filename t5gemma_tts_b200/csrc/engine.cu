@@ -47,7 +47,9 @@ struct T5GEngine {
   int device = 0, num_sms = 148;
   int d, I, Hq, Hkv, D, QD, KD, QKV, V, Vpad, PT;
   int max_self_pages, max_cross_pages, n_pages;
-  bool use_pdl = true, use_graph = true, use_l2pf = false;   // L2 weight prefetch: measured net-negative (profiles/), opt-in
+  bool use_pdl = true, use_graph = true, use_l2pf = false;   // L2 weight prefetch from kernels that wait on attention: measured
+                                                             // zero-sum (profiles/r1_gemv_design_experiments.md), opt-in
+  size_t l2pf_gu_elems = 0;                                 // gate|up elements prefetched by o_cross (T5G_L2PF_GU_MB)
   int gemm_impl = 1;                       // 1 tcgen05/TMEM/TMA (default), 0 = SIMT cross-check kernel
   cudaStream_t load_stream = nullptr;
   std::vector<void*> allocs;               // every cudaMalloc of this engine
@@ -224,6 +226,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_GEMM")) e->gemm_impl = atoi(s);
   if (const char* s = getenv("T5G_TRACE")) e->use_trace = atoi(s) != 0;
   if (const char* s = getenv("T5G_L2PF")) e->use_l2pf = atoi(s) != 0;
+  if (const char* s = getenv("T5G_L2PF_GU_MB")) e->l2pf_gu_elems = (size_t)atoi(s) * 1024 * 512;
   *out = e;   // so that the caller can destroy on failure
   T5G_CUDA(cudaStreamCreateWithFlags(&e->load_stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev) T5G_CUDA(cudaEventCreate(&ev));
@@ -653,7 +656,7 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
     if (n_elems == (size_t)-1) n_elems = elems - off_elems;
     return PrefetchRange{(const char*)p + off_elems * 2, (unsigned long long)n_elems * 2};
   };
-  const size_t GU = (size_t)2 * I * d, GUH = (GU / 2 + 7) / 8 * 8;
+  const size_t GU = (size_t)2 * I * d;
   if (e->use_trace) {
     CU(cudaMemsetAsync(e->d_trace, 0xFF, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
     CU(cudaMemsetAsync(e->d_trace + T5G_TRACE_STRIDE, 0, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
@@ -672,23 +675,21 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
     s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = B; s.host_mirror = e->d_mirror;
     s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
     s.trace = next_trace();
-    { const DecLayer& L0 = e->dec[0]; s.pf[0] = PF(L0.wqkv, (size_t)QKV * d); s.pf[1] = PF(L0.wo, (size_t)d * QD); s.pf[2] = PF(L0.wq_c, (size_t)QD * d); s.pf[3] = PF(L0.wo_c, (size_t)d * QD); }
     CU(launch_sampler(s, st, pdl)); nl++; }
   // ---- 26 decoder layers at q_len = 1 ----
   int t = 0;   // hbuf[t] holds the current residual
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
     { GemvArgs a = z; a.W = L.wqkv; a.N = QKV; a.K = d; a.g_pre = L.g_pre_sa; a.out = e->d_qkv; a.out_stride = QKV;
-      a.pf[0] = PF(L.wq_c, (size_t)QD * d); a.pf[1] = PF(L.wo_c, (size_t)d * QD);
       if (l == 0) { a.emb = e->audio_emb; a.emb_scale = sqrtf((float)d); a.h_out = hbuf[0]; t = 0; CU(gemv_all(a, P_EMBED_NORM, E_STORE, 0, QKV)); }
       else { a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = e->dec[l - 1].g_post_ff; a.h_out = hbuf[t ^ 1]; t ^= 1; CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QKV)); } }
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.pf[0] = PF(L.wgu, GU, 0, GUH);
       a.out = e->d_attn; a.trace = next_trace();
       CU(launch_attn_decode(a, st, pdl)); nl++; }
     { GemvArgs a = z; a.W = L.wo; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
+      a.pf[0] = PF(L.wq_c, (size_t)QD * d);                 // issued while this kernel waits on the attention kernel
       CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
     { GemvArgs a = z; a.W = L.wq_c; a.N = QD; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_sa; a.g_pre = L.g_pre_ca; a.h_out = hbuf[t ^ 1]; t ^= 1;
       a.out = e->d_qc; a.out_stride = QD;
@@ -696,17 +697,15 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
       a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.pf[0] = PF(L.wgu, GU, GUH);
       a.out = e->d_attn; a.trace = next_trace();
       CU(launch_attn_decode(a, st, pdl)); nl++; }
     { GemvArgs a = z; a.W = L.wo_c; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
+      a.pf[0] = PF(L.wgu, GU, 0, std::min(GU, e->l2pf_gu_elems));
       CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
     { GemvArgs a = z; a.W = L.wgu; a.N = 2 * I; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_ca; a.g_pre = L.g_pre_ff; a.h_out = hbuf[t ^ 1]; t ^= 1;
-      a.out = e->d_act; a.out_stride = I; a.pf[0] = PF(L.wd, (size_t)d * I);
+      a.out = e->d_act; a.out_stride = I;
       CU(gemv_all(a, P_RES_NORM, E_GEGLU, 0, I)); }
     { GemvArgs a = z; a.W = L.wd; a.N = d; a.K = I; a.x = e->d_act; a.out = e->d_y; a.out_stride = d;
-      if (l + 1 < c.n_dec_layers) { a.pf[0] = PF(e->dec[l + 1].wqkv, (size_t)QKV * d); a.pf[1] = PF(e->dec[l + 1].wo, (size_t)d * QD); }
-      else { a.pf[0] = PF(e->head_w1, (size_t)d * d); a.pf[1] = PF(e->head_w2, (size_t)e->Vpad * d, 0, std::min((size_t)e->Vpad * d, (size_t)24 << 20)); }
       CU(gemv_all(a, P_PLAIN, E_STORE, I, d)); }
   }
   if (t != e->h_end) { t5g_set_error("internal: residual buffer parity %d != %d", t, e->h_end); return T5G_ERR_STATE; }

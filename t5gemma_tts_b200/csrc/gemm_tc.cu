@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cooperative_groups.h>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -238,6 +239,184 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight-streaming variant for skinny problems (M <= 64 tokens: batched decode).  Same tcgen05/TMEM math, but the
+// operand tiles are fetched with per-thread 16-byte cp.async (LDGSTS) copies written straight into the 128-byte
+// swizzled layout the UMMA descriptor expects: 128 producer threads keep NSTAGE x (16 KB + TOKT*128 B) in flight
+// per SM with no register cost, which sustains HBM streaming where the TMA path is limited by its per-CTA request
+// depth (profiles/r1_gemv_design_experiments.md).  Completion is tracked with cp.async.mbarrier.arrive.noinc, so
+// producers never block; the four producer warps become the epilogue warps once their loads are issued.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ST_THREADS = 160;     // warps 0-3: cp.async producers, then epilogue; warp 4: MMA issuer + TMEM alloc
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill (rows beyond N / M)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int TOKT, int NSTAGE>
+__global__ void __launch_bounds__(ST_THREADS, 1) gemm_stream_kernel(const bf16* __restrict__ W, const bf16* X, TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  TcSmem<TOKT, NSTAGE>& S = *reinterpret_cast<TcSmem<TOKT, NSTAGE>*>(
+      (reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+  constexpr int TMEM_COLS = TOKT < 32 ? 32 : TOKT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int f0 = blockIdx.x * TC_BM, t0 = blockIdx.y * TOKT;
+  const int kb_total = p.K / TC_BK;
+  const int kb0 = blockIdx.z * p.k_blocks_per_split;
+  const int nkb = min(p.k_blocks_per_split, kb_total - kb0);
+
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&S.full[i], 128); mbar_init(&S.empty[i], 1); }
+    mbar_init(&S.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = S.tmem_base;
+
+  if (warp < 4) {
+    // ===== producers: thread t copies chunks t, t+128, ... of every tile (8 consecutive threads = one 128 B row) =====
+    auto load_w = [&](int i, int s) {
+      const int kc = (kb0 + i) * TC_BK;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = tid + u * 128, row = c >> 3, col = c & 7;
+        const int n = f0 + row;
+        cp_async16(S.w[s] + row * 128 + ((col ^ (row & 7)) << 4), W + (size_t)min(n, p.N - 1) * p.K + kc + col * 8, n < p.N);
+      }
+    };
+    auto load_x = [&](int i, int s) {
+      const int kc = (kb0 + i) * TC_BK;
+#pragma unroll
+      for (int u = 0; u < (TOKT * 8 + 127) / 128; ++u) {
+        const int c = tid + u * 128, row = c >> 3, col = c & 7;
+        if (c < TOKT * 8) {
+          const int m = t0 + row;
+          cp_async16(S.x[s] + row * 128 + ((col ^ (row & 7)) << 4), X + (size_t)min(m, p.M - 1) * p.K + kc + col * 8, m < p.M);
+        }
+      }
+    };
+    const int pre = min(nkb, NSTAGE);
+    for (int i = 0; i < pre; ++i) load_w(i, i);          // weights are immutable: before the PDL dependency resolves
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int i = 0; i < pre; ++i) { load_x(i, i); cp_async_arrive(&S.full[i]); }
+    for (int i = NSTAGE; i < nkb; ++i) {
+      const int s = i % NSTAGE;
+      mbar_wait(&S.empty[s], ((i / NSTAGE) - 1) & 1);
+      load_w(i, s);
+      load_x(i, s);
+      cp_async_arrive(&S.full[s]);
+    }
+  } else if (lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TOKT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % NSTAGE;
+      mbar_wait(&S.full[s], (i / NSTAGE) & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // cp.async (generic proxy) -> tcgen05 (async proxy)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t wa = smem_u32(S.w[s]), xa = smem_u32(S.x[s]);
+#pragma unroll
+      for (int k = 0; k < TC_BK / 16; ++k)
+        umma_bf16(tmem_d, umma_desc_sw128(wa + k * 32), umma_desc_sw128(xa + k * 32), idesc, (i | k) ? 1u : 0u);
+      umma_commit(&S.empty[s]);
+    }
+    umma_commit(&S.acc_full);
+  }
+  if (warp < 4) {
+    // ===== epilogue (same warps): TMEM lane quarter = warp index =====
+    const int q = warp, fl = q * 32 + lane, f = f0 + fl;
+    mbar_wait(&S.acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* red = reinterpret_cast<float*>(&S.w[0][0]);
+#pragma unroll 1
+    for (int c = 0; c < TOKT; c += 16) {
+      if (t0 + c >= p.M) break;
+      float v[16];
+      tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (p.atomic) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (t0 + c + j < p.M && f < p.N) atomicAdd(reinterpret_cast<float*>(p.out) + (size_t)(t0 + c + j) * p.ldo + f, v[j]);
+        continue;
+      }
+      if (p.split_k > 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) red[(c + j) * TC_BM + fl] = v[j];
+        continue;
+      }
+      const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float other = (p.epilogue == GE_GEGLU_BF16) ? __shfl_xor_sync(0xffffffffu, v[j], 1) : 0.f;
+        epilogue_store(p, t0 + c + j, f, v[j], other, bias, (lane & 1) == 0);
+      }
+    }
+  }
+  if (p.split_k > 1 && !p.atomic) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (warp < 4) {
+      const int rank = (int)cluster.block_rank(), nr = p.split_k;
+      const int fl = warp * 32 + lane, f = f0 + fl;
+      const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
+      float* red = reinterpret_cast<float*>(&S.w[0][0]);
+      for (int j = rank; j < TOKT && t0 + j < p.M; j += nr) {
+        float acc = 0.f, acc_up = 0.f;
+        for (int r = 0; r < nr; ++r) {
+          const float* rr = cluster.map_shared_rank(red, r);
+          acc += rr[j * TC_BM + fl];
+          if (p.epilogue == GE_GEGLU_BF16) acc_up += rr[j * TC_BM + (fl | 1)];
+        }
+        epilogue_store(p, t0 + j, f, acc, acc_up, bias, (fl & 1) == 0);
+      }
+    }
+    cluster.sync();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int TOKT, int NSTAGE>
+cudaError_t launch_stream(const GemmArgs& a, const TcParams& p, dim3 grid, cudaStream_t st, bool pdl) {
+  auto kern = gemm_stream_kernel<TOKT, NSTAGE>;
+  const size_t smem = sizeof(TcSmem<TOKT, NSTAGE>) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(ST_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = p.atomic ? 1 : p.split_k;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, a.W, a.A, p);
+}
+
 // ---- host side: tensor maps -------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -320,6 +499,15 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
   }
   TcParams p{a.M, a.N, a.K, a.epilogue, a.bias, a.out, a.ldo, kbps, split, atomic};
   dim3 grid((a.N + TC_BM - 1) / TC_BM, (a.M + tokt - 1) / tokt, split);
+  static int use_stream = -1;
+  if (use_stream < 0) { const char* e = getenv("T5G_GEMM_STREAM"); use_stream = e ? atoi(e) : 1; }
+  if (use_stream && tokt <= 64) {
+    switch (tokt) {
+      case 16: return launch_stream<16, 8>(a, p, grid, st, pdl);
+      case 32: return launch_stream<32, 8>(a, p, grid, st, pdl);
+      default: return launch_stream<64, 6>(a, p, grid, st, pdl);
+    }
+  }
   switch (tokt) {
     case 16: return launch_tc<16, 8>(mw, mx, p, grid, st, pdl);
     case 32: return launch_tc<32, 8>(mw, mx, p, grid, st, pdl);

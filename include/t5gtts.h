@@ -94,6 +94,11 @@ typedef struct T5GRequest {
    * decoder instead of the engine's own pick; the pick is still recorded (t5g_read_picks). */
   const int32_t* forced_tokens;
   int32_t n_forced;
+  /* Silence-repetition penalty (models/t5gemma.py:999-1011, 1050-1054): HOST pointer to the silence token ids
+   * (NULL/0 = off, what every shipped caller passes) and the stop_repetition argument of inference_tts. */
+  const int32_t* silence_tokens;
+  int32_t n_silence;
+  int32_t stop_repetition;
 } T5GRequest;
 
 /* Host-visible per-slot state after t5g_decode / t5g_poll. */
@@ -155,9 +160,13 @@ typedef struct T5GSampleRow {
   int32_t prompt_offset;        /* prompt_frames + 1 */
   int32_t target_total;
   int32_t n_text;
+  int32_t prev_token;           /* silence-repetition state (models/t5gemma.py:967-968): -1 initially */
+  int32_t consec_silence_count;
 } T5GSampleRow;
 int t5g_sample(T5GEngine* eng, float* logits, const T5GSampleRow* rows /* host */, int n_rows,
                int32_t* out_tokens /* host */, int32_t* out_argmax /* host, may be NULL */, void* stream);
+/* Silence-repetition settings used by t5g_sample rows (shared by all rows of the call; NULL/0 = off). */
+int t5g_sample_set_silence(T5GEngine* eng, const int32_t* silence_tokens /* host */, int n_silence, int stop_repetition);
 
 /* Accounting for bench.py: kernel launches issued by the engine since creation, and per-step byte model. */
 int64_t t5g_launch_count(const T5GEngine* eng);

@@ -77,6 +77,22 @@ def run_case(model, x, y, tgt, prompt_frames, top_k=1):
                 step_logits=step_logits.numpy(), est_total=np.int64(est_total))
 
 
+def silence_case(model):
+    """Silence-repetition penalty (models/t5gemma.py:999-1011,1050-1054) exercised through the reference's own
+    sample_helper: a forward hook replaces the head output by crafted logits so that greedy decoding repeats token 7."""
+    V = model.predict_layer[0][2].out_features
+    base = (torch.randn(V, generator=torch.Generator().manual_seed(99)) * 0.1)
+    base[7], base[9], base[11] = 5.0, 3.0, -4.0
+    hook = model.predict_layer[0].register_forward_hook(lambda m, i, o: base.clone().reshape(1, 1, V).expand(o.shape[0], o.shape[1], V).clone())
+    x = torch.randint(2, 500, (1, 9), generator=torch.Generator().manual_seed(5))
+    y = torch.zeros((1, 0, 1), dtype=torch.long)
+    res, gen = model.inference_tts(x, torch.tensor([9]), y, torch.tensor([20]), top_k=1, top_p=1.0, temperature=1.0,
+                                   prompt_frames=0, stop_repetition=2, silence_tokens=[7, 11])
+    hook.remove()
+    return dict(x=x.numpy(), base_logits=base.numpy(), gen=gen.numpy(), tgt=np.int64(20), stop_repetition=np.int64(2),
+                silence_tokens=np.array([7, 11], dtype=np.int64))
+
+
 def sampler_cases():
     U = ref_loader.load_reference_sampling()
     rows = []
@@ -130,6 +146,10 @@ def main():
         c = run_case(model, x, y, tgt=12, prompt_frames=0)
         np.savez_compressed(os.path.join(OUT, f"case_{name}_noprompt.npz"), **c)
         print(name, "noprompt gen len", c["gen"].shape)
+        if name == "tinyA_eager":
+            sc = silence_case(model)
+            np.savez_compressed(os.path.join(OUT, "case_tinyA_eager_silence.npz"), **sc)
+            print("silence gen head", sc["gen"][0, 0, :24])
     # tiny B: wider heads (head_dim 32, 4 layers, GQA 4/2), softcap strongly binding (cap 5)
     t5b = ref_loader.tiny_t5_config_dict(hidden=128, inter=256, layers=4, heads=4, kv_heads=2, head_dim=32,
                                          window=16, qpas=32, softcap=5.0)

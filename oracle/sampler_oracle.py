@@ -149,7 +149,8 @@ def draw(z, survivors, filtered, u):
 
 def sample_step(logits, *, eos, cur_num_gen, current_length, prompt_offset, target_total, encodec_sr=50,
                 extra_cutoff=5.0, top_k=-100, top_p=1.0, min_p=0.0, temperature=1.0, u=0.5,
-                x_len=0, text_guard_frames_per_token=0, return_detail=False):
+                x_len=0, text_guard_frames_per_token=0, return_detail=False,
+                prev_token=-1, consec_silence_count=0, stop_repetition=3, silence_tokens=()):
     """One sample_helper call (models/t5gemma.py:971-1055) for text_input_type=="text",
     silence_tokens=[] (every shipped caller).  `logits` fp32 [V] is edited in place like the reference."""
     logits = np.asarray(logits)
@@ -159,6 +160,13 @@ def sample_step(logits, *, eos, cur_num_gen, current_length, prompt_offset, targ
         logits[eos] = f32(-1e9)
     if cur_num_gen <= int(encodec_sr) // 5:
         logits[eos] = f32(-10000.0)
+    # silence-repetition penalty (models/t5gemma.py:999-1011)
+    if stop_repetition > 0 and prev_token in silence_tokens and consec_silence_count > stop_repetition:
+        fct = f32(consec_silence_count - (stop_repetition - 1))
+        if logits[prev_token] < 0:
+            logits[prev_token] = f32(logits[prev_token] * fct)
+        else:
+            logits[prev_token] = f32(logits[prev_token] / fct)
     amax = int(np.argmax(logits))
     z = logits / f32(temperature) if temperature != 1.0 else logits
     z = z.astype(f32, copy=False)
@@ -173,5 +181,11 @@ def sample_step(logits, *, eos, cur_num_gen, current_length, prompt_offset, targ
     if force or budget:
         token_id = eos
     if return_detail:
-        return token_id, dict(survivors=survivors, argmax=amax, sampled=sampled)
+        # models/t5gemma.py:1050-1054
+        if token_id in silence_tokens and token_id == prev_token:
+            consec_silence_count += 1
+        else:
+            consec_silence_count = 0
+        return token_id, dict(survivors=survivors, argmax=amax, sampled=sampled, prev_token=token_id,
+                              consec_silence_count=consec_silence_count)
     return token_id

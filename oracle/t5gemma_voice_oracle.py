@@ -286,7 +286,8 @@ class Oracle:
     def inference_tts(self, x: torch.Tensor, x_lens: torch.Tensor, y: torch.Tensor, tgt_y_lens: torch.Tensor,
                       top_k=-100, top_p: float = 1.0, min_p: float = 0.0, temperature: float = 1.0,
                       prompt_frames: Optional[int] = None, uniforms: Optional[Sequence[float]] = None,
-                      max_new_tokens: Optional[int] = None, return_logits: bool = False):
+                      max_new_tokens: Optional[int] = None, return_logits: bool = False,
+                      stop_repetition: int = 3, silence_tokens: Sequence[int] = (), logits_hook=None):
         """Same contract as the reference, bs=1.  `uniforms[i]` is the U[0,1) draw consumed by step i
         (the reference consumes torch.multinomial's stream instead; see sampler_oracle)."""
         c = self.cfg
@@ -309,17 +310,23 @@ class Oracle:
         gen: List[int] = []
         all_logits = []
         cur_num_gen = 0
+        prev_token, consec = -1, 0                       # models/t5gemma.py:967-968
         while True:
             logits = self.head(last_hidden)[0].clone()
+            if logits_hook is not None:
+                logits = torch.from_numpy(np.asarray(logits_hook(logits.numpy(), cur_num_gen), dtype=np.float32)).clone()
             if return_logits:
                 all_logits.append(logits.clone())
             u = float(uniforms[cur_num_gen]) if uniforms is not None else 0.5
             kk = top_k[min(len(top_k) - 1, cur_num_gen)] if isinstance(top_k, (list, tuple)) else top_k
-            token_id = sampler_oracle.sample_step(
+            token_id, det = sampler_oracle.sample_step(
                 logits.numpy(), eos=c.eos, cur_num_gen=cur_num_gen, current_length=current_length,
                 prompt_offset=prompt_offset, target_total=target_total, encodec_sr=c.encodec_sr,
                 extra_cutoff=c.extra_cutoff, top_k=kk, top_p=top_p, min_p=min_p, temperature=temperature, u=u,
-                x_len=S, text_guard_frames_per_token=c.text_guard_frames_per_token)
+                x_len=S, text_guard_frames_per_token=c.text_guard_frames_per_token, return_detail=True,
+                prev_token=prev_token, consec_silence_count=consec, stop_repetition=stop_repetition,
+                silence_tokens=tuple(silence_tokens))
+            prev_token, consec = det["prev_token"], det["consec_silence_count"]
             if max_new_tokens is not None and cur_num_gen + 1 >= max_new_tokens:
                 token_id = c.eos
             gen.append(token_id)

@@ -151,4 +151,10 @@ struct SlotDev {
   float pos;           // PM-RoPE position of that token
   int error;           // sampler error flags
   int n_forced;        // teacher-forced prefix length (tests)
+  int prev_token;      // silence-repetition state (models/t5gemma.py:967-968)
+  int consec_silence;
+  int stop_repetition;
+  int silence_off;     // offset into the engine's int pool, -1 = none
+  int n_silence;
+  int pad_;
 };

@@ -71,7 +71,8 @@ struct T5GEngine {
   int* h_tokens = nullptr; int* d_tokens = nullptr;           // mapped pinned [max_slots][max_dec_len]
   int* h_picks = nullptr; int* d_picks = nullptr;             // mapped pinned [max_slots][max_dec_len]
   int* d_forced = nullptr;                                    // [max_slots][max_dec_len]
-  int* d_topk_pool = nullptr; int topk_pool_cap = 0, topk_pool_used = 0;
+  int* d_topk_pool = nullptr; int topk_pool_cap = 0, topk_pool_used = 0;   // int pool: top-k schedules + silence token lists
+  int* d_sample_silence = nullptr; int n_sample_silence = 0, sample_stop_repetition = 0;   // t5g_sample settings
   // prefill workspaces (T = max_prefill_tokens)
   float *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_memory = nullptr, *p_ckv = nullptr, *p_final = nullptr;
   bf16 *p_xn = nullptr, *p_q = nullptr, *p_k = nullptr, *p_v = nullptr, *p_att = nullptr, *p_act = nullptr,
@@ -310,7 +311,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   T5G_CUDA(cudaMemset(e->d_y, 0, sizeof(float) * (size_t)B * d));
   T5G_CUDA(cudaMemset(e->d_hA, 0, sizeof(float) * (size_t)B * d));
   T5G_CUDA(cudaMemset(e->d_hB, 0, sizeof(float) * (size_t)B * d));
-  DM(e->d_sample_u, 4096); DM(e->d_sample_slots, 4096);
+  DM(e->d_sample_u, 4096); DM(e->d_sample_slots, 4096); DM(e->d_sample_silence, 256);
   DM(e->d_attn, (size_t)B * QD); DM(e->d_trace, 2 * T5G_TRACE_STRIDE);
   DM(e->d_xn, (size_t)B * d); DM(e->d_attn_bf, (size_t)B * QD); DM(e->d_act_bf, (size_t)B * I); DM(e->d_t1_bf, (size_t)B * d);
   T5G_CUDA(cudaDeviceSynchronize());
@@ -465,6 +466,13 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     sd.max_new_tokens = q.max_new_tokens; sd.top_k = q.sampling.top_k; sd.top_p = q.sampling.top_p; sd.min_p = q.sampling.min_p;
     sd.temperature = q.sampling.temperature; sd.uniforms = q.uniforms; sd.n_uniforms = q.n_uniforms;
     sd.topk_sched_off = -1; sd.n_topk_sched = 0; sd.last_token = 0; sd.pos = 0.f;
+    sd.prev_token = -1; sd.consec_silence = 0; sd.stop_repetition = q.stop_repetition; sd.silence_off = -1; sd.n_silence = 0;
+    if (q.silence_tokens && q.n_silence > 0) {
+      T5G_CHECK(e->topk_pool_used + q.n_silence <= e->topk_pool_cap, T5G_ERR_OOM, "int pool exhausted (silence tokens)");
+      CU(cudaMemcpyAsync(e->d_topk_pool + e->topk_pool_used, q.silence_tokens, sizeof(int) * q.n_silence, cudaMemcpyHostToDevice, st));
+      sd.silence_off = e->topk_pool_used; sd.n_silence = q.n_silence;
+      e->topk_pool_used += q.n_silence;
+    }
     if (q.top_k_schedule && q.n_top_k_schedule > 0) {
       T5G_CHECK(e->topk_pool_used + q.n_top_k_schedule <= e->topk_pool_cap, T5G_ERR_OOM, "top_k schedule pool exhausted");
       for (int i = 0; i < q.n_top_k_schedule; ++i)
@@ -916,6 +924,8 @@ extern "C" int t5g_sample(T5GEngine* e, float* logits, const T5GSampleRow* rows,
     s.budget_limit = (int)std::floor((double)r.target_total - (double)r.prompt_offset + (double)c.encodec_sr * (double)c.extra_cutoff);
     s.top_k = r.sampling.top_k; s.top_p = r.sampling.top_p; s.min_p = r.sampling.min_p; s.temperature = r.sampling.temperature;
     s.uniforms = e->d_sample_u + i; s.n_uniforms = 1; s.topk_sched_off = -1;
+    s.prev_token = r.prev_token; s.consec_silence = r.consec_silence_count; s.stop_repetition = e->sample_stop_repetition;
+    s.silence_off = 0; s.n_silence = e->n_sample_silence;
     // the kernel indexes uniforms by n_generated (clamped to n_uniforms-1 = 0)
     us[i] = r.u;
   }
@@ -924,7 +934,7 @@ extern "C" int t5g_sample(T5GEngine* e, float* logits, const T5GSampleRow* rows,
   d_amax = d_tok + n_rows;
   CU(cudaMemcpyAsync(e->d_sample_u, us.data(), sizeof(float) * n_rows, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(e->d_sample_slots, sd.data(), sizeof(SlotDev) * n_rows, cudaMemcpyHostToDevice, st));
-  SamplerArgs s{}; s.logits = logits; s.ld = e->V; s.V = e->V; s.slots = e->d_sample_slots; s.topk_sched_pool = e->d_topk_pool;
+  SamplerArgs s{}; s.logits = logits; s.ld = e->V; s.V = e->V; s.slots = e->d_sample_slots; s.topk_sched_pool = e->d_sample_silence;
   s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
   s.tokens_out = d_tok; s.tokens_stride = 1; s.flat_tokens = 1; s.argmax_out = d_amax; s.rows = n_rows; s.host_mirror = nullptr;
   cudaError_t er = launch_sampler(s, st, false);
@@ -934,6 +944,14 @@ extern "C" int t5g_sample(T5GEngine* e, float* logits, const T5GSampleRow* rows,
   if (er == cudaSuccess) er = cudaStreamSynchronize(st);
   cudaFree(d_tok);
   CU(er);
+  return T5G_OK;
+}
+
+extern "C" int t5g_sample_set_silence(T5GEngine* e, const int32_t* toks, int n, int stop_repetition) {
+  T5G_CHECK(e && n >= 0 && n <= 256 && (n == 0 || toks), T5G_ERR_INVALID, "bad arguments (at most 256 silence tokens)");
+  T5G_CUDA(cudaSetDevice(e->device));
+  if (n > 0) CU(cudaMemcpy(e->d_sample_silence, toks, sizeof(int) * n, cudaMemcpyHostToDevice));
+  e->n_sample_silence = n; e->sample_stop_repetition = stop_repetition;
   return T5G_OK;
 }
 

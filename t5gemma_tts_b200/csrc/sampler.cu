@@ -79,6 +79,16 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
   if (tid == 0) {
     if (eff_len == 0) lg[eos] = -1e9f;
     if (n_gen <= a.encodec_sr / 5) lg[eos] = -10000.0f;
+    // silence-repetition penalty (models/t5gemma.py:999-1011), in place like the reference
+    if (sl.stop_repetition > 0 && sl.n_silence > 0 && sl.prev_token >= 0 && sl.consec_silence > sl.stop_repetition) {
+      bool in_set = false;
+      for (int i = 0; i < sl.n_silence; ++i) in_set |= (a.topk_sched_pool[sl.silence_off + i] == sl.prev_token);
+      if (in_set) {
+        const float f = (float)(sl.consec_silence - (sl.stop_repetition - 1));
+        const float v = lg[sl.prev_token];
+        lg[sl.prev_token] = (v < 0.f) ? __fmul_rn(v, f) : __fdiv_rn(v, f);
+      }
+    }
     S.n_cand = 0; S.overflow = 0;
   }
   __syncthreads();
@@ -385,6 +395,12 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
     if (a.tokens_out) a.tokens_out[(size_t)row * a.tokens_stride + (a.flat_tokens ? 0 : n_gen)] = token;
     if (a.argmax_out) a.argmax_out[row] = amax;
     if (S.overflow) sl.error |= 1;
+    {   // models/t5gemma.py:1050-1054
+      bool in_set = false;
+      for (int i = 0; i < sl.n_silence; ++i) in_set |= (a.topk_sched_pool[sl.silence_off + i] == token);
+      sl.consec_silence = (in_set && token == sl.prev_token) ? sl.consec_silence + 1 : 0;
+      sl.prev_token = token;
+    }
     sl.n_generated = n_gen + 1;
     const int new_len = cur_len + 1;
     sl.cur_len = new_len;

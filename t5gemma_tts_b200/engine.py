@@ -42,6 +42,8 @@ class GenerationRequest:
     max_new_tokens: int = 0                       # 0 = reference stop rules only
     uniforms: Optional[torch.Tensor] = None       # explicit U[0,1) draws (CUDA fp32); default torch.rand
     forced_tokens: Optional[Sequence[int]] = None # teacher forcing (parity tests)
+    stop_repetition: int = 3                      # inference_tts(stop_repetition=...)
+    silence_tokens: Optional[Sequence[int]] = None   # inference_tts(silence_tokens=...), [] in every shipped caller
 
 
 class T5GemmaVoiceEngine:
@@ -235,7 +237,16 @@ class T5GemmaVoiceEngine:
             else:
                 q.forced_tokens = None
                 q.n_forced = 0
-            keep.append((text, dec, sched, forced))
+            sil = None
+            if r.silence_tokens is not None and len(r.silence_tokens) > 0:
+                sil = np.ascontiguousarray(np.asarray(r.silence_tokens, dtype=np.int32))
+                q.silence_tokens = sil.ctypes.data_as(C.POINTER(C.c_int32))
+                q.n_silence = len(sil)
+            else:
+                q.silence_tokens = None
+                q.n_silence = 0
+            q.stop_repetition = int(r.stop_repetition)
+            keep.append((text, dec, sched, forced, sil))
             self._keep[slot] = u
         torch.cuda.current_stream(self.device).synchronize()     # uniforms were produced on torch's stream
         L.check(self.lib, self.lib.t5g_prefill(self._h, arr, len(reqs), self._stream()))
@@ -286,6 +297,10 @@ class T5GemmaVoiceEngine:
         L.check(self.lib, self.lib.t5g_prefill_logits(self._h, slot, out.ctypes.data_as(C.POINTER(C.c_float)), self._stream()))
         return out
 
+    def set_sample_silence(self, silence_tokens: Sequence[int], stop_repetition: int = 3):
+        arr = np.ascontiguousarray(np.asarray(list(silence_tokens), dtype=np.int32))
+        L.check(self.lib, self.lib.t5g_sample_set_silence(self._h, arr.ctypes.data_as(C.POINTER(C.c_int32)), len(arr), int(stop_repetition)))
+
     def sample(self, logits: torch.Tensor, rows: Sequence[dict]) -> Tuple[np.ndarray, np.ndarray]:
         """Standalone sampler S on CUDA fp32 logits [n, n_audio_tokens] (edited in place)."""
         assert logits.is_cuda and logits.dtype == torch.float32 and logits.is_contiguous()
@@ -299,6 +314,7 @@ class T5GemmaVoiceEngine:
             a.u = float(r.get("u", 0.5))
             a.cur_num_gen, a.current_length = int(r["cur_num_gen"]), int(r["current_length"])
             a.prompt_offset, a.target_total, a.n_text = int(r["prompt_offset"]), int(r["target_total"]), int(r.get("n_text", 1))
+            a.prev_token, a.consec_silence_count = int(r.get("prev_token", -1)), int(r.get("consec_silence_count", 0))
         tok = np.zeros(n, dtype=np.int32)
         amax = np.zeros(n, dtype=np.int32)
         torch.cuda.current_stream(self.device).synchronize()
@@ -369,9 +385,6 @@ class T5GemmaVoiceEngine:
             raise ValueError("XCodec2 inference expects n_codebooks=1.")
         if multi_trial:
             logging.warning("multi_trial is unsupported and will be ignored.")
-        if silence_tokens and stop_repetition > 0:
-            raise NotImplementedError("silence-repetition penalty (models/t5gemma.py:999-1011) is dormant in every "
-                                      "reference caller and not implemented")
         batch_size = x.shape[0]
         assert batch_size == 1, "Current implementation only supports batch size 1."
         S = int(x_lens[0].item())
@@ -382,6 +395,7 @@ class T5GemmaVoiceEngine:
         req = GenerationRequest(text_ids=text, prompt_ids=prompt, target_total=int(tgt_y_lens[0].item()),
                                 prompt_frames=kwargs.get("prompt_frames", y_len), top_k=top_k, top_p=top_p, min_p=min_p,
                                 temperature=temperature, max_new_tokens=int(kwargs.get("max_new_tokens", 0) or 0),
+                                stop_repetition=int(stop_repetition), silence_tokens=list(silence_tokens or []),
                                 uniforms=kwargs.get("uniforms"))
         gen = self.generate([req], chunk_steps=int(kwargs.get("chunk_steps", 32)))[0]
         if self.cfg.special_first:

@@ -44,6 +44,7 @@ class T5GRequest(C.Structure):
         ("top_k_schedule", C.POINTER(C.c_int32)), ("n_top_k_schedule", C.c_int32),
         ("uniforms", C.c_void_p), ("n_uniforms", C.c_int32),
         ("forced_tokens", C.POINTER(C.c_int32)), ("n_forced", C.c_int32),
+        ("silence_tokens", C.POINTER(C.c_int32)), ("n_silence", C.c_int32), ("stop_repetition", C.c_int32),
     ]
 
 
@@ -54,7 +55,7 @@ class T5GSlotState(C.Structure):
 class T5GSampleRow(C.Structure):
     _fields_ = [("sampling", T5GSampling), ("u", C.c_float), ("cur_num_gen", C.c_int32),
                 ("current_length", C.c_int32), ("prompt_offset", C.c_int32), ("target_total", C.c_int32),
-                ("n_text", C.c_int32)]
+                ("n_text", C.c_int32), ("prev_token", C.c_int32), ("consec_silence_count", C.c_int32)]
 
 
 # every symbol include/t5gtts.h declares: name -> (restype, argtypes)
@@ -75,6 +76,7 @@ SYMBOLS = {
     "t5g_read_logits": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P]),
     "t5g_prefill_logits": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P]),
     "t5g_sample": (C.c_int, [_P, _P, C.POINTER(T5GSampleRow), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
+    "t5g_sample_set_silence": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int, C.c_int]),
     "t5g_launch_count": (C.c_int64, [_P]),
     "t5g_weight_bytes_per_step": (C.c_int64, [_P]),
     "t5g_kv_bytes_per_token": (C.c_int64, [_P]),

@@ -123,3 +123,17 @@ def test_stop_rules():
     assert sampler_oracle.sample_step(lg, cur_num_gen=259, current_length=265, **kw) == 7
     lg = base.copy()
     assert sampler_oracle.sample_step(lg, cur_num_gen=260, current_length=266, **kw) == eos
+
+
+def test_silence_repetition_penalty_matches_reference():
+    """models/t5gemma.py:999-1011,1050-1054 pinned through the reference's own sample_helper (crafted head logits)."""
+    orc = fixtures.load_oracle("tinyA_eager")
+    c = fixtures.load_case("tinyA_eager_silence")
+    x = torch.from_numpy(c["x"])
+    base = c["base_logits"]
+    res, gen = orc.inference_tts(x, torch.tensor([x.shape[1]]), torch.zeros((1, 0, 1), dtype=torch.long),
+                                 torch.tensor([int(c["tgt"])]), top_k=1, top_p=1.0, temperature=1.0, prompt_frames=0,
+                                 stop_repetition=int(c["stop_repetition"]), silence_tokens=c["silence_tokens"].tolist(),
+                                 logits_hook=lambda lg, step: base.copy())
+    assert np.array_equal(gen.numpy(), c["gen"])
+    assert gen[0, 0, :10].tolist() == [7, 7, 7, 7, 9, 7, 7, 7, 7, 9]

@@ -96,3 +96,34 @@ def test_sampler_rejects_unsupported():
     dl = torch.zeros(1, eng.cfg.n_audio_tokens, device="cuda")
     with pytest.raises(T5GError):
         eng.sample(dl, [dict(top_k=0, top_p=0.5, cur_num_gen=0, current_length=1, prompt_offset=1, target_total=10)])
+
+
+def test_sampler_silence_penalty_bit_exact():
+    """Silence-repetition penalty + state update (models/t5gemma.py:999-1011,1050-1054) vs the numpy oracle."""
+    eng = engine_for("tinyA_eager")
+    V, eos = eng.cfg.n_audio_tokens, eng.cfg.stop_token
+    silence = [7, 11, 42]
+    eng.set_sample_silence(silence, stop_repetition=2)
+    rng = np.random.default_rng(3)
+    n = 96
+    logits = (rng.standard_normal((n, V)) * 2).astype(np.float32)
+    rows, want = [], []
+    for i in range(n):
+        prev = [7, 11, 42, 5, -1][i % 5]
+        consec = int(rng.integers(0, 7))
+        logits[i, 7] = 6.0 if i % 2 else -6.0           # both branches of the penalty (divide / multiply)
+        p = dict(top_k=[1, 30][i % 2], top_p=0.9, temperature=1.0, u=float(np.float32(rng.random())), cur_num_gen=20,
+                 current_length=40, prompt_offset=6, target_total=400, prev_token=prev, consec_silence_count=consec)
+        rows.append(p)
+        lg = logits[i].copy()
+        tok = sampler_oracle.sample_step(lg, eos=eos, cur_num_gen=20, current_length=40, prompt_offset=6, target_total=400,
+                                         top_k=p["top_k"], top_p=0.9, temperature=1.0, u=p["u"], prev_token=prev,
+                                         consec_silence_count=consec, stop_repetition=2, silence_tokens=tuple(silence))
+        want.append((tok, lg))
+    dl = torch.from_numpy(logits).cuda()
+    tok, _ = eng.sample(dl, rows)
+    got_l = dl.cpu().numpy()
+    for i in range(n):
+        assert int(tok[i]) == want[i][0], i
+        assert np.array_equal(got_l[i], want[i][1]), i       # the in-place edit is bit-identical
+    eng.set_sample_silence([], 3)

@@ -72,6 +72,7 @@ struct T5GEngine {
   int* h_picks = nullptr; int* d_picks = nullptr;             // mapped pinned [max_slots][max_dec_len]
   int* d_forced = nullptr;                                    // [max_slots][max_dec_len]
   int* d_topk_pool = nullptr; int topk_pool_cap = 0, topk_pool_used = 0;   // int pool: top-k schedules + silence token lists
+  unsigned long long* d_samp_u64 = nullptr; float* d_samp_f32 = nullptr; int samp_scratch_rows = 0;   // sampler general path
   int* d_sample_silence = nullptr; int n_sample_silence = 0, sample_stop_repetition = 0;   // t5g_sample settings
   // prefill workspaces (T = max_prefill_tokens)
   float *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_memory = nullptr, *p_ckv = nullptr, *p_final = nullptr;
@@ -312,6 +313,8 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   T5G_CUDA(cudaMemset(e->d_hA, 0, sizeof(float) * (size_t)B * d));
   T5G_CUDA(cudaMemset(e->d_hB, 0, sizeof(float) * (size_t)B * d));
   DM(e->d_sample_u, 4096); DM(e->d_sample_slots, 4096); DM(e->d_sample_silence, 256);
+  e->samp_scratch_rows = std::max(B, 16);
+  { const size_t V8 = ((size_t)e->V + 7) & ~(size_t)7; DM(e->d_samp_u64, (size_t)e->samp_scratch_rows * 2 * V8); DM(e->d_samp_f32, (size_t)e->samp_scratch_rows * 2 * V8); }
   DM(e->d_attn, (size_t)B * QD); DM(e->d_trace, 2 * T5G_TRACE_STRIDE);
   DM(e->d_xn, (size_t)B * d); DM(e->d_attn_bf, (size_t)B * QD); DM(e->d_act_bf, (size_t)B * I); DM(e->d_t1_bf, (size_t)B * d);
   T5G_CUDA(cudaDeviceSynchronize());
@@ -426,9 +429,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     const T5GSampling& s = q.sampling;
     const bool minp = s.min_p > 0.f && s.min_p < 1.f;
     T5G_CHECK(s.temperature > 0.f, T5G_ERR_INVALID, "request %d: temperature must be > 0", r);
-    if (!q.top_k_schedule)
-      T5G_CHECK(minp || s.top_k > 0 || s.top_p >= 1.0f, T5G_ERR_UNSUPPORTED, "request %d: top_p<1 without top_k>0 needs a full-vocabulary sort (not implemented)", r);
-    T5G_CHECK(s.top_k <= 1024, T5G_ERR_UNSUPPORTED, "request %d: top_k > 1024 not supported", r);
+    (void)minp;
     Te += q.n_text; Td += q.n_dec;
   }
   T5G_CHECK(Te <= c.max_prefill_tokens && Td <= c.max_prefill_tokens, T5G_ERR_INVALID, "prefill tokens (%d text, %d audio) exceed max_prefill_tokens %d", Te, Td, c.max_prefill_tokens);
@@ -476,7 +477,6 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     if (q.top_k_schedule && q.n_top_k_schedule > 0) {
       T5G_CHECK(e->topk_pool_used + q.n_top_k_schedule <= e->topk_pool_cap, T5G_ERR_OOM, "top_k schedule pool exhausted");
       for (int i = 0; i < q.n_top_k_schedule; ++i)
-        T5G_CHECK((q.top_k_schedule[i] > 0 && q.top_k_schedule[i] <= 1024) || (q.sampling.top_p >= 1.0f && q.top_k_schedule[i] <= 1024), T5G_ERR_UNSUPPORTED, "request %d: schedule entry needs top_k in [1,1024] when top_p<1", r);
       CU(cudaMemcpyAsync(e->d_topk_pool + e->topk_pool_used, q.top_k_schedule, sizeof(int) * q.n_top_k_schedule, cudaMemcpyHostToDevice, st));
       sd.topk_sched_off = e->topk_pool_used; sd.n_topk_sched = q.n_top_k_schedule;
       e->topk_pool_used += q.n_top_k_schedule;
@@ -682,6 +682,7 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
     s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
     s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = B; s.host_mirror = e->d_mirror;
     s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
+    s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32;
     s.trace = next_trace();
     CU(launch_sampler(s, st, pdl)); nl++; }
   // ---- 26 decoder layers at q_len = 1 ----
@@ -748,6 +749,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
     s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
     s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = B; s.host_mirror = e->d_mirror;
     s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
+    s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32;
     CU(launch_sampler(s, st, pdl_samp)); nl++; }
   CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st, pdl_emb)); nl++;
   for (int l = 0; l < c.n_dec_layers; ++l) {
@@ -916,8 +918,7 @@ extern "C" int t5g_sample(T5GEngine* e, float* logits, const T5GSampleRow* rows,
     const T5GSampleRow& r = rows[i];
     const bool minp = r.sampling.min_p > 0.f && r.sampling.min_p < 1.f;
     T5G_CHECK(r.sampling.temperature > 0.f, T5G_ERR_INVALID, "row %d: temperature must be > 0", i);
-    T5G_CHECK(minp || r.sampling.top_k > 0 || r.sampling.top_p >= 1.0f, T5G_ERR_UNSUPPORTED, "row %d: top_p<1 without top_k>0 not implemented", i);
-    T5G_CHECK(r.sampling.top_k <= 1024, T5G_ERR_UNSUPPORTED, "row %d: top_k > 1024 not supported", i);
+    (void)minp;
     SlotDev& s = sd[i]; memset(&s, 0, sizeof(s));
     s.active = 1; s.n_generated = r.cur_num_gen; s.cur_len = r.current_length; s.prompt_offset = r.prompt_offset; s.target_total = r.target_total;
     s.est_total = std::max(r.target_total + 1, 1); s.n_text = r.n_text;
@@ -936,9 +937,17 @@ extern "C" int t5g_sample(T5GEngine* e, float* logits, const T5GSampleRow* rows,
   CU(cudaMemcpyAsync(e->d_sample_slots, sd.data(), sizeof(SlotDev) * n_rows, cudaMemcpyHostToDevice, st));
   SamplerArgs s{}; s.logits = logits; s.ld = e->V; s.V = e->V; s.slots = e->d_sample_slots; s.topk_sched_pool = e->d_sample_silence;
   s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
-  s.tokens_out = d_tok; s.tokens_stride = 1; s.flat_tokens = 1; s.argmax_out = d_amax; s.rows = n_rows; s.host_mirror = nullptr;
-  cudaError_t er = launch_sampler(s, st, false);
-  e->launches++;
+  s.tokens_stride = 1; s.flat_tokens = 1; s.host_mirror = nullptr;
+  s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32;
+  cudaError_t er = cudaSuccess;
+  for (int off = 0; off < n_rows && er == cudaSuccess; off += e->samp_scratch_rows) {     // scratch covers samp_scratch_rows rows
+    SamplerArgs c2 = s;
+    c2.rows = std::min(e->samp_scratch_rows, n_rows - off);
+    c2.logits = logits + (size_t)off * e->V; c2.slots = e->d_sample_slots + off;
+    c2.tokens_out = d_tok + off; c2.argmax_out = d_amax + off;
+    er = launch_sampler(c2, st, false);
+    e->launches++;
+  }
   if (er == cudaSuccess) er = cudaMemcpyAsync(out_tokens, d_tok, sizeof(int) * n_rows, cudaMemcpyDeviceToHost, st);
   if (er == cudaSuccess && out_argmax) er = cudaMemcpyAsync(out_argmax, d_amax, sizeof(int) * n_rows, cudaMemcpyDeviceToHost, st);
   if (er == cudaSuccess) er = cudaStreamSynchronize(st);

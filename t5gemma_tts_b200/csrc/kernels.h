@@ -112,6 +112,8 @@ struct SamplerArgs {
   float* rope_out; const float* inv_freq; int head_dim;   // optional: cos|sin table of the new position per row
   unsigned long long* trace;
   PrefetchRange pf[4];
+  unsigned long long* scratch_u64;    // general path: [rows][2][V8] composites (V8 = V rounded up to 8), may be null
+  float* scratch_f32;                 // [rows][2][V8]
   int* argmax_out;                    // optional [rows]
   int* picks_out;                     // optional [slot][tokens_stride]: engine's own sampled id per step
   const int* forced_pool;             // optional [slot][tokens_stride]: teacher-forced ids

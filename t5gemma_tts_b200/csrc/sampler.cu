@@ -51,6 +51,7 @@ struct Shared {
   unsigned tmax[SAMP_THREADS];       // per-thread maxima (lower-bound selection for 32 < k <= 1024)
   unsigned redk[32];
   unsigned lb; int n_surv;
+  unsigned whist[32][16];            // full-sort path: per-warp digit counts / bases
   unsigned hist[256];
   unsigned long long cand[CAND_CAP];
   float e[CAND_CAP];
@@ -59,6 +60,154 @@ struct Shared {
   unsigned prefix; int kth; unsigned n_cand; int overflow;
   float zmax; int amax; int n_keep; float total;
 };
+
+
+// ---- general path helpers (survivor sets larger than CAND_CAP: nucleus sampling without top-k, top_k > 1024,
+//      pathological ties): stable LSD radix sort (4-bit digits, 8 passes) of all V composites in global scratch by
+//      one CTA.  Every warp owns a contiguous block so that ballot/match ranking keeps the sort stable. ------------
+__device__ __noinline__ void full_sort_desc(unsigned long long* src, unsigned long long* dst, int V, Shared& S, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const int BL = ((V + 31) / 32 + 31) / 32 * 32;                 // block per warp, multiple of 32
+  const int w_begin = min(V, warp * BL), w_end = min(V, w_begin + BL);
+  for (int shift = 32; shift < 64; shift += 4) {
+    if (tid < 512) (&S.whist[0][0])[tid] = 0u;
+    __syncthreads();
+    for (int i0 = w_begin; i0 < w_end; i0 += 32) {
+      const int i = i0 + lane;
+      const bool ok = i < w_end;
+      const unsigned d = ok ? 15u - (unsigned)((src[i] >> shift) & 15ull) : 0u;
+      const unsigned act = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const unsigned peers = __match_any_sync(act, d);
+        if ((int)(__ffs(peers) - 1) == lane) S.whist[warp][d] += (unsigned)__popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (tid == 0) {                                              // exclusive scan, digit-major then warp
+      unsigned run = 0;
+      for (int d = 0; d < 16; ++d)
+        for (int w = 0; w < 32; ++w) { const unsigned c = S.whist[w][d]; S.whist[w][d] = run; run += c; }
+    }
+    __syncthreads();
+    for (int i0 = w_begin; i0 < w_end; i0 += 32) {
+      const int i = i0 + lane;
+      const bool ok = i < w_end;
+      const unsigned long long v = ok ? src[i] : 0ull;
+      const unsigned d = ok ? 15u - (unsigned)((v >> shift) & 15ull) : 0u;
+      const unsigned act = __ballot_sync(0xffffffffu, ok);
+      unsigned peers = 0, base = 0;
+      if (ok) {
+        peers = __match_any_sync(act, d);
+        base = S.whist[warp][d];
+      }
+      __syncwarp();
+      if (ok) {
+        dst[base + (unsigned)__popc(peers & ((1u << lane) - 1u))] = v;
+        if ((int)(__ffs(peers) - 1) == lane) S.whist[warp][d] = base + (unsigned)__popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    unsigned long long* t = src; src = dst; dst = t;
+  }
+  // 8 passes: the result is back in the original `src` buffer
+}
+
+// sequential left-to-right fp32 sum of e[0..n) by ONE thread (the oracle's order), 8 loads in flight
+__device__ float seq_sum_global(const float* e, int n) {
+  float s = 0.f;
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    const float4 a = *reinterpret_cast<const float4*>(e + i), b = *reinterpret_cast<const float4*>(e + i + 4);
+    s = __fadd_rn(s, a.x); s = __fadd_rn(s, a.y); s = __fadd_rn(s, a.z); s = __fadd_rn(s, a.w);
+    s = __fadd_rn(s, b.x); s = __fadd_rn(s, b.y); s = __fadd_rn(s, b.z); s = __fadd_rn(s, b.w);
+  }
+  for (; i < n; ++i) s = __fadd_rn(s, e[i]);
+  return s;
+}
+
+// first i in [0,n) whose running sequential sum (after adding p[i]) exceeds x, else -1; ONE thread, oracle order
+__device__ int seq_first_exceed(const float* p, int n, float x) {
+  float c = 0.f;
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    const float4 a = *reinterpret_cast<const float4*>(p + i), b = *reinterpret_cast<const float4*>(p + i + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c = __fadd_rn(c, v[j]); if (c > x) return i + j; }
+  }
+  for (; i < n; ++i) { c = __fadd_rn(c, p[i]); if (c > x) return i; }
+  return -1;
+}
+
+// General path: all V tokens sorted (value desc, index asc); top-k / min-p / top-p are prefix cuts of that order and
+// the sums run sequentially exactly as in oracle/sampler_oracle.py.  Called by every thread of the CTA.
+__device__ __noinline__ int sample_large(const SamplerArgs& a, Shared& S, int row, int tid, const float* lg, int V, float T, bool scaled,
+                            float zmax, int top_k, float top_p, float min_p, bool minp_mode, const SlotDev& sl, int n_gen) {
+  const int Vs = (V + 7) & ~7;
+  unsigned long long* A = a.scratch_u64 + (size_t)row * 2 * Vs;
+  unsigned long long* Bf = A + Vs;
+  float* E = a.scratch_f32 + (size_t)row * 2 * Vs;
+  float* P = E + Vs;
+  for (int i = tid; i < V; i += SAMP_THREADS) {
+    const float v = lg[i];
+    const float z = scaled ? __fdiv_rn(v, T) : v;
+    A[i] = ((unsigned long long)key_of(z) << 32) | (0xffffffffu - (unsigned)i);
+  }
+  __syncthreads();
+  full_sort_desc(A, Bf, V, S, tid);
+  if (tid == 0) S.n_surv = V;
+  __syncthreads();
+  if (minp_mode) {
+    const float tot = S.total;
+    for (int i = tid; i < V; i += SAMP_THREADS) {
+      const bool keep = !(__fdiv_rn(det_exp(__fsub_rn(val_of((unsigned)(A[i] >> 32)), zmax)), tot) < min_p);
+      const bool keep_next = (i + 1 < V) && !(__fdiv_rn(det_exp(__fsub_rn(val_of((unsigned)(A[i + 1] >> 32)), zmax)), tot) < min_p);
+      if (keep && !keep_next) S.n_surv = i + 1;
+    }
+  } else if (top_k > 0) {
+    const int k = min(max(top_k, 1), V);
+    const unsigned thr = (unsigned)(A[k - 1] >> 32);
+    for (int i = tid; i < V; i += SAMP_THREADS) {
+      const bool in = (unsigned)(A[i] >> 32) >= thr;
+      const bool next_in = (i + 1 < V) && ((unsigned)(A[i + 1] >> 32) >= thr);
+      if (in && !next_in) S.n_surv = i + 1;
+    }
+  }
+  __syncthreads();
+  const int n = S.n_surv;
+  const float z0 = val_of((unsigned)(A[0] >> 32));
+  for (int i = tid; i < n; i += SAMP_THREADS) E[i] = det_exp(__fsub_rn(val_of((unsigned)(A[i] >> 32)), z0));
+  __syncthreads();
+  if (tid == 0) S.n_keep = n;
+  if (top_p < 1.0f && !minp_mode) {
+    if (tid == 0) S.total = seq_sum_global(E, n);
+    __syncthreads();
+    const float s = S.total;
+    for (int i = tid; i < n; i += SAMP_THREADS) P[i] = __fdiv_rn(E[i], s);
+    __syncthreads();
+    if (tid == 0) {
+      const int j = seq_first_exceed(P, n - 1, top_p);      // cum through i exceeds p -> token i+1 (and later) removed
+      S.n_keep = (j < 0) ? n : j + 1;
+    }
+  }
+  __syncthreads();
+  const int n_keep = S.n_keep;
+  if (tid == 0) S.total = seq_sum_global(E, n_keep);
+  __syncthreads();
+  const float s2 = S.total;
+  for (int i = tid; i < n_keep; i += SAMP_THREADS) P[i] = __fdiv_rn(E[i], s2);
+  __syncthreads();
+  if (tid == 0) {
+    const float u = sl.uniforms ? sl.uniforms[min(n_gen, max(sl.n_uniforms - 1, 0))] : 0.5f;
+    const int j = seq_first_exceed(P, n_keep, u);
+    const int pick = (j < 0) ? n_keep - 1 : j;
+    S.n_keep = (int)(0xffffffffu - (unsigned)(A[pick] & 0xffffffffull));
+  }
+  __syncthreads();
+  return S.n_keep;
+}
 
 __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -146,7 +295,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
   const float min_p = sl.min_p;
   const int nchunk = (V + CHUNK - 1) / CHUNK;
   bool have_csum = false;
-  bool filtered = false;
+  bool filtered = false, minp_mode = false;
 
   // (3) min-p (models/utils.py:72-80): full softmax with the oracle's chunked sum
   if (min_p > 0.f && min_p < 1.f) {
@@ -171,7 +320,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
       }
     }
     __syncthreads();
-    if (S.n_cand > 0) { filtered = true; top_k = 0; top_p = 1.0f; }
+    if (S.n_cand > 0) { filtered = true; minp_mode = true; top_k = 0; top_p = 1.0f; }
   }
 
   // (4) top-k, ties kept (models/utils.py:82-86).
@@ -180,7 +329,9 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
   // of the top-k and of all ties at the k-th value).  Candidates are re-read exactly, sorted (value desc,
   // index asc) and cut at the k-th value.  Falls back to the exact radix select if the superset overflows.
   bool fast_done = false;
-  if (!filtered && top_k > 0 && use_hi) {
+  bool large = !filtered && ((top_k <= 0 && top_p < 1.0f) || top_k > 1024);   // needs the full sort
+  if (filtered && S.overflow) { large = true; filtered = false; }               // min-p kept more than CAND_CAP
+  if (!large && !filtered && top_k > 0 && use_hi) {
     const int k = min(max(top_k, 1), V);
     if (k <= 32) {
       if (warp == 0) {
@@ -252,7 +403,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
       __syncthreads();
     }
   }
-  if (!filtered && top_k > 0) {
+  if (!large && !filtered && top_k > 0) {
     int k = min(max(top_k, 1), V);
     unsigned prefix = 0, mask = 0;
     for (int shift = 24; shift >= 0; shift -= 8) {
@@ -291,11 +442,14 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
       }
     }
     __syncthreads();
-    filtered = true;
+    if (S.overflow) large = true; else filtered = true;       // > CAND_CAP ties at the k-th value: full sort
   }
 
   int token = 0;
-  if (filtered) {
+  if (large) {
+    if (!a.scratch_u64) { if (tid == 0) sl.error |= 2; token = S.amax; }
+    else token = sample_large(a, S, row, tid, lg, V, T, scaled, zmax, top_k, top_p, min_p, minp_mode, sl, n_gen);
+  } else if (filtered) {
     // sort survivors (value desc, index asc): bitonic on the 64-bit composite, descending
     int n;
     if (fast_done) {

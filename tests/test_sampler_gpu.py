@@ -90,12 +90,39 @@ def test_sampler_known_answers_appendix_a():
         assert set(tok.tolist()) == want, (kw, set(tok.tolist()))
 
 
-def test_sampler_rejects_unsupported():
-    eng = engine_for("tinyA_eager")
-    from t5gemma_tts_b200 import T5GError
-    dl = torch.zeros(1, eng.cfg.n_audio_tokens, device="cuda")
-    with pytest.raises(T5GError):
-        eng.sample(dl, [dict(top_k=0, top_p=0.5, cur_num_gen=0, current_length=1, prompt_offset=1, target_total=10)])
+LARGE_PARAMS = [dict(top_k=0, top_p=0.9, temperature=1.0), dict(top_k=-100, top_p=0.5, temperature=0.8),
+                dict(top_k=2000, top_p=1.0, temperature=1.0), dict(top_k=5000, top_p=0.95, temperature=1.2),
+                dict(top_k=0, top_p=0.999, temperature=1.0), dict(top_k=30, top_p=0.9, min_p=1e-5, temperature=1.0)]
+
+
+def _run_large(eng, V, eos, scale, n_rows, seed, ties=False):
+    rng = np.random.default_rng(seed)
+    logits = (rng.standard_normal((n_rows, V)) * scale).astype(np.float32)
+    if ties:
+        logits = np.round(logits * 4) / 4          # massive ties: > CAND_CAP equal values around any threshold
+    rows, want = [], []
+    for i in range(n_rows):
+        p = dict(LARGE_PARAMS[i % len(LARGE_PARAMS)])
+        p.update(u=float(np.float32(rng.random())), cur_num_gen=20, current_length=40, prompt_offset=6, target_total=400)
+        rows.append(p)
+        want.append(sampler_oracle.sample_step(logits[i].copy(), eos=eos, cur_num_gen=20, current_length=40,
+                                               prompt_offset=6, target_total=400, top_k=p.get("top_k", -100),
+                                               top_p=p.get("top_p", 1.0), min_p=p.get("min_p", 0.0),
+                                               temperature=p.get("temperature", 1.0), u=p["u"]))
+    tok, _ = eng.sample(torch.from_numpy(logits).cuda(), rows)
+    assert np.array_equal(tok, np.array(want)), (tok, want)
+
+
+def test_sampler_general_path_bit_exact():
+    """Nucleus sampling without top-k, top_k > 1024, min-p with many survivors, and > 2048 ties at the k-th value all
+    take the full-sort path (stable LSD radix sort in global scratch + the oracle's sequential sums)."""
+    eng = _full_vocab_engine()
+    _run_large(eng, 65541, 65539, 0.2, 18, 11)
+    _run_large(eng, 65541, 65539, 3.0, 12, 12)
+    _run_large(eng, 65541, 65539, 1.0, 6, 13, ties=True)
+    eng.close()
+    small = engine_for("tinyA_eager")
+    _run_large(small, small.cfg.n_audio_tokens, small.cfg.stop_token, 2.0, 48, 14)
 
 
 def test_sampler_silence_penalty_bit_exact():

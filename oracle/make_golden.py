@@ -93,6 +93,27 @@ def silence_case(model):
                 silence_tokens=np.array([7, 11], dtype=np.int64))
 
 
+def glue_cases():
+    """_strip_sep_and_eos (inference_tts_utils.py:323-354, a nested function) extracted by AST and run on random frames."""
+    import ast
+    from typing import Optional
+    src = open(os.path.join(ref_loader.REFERENCE_ROOT, "inference_tts_utils.py")).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "_strip_sep_and_eos")
+    ns = {"torch": torch, "Optional": Optional}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_strip", "exec"), ns)
+    rng = np.random.default_rng(3)
+    out = {}
+    for i in range(6):
+        T = int(rng.integers(1, 40))
+        fr = rng.integers(95, 105, (1, 1, T))
+        fr[0, 0, -1] = 103
+        if i % 2:
+            fr[0, 0, T // 2] = 104
+        out[f"in_{i}"] = fr
+        out[f"out_{i}"] = ns["_strip_sep_and_eos"](torch.from_numpy(fr), 104, 103).numpy()
+    np.savez_compressed(os.path.join(OUT, "glue_strip.npz"), **out)
+
+
 def sampler_cases():
     U = ref_loader.load_reference_sampling()
     rows = []
@@ -161,6 +182,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "case_tinyB_eager_prompt.npz"), **c)
     print("tinyB gen len", c["gen"].shape)
     sampler_cases()
+    glue_cases()
 
 
 if __name__ == "__main__":

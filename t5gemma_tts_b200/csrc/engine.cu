@@ -189,7 +189,7 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // ---- GEMM dispatch (prefill / batched path) ----------------------------------------------------
 cudaError_t gemm(T5GEngine* e, const bf16* A, const bf16* W, int M, int N, int K, int epi, const float* bias,
                  void* out, int ldo, cudaStream_t st) {
-  GemmArgs g{A, W, M, N, K, epi, bias, out, ldo};
+  GemmArgs g{A, W, M, N, K, epi, bias, out, ldo, 0};
   e->launches++;
   if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms);
   return launch_gemm_simt(g, st);
@@ -734,8 +734,8 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
   int mask = 31; if (const char* m = getenv("T5G_PDL_MASK")) mask = atoi(m);
   const bool pdl_norm = pdl && (mask & 1), pdl_gemm = pdl && (mask & 2), pdl_attn = pdl && (mask & 4), pdl_samp = pdl && (mask & 8), pdl_emb = pdl && (mask & 16);
   auto G = [&](const bf16* A, const bf16* W, int N, int K, int epi, const float* bias, void* out, int ldo) -> cudaError_t {
-    GemmArgs g{A, W, B, N, K, epi, bias, out, ldo};
-    nl += 2;                                           // kernel (+ memset when split-K)
+    GemmArgs g{A, W, B, N, K, epi, bias, out, ldo, 1};   // fp32 outputs are pre-zeroed by the preceding norm kernel
+    nl += 1;
     if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms, pdl_gemm);
     return launch_gemm_simt(g, st);
   };
@@ -754,8 +754,8 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
   CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st, pdl_emb)); nl++;
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
-    if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm));
-    else CU(launch_norm(h, e->d_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm));
+    if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d));
+    else CU(launch_norm(h, e->d_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d));
     nl++;
     CU(G(e->d_xn, L.wqkv, QKV, d, GE_F32, nullptr, e->d_qkv, QKV));
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
@@ -764,7 +764,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       a.out = nullptr; a.out_bf = e->d_attn_bf;
       CU(launch_attn_decode(a, st, pdl_attn)); nl++; }
     CU(G(e->d_attn_bf, L.wo, d, QD, GE_F32, nullptr, e->d_y, d));
-    CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm)); nl++;
+    CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qc, QD, e->d_y, d)); nl++;
     CU(G(e->d_xn, L.wq_c, QD, d, GE_F32, nullptr, e->d_qc, QD));
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
@@ -772,7 +772,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       a.out = nullptr; a.out_bf = e->d_attn_bf;
       CU(launch_attn_decode(a, st, pdl_attn)); nl++; }
     CU(G(e->d_attn_bf, L.wo_c, d, QD, GE_F32, nullptr, e->d_y, d));
-    CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm)); nl++;
+    CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_y, d, nullptr, 0)); nl++;
     CU(G(e->d_xn, L.wgu, 2 * I, d, GE_GEGLU_BF16, nullptr, e->d_act_bf, I));
     CU(G(e->d_act_bf, L.wd, d, I, GE_F32, nullptr, e->d_y, d));
   }
@@ -1002,7 +1002,7 @@ extern "C" int t5g_debug_trace(T5GEngine* e, uint64_t* begin_ns, uint64_t* end_n
 extern "C" int t5g_debug_gemm(T5GEngine* e, const void* x, const void* w, float* out, int M, int N, int K, int impl, void* stream_) {
   T5G_CHECK(e && x && w && out, T5G_ERR_INVALID, "bad arguments");
   T5G_CUDA(cudaSetDevice(e->device));
-  GemmArgs g{(const bf16*)x, (const bf16*)w, M, N, K, GE_F32, nullptr, out, N};
+  GemmArgs g{(const bf16*)x, (const bf16*)w, M, N, K, GE_F32, nullptr, out, N, 0};
   e->launches++;
   CU(impl == 1 ? launch_gemm_tc(g, (cudaStream_t)stream_, e->num_sms) : launch_gemm_simt(g, (cudaStream_t)stream_));
   return T5G_OK;

@@ -59,7 +59,8 @@ cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pd
 cudaError_t launch_embed(const bf16* table, const int* ids, float scale, float* h, int M, int d, cudaStream_t st);
 // h_out = h_in + rmsnorm(y)*g_post (if y) ; xn = bf16(rmsnorm(h_out)*g_pre) (if xn) ; hf32 = fp32 normed (if xf)
 cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, const float* g_pre, float* h_out,
-                        bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st, bool pdl = false);
+                        bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st, bool pdl = false,
+                        float* zero_a = nullptr, int na = 0, float* zero_b = nullptr, int nb = 0);
 // qkv fp32 [M, ld] -> RoPE(q,k) at pos[M]; q_out bf16 [M,Hq*D]; k_out/v_out bf16 [M,Hkv*D]; optional page append
 struct RopeSplitArgs {
   const float* qkv; int ld; int q_off, k_off, v_off;   // column offsets (negative = absent)
@@ -85,6 +86,7 @@ struct GemmArgs {
   const bf16* A; const bf16* W; int M, N, K;
   int epilogue; const float* bias;
   void* out; int ldo;     // GE_GEGLU: N counts interleaved rows, out is [M, N/2]
+  int out_zeroed;         // GE_F32 split-K: the caller guarantees `out` is already zero (no memset node is inserted)
 };
 cudaError_t launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool pdl = false);   // tcgen05/TMEM/TMA path (gemm_tc.cu)

@@ -31,7 +31,8 @@ constexpr int NK_MAXV = 8;                       // float4 per thread: d <= 128*
 // they must not come from the non-coherent read-only path)
 __global__ void __launch_bounds__(NK_THREADS) norm_kernel(const float* h_in, const float* y,
                                                           const float* __restrict__ g_post, const float* __restrict__ g_pre,
-                                                          float* h_out, bf16* xn, float* xf, int d, float eps) {
+                                                          float* h_out, bf16* xn, float* xf, int d, float eps,
+                                                          float* zero_a, int na, float* zero_b, int nb) {
   __shared__ float red[128];
   const size_t base = (size_t)blockIdx.x * d;
   const int nv = d >> 2;
@@ -64,6 +65,10 @@ __global__ void __launch_bounds__(NK_THREADS) norm_kernel(const float* h_in, con
     }
     yv[u] = make_float4(yy[0] * gg[0], yy[1] * gg[1], yy[2] * gg[2], yy[3] * gg[3]);     // y*g_post
   }
+  // optional side job: zero this row of up to two buffers that the following split-K GEMMs accumulate into with
+  // red.global.add (after the loads above, so `y` itself may be one of them)
+  if (zero_a) for (int i = threadIdx.x; i < (na >> 2); i += NK_THREADS) reinterpret_cast<float4*>(zero_a + (size_t)blockIdx.x * na)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (zero_b) for (int i = threadIdx.x; i < (nb >> 2); i += NK_THREADS) reinterpret_cast<float4*>(zero_b + (size_t)blockIdx.x * nb)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   block_sum4(s1, s2, s3, s4, red);
   const float ry = y ? rsqrtf(s1 / (float)d + eps) : 0.f;
   const float ss = s2 + 2.f * ry * s3 + ry * ry * s4;
@@ -246,9 +251,10 @@ cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float sc
 }
 
 cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, const float* g_pre, float* h_out,
-                        bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st, bool pdl) {
+                        bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st, bool pdl,
+                        float* zero_a, int na, float* zero_b, int nb) {
   if (M <= 0) return cudaSuccess;
-  if (d % 4 != 0 || d > NK_THREADS * 4 * NK_MAXV) return cudaErrorInvalidValue;
+  if (d % 4 != 0 || d > NK_THREADS * 4 * NK_MAXV || (na & 3) || (nb & 3)) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(M);
   cfg.blockDim = dim3(NK_THREADS);
@@ -259,7 +265,7 @@ cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, norm_kernel, h_in, y, g_post, g_pre, h_out, xn, xf, d, eps);
+  return cudaLaunchKernelEx(&cfg, norm_kernel, h_in, y, g_post, g_pre, h_out, xn, xf, d, eps, zero_a, na, zero_b, nb);
 }
 
 cudaError_t launch_rope_split(const RopeSplitArgs& a, cudaStream_t st) {

@@ -186,6 +186,12 @@ int t5g_abi_version(void);
 int t5g_debug_trace(T5GEngine* eng, uint64_t* begin_ns, uint64_t* end_ns, int max_entries, int* n_out);
 int t5g_debug_gemm(T5GEngine* eng, const void* x_bf16 /* dev [M,K] */, const void* w_bf16 /* dev [N,K] */,
                    float* out /* dev [M,N] */, int M, int N, int K, int impl /* 0 = simt, 1 = tcgen05 */, void* stream);
+/* Prefill attention kernel alone (impl 0 = CUDA-core kernel, 1 = tcgen05 kernel) on caller device buffers: q [Tq, Hq*D],
+ * k/v [Tk, Hkv*D] bf16, varlen segments (device int32 arrays: q_seg_off/k_seg_off [n_seg+1], q_seg_of [Tq]), out bf16
+ * [Tq, Hq*D].  Geometry (heads, head_dim, scale) comes from the engine config. */
+int t5g_debug_attn_prefill(T5GEngine* eng, const void* q, const void* k, const void* v, const int32_t* q_seg_off,
+                           const int32_t* k_seg_off, const int32_t* q_seg_of, int n_seg, int Tq, int Tk, int max_lq,
+                           int causal, int window, float softcap, void* out, int impl, void* stream);
 /* Launches the decode step's dominant kernel (gate|up projection: post-norm + residual + pre-norm prologue, GeGLU
  * epilogue; gemv_kernel<1,P_RES_NORM,E_GEGLU>) on caller-provided interleaved weights [2*inter, hidden] (device,
  * bf16) using the engine's own decode buffers of row 0.  Used by bench.py to time that kernel live. */

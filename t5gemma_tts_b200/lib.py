@@ -85,6 +85,8 @@ SYMBOLS = {
     "t5g_abi_version": (C.c_int, []),
     "t5g_debug_trace": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]),
     "t5g_debug_gemm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "t5g_debug_attn_prefill": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_float, _P, C.c_int, _P]),
     "t5g_debug_gemv_gateup": (C.c_int, [_P, _P, _P]),
     "t5g_debug_gemv": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
 }

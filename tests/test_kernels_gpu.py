@@ -59,3 +59,31 @@ def test_gemm_tcgen05_vs_torch(M, N, K):
     ref = a.double() @ w.double().t()
     err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-5, err
+
+
+ATTN_CASES = [
+    # D, Hq, Hkv, q_lens, k_lens, causal, window, softcap
+    (64, 4, 2, [5], [5], False, 0, 0.0),
+    (64, 4, 2, [5, 5], [5, 5], False, 0, 0.0),                 # second request at an unaligned token offset
+    (64, 4, 2, [70, 130], [70, 130], False, 0, 50.0),
+    (256, 8, 4, [152, 33, 300], [152, 33, 300], True, 0, 50.0),
+    (256, 8, 4, [200, 90], [200, 90], True, 40, 50.0),         # causal sliding window
+    (256, 8, 4, [300], [300], False, 37, 0.0),                 # bidirectional window
+    (256, 8, 4, [152, 20], [64, 96], False, 0, 50.0),          # cross-attention shapes
+    (128, 4, 4, [257], [257], True, 0, 5.0),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ATTN_CASES, ids=[f"D{c[0]}-q{'_'.join(map(str, c[3]))}-c{int(c[5])}w{c[6]}" for c in ATTN_CASES])
+def test_prefill_attention_vs_torch(case):
+    """Both prefill attention kernels (CUDA-core varlen and the tcgen05/TMA one) against an fp32 torch softmax(QK^T)V with
+    the reference's masks (modeling_t5gemma_voice.py make_attention_mask / sliding window) and softcap."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from check_attn_tc import run
+    res = run(*case)
+    TOL = 2e-2     # bf16 inputs / bf16 probabilities, relative to max |out|
+    assert res[0][0] < TOL, f"CUDA-core kernel err {res[0][0]}"
+    assert res[1][0] < TOL, f"tcgen05 kernel err {res[1][0]}"

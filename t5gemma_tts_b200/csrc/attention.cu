@@ -117,42 +117,85 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
     l2_prefetch_range(a.pf[1], cta, n);
   }
   pdl_launch_dependents();
-  pdl_wait();
-  trace_begin(a.trace);
   const int hk = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
   const int NS = a.n_splits;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = lane / LPT, l8 = lane % LPT;
   const int PT = a.pool.page_tokens;
   const int* bt = a.block_table + (size_t)b * a.bt_stride;
-  // ---- one round trip: slot state, RoPE table, raw q, new k/v and the block-table row are all independent:
-  //      every load is issued into registers before the first shared-memory store (stores wait on their loads) ----
+  constexpr int NT = ATD_WARPS * 32;
+  constexpr int QPT = (G * D + NT - 1) / NT, KPT = (D + NT - 1) / NT, RPT = (D / 2 + NT - 1) / NT;
+  // ---- before the PDL dependency resolves: everything that only depends on EARLIER steps.  The slot state and
+  //      the RoPE table were written by this step's sampler, which is complete because the first kernel after it
+  //      is launched without programmatic overlap (engine.cu); the block table is host-written before the launch
+  //      and cached K/V rows of earlier tokens are immutable.  Only q and the new k/v come from the producer. ----
   const SlotDev& sl = a.slots[b];
   const int active = sl.active;
   const int L = a.is_cross ? sl.n_text : sl.cur_len;
   const float pos = sl.pos;
-  constexpr int NT = ATD_WARPS * 32;
-  constexpr int QPT = (G * D + NT - 1) / NT, KPT = (D + NT - 1) / NT, RPT = (D / 2 + NT - 1) / NT;
-  float rq[QPT], rk[KPT], rv[KPT], rc[RPT], rs[RPT];
+  {
+    float rc[RPT], rs[RPT];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      const int i = tid + u * NT;
+      const bool ok = a.rope_cs && i < D / 2;
+      rc[u] = ok ? a.rope_cs[(size_t)b * D + i] : 1.f;
+      rs[u] = ok ? a.rope_cs[(size_t)b * D + D / 2 + i] : 0.f;
+    }
+    const int bt_v = (tid < ATD_BT_CACHE && tid < a.bt_stride) ? bt[tid] : 0;
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) { const int i = tid + u * NT; if (i < D / 2) { cs[i] = rc[u]; sn[i] = rs[u]; } }
+    if (tid < ATD_BT_CACHE) bt_s[tid] = bt_v;
+    if (!a.rope_cs) {
+      for (int i = tid; i < D / 2; i += blockDim.x) {
+        float s_, c_;
+        sincosf(pos * a.inv_freq[i], &s_, &c_);
+        cs[i] = c_; sn[i] = s_;
+      }
+    }
+  }
+  const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
+  int chunk = (L - lo + NS - 1) / NS;
+  chunk = (chunk + TPW - 1) / TPW * TPW;
+  const int t_begin = lo + split * chunk, t_end = min(L, t_begin + chunk);
+  const bool has_new = (!a.is_cross) && (t_end == L) && (t_end > t_begin);
+  __syncthreads();
+  auto page_of = [&](int t) -> int { const int pi = t / PT; return pi < ATD_BT_CACHE ? bt_s[pi] : bt[pi]; };
+  // K/V rows of the first two token groups of this warp: in flight while the producer kernel is still running
+  uint4 ku[2][NV], vu[2][NV];
+  auto load_groups = [&](int t0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * ATD_WARPS * TPW + grp;
+      if (t < t_end && !(has_new && t == L - 1)) {
+        const int page = page_of(t), off = t % PT;
+        const bf16* kp = a.pool.ptr(a.layer, 0, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
+        const bf16* vp = a.pool.ptr(a.layer, 1, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { ku[u][i] = *reinterpret_cast<const uint4*>(kp + i * 8); vu[u][i] = *reinterpret_cast<const uint4*>(vp + i * 8); }
+      }
+    }
+  };
+  const int t_first = t_begin + warp * TPW;
+  if (active && a.preload) load_groups(t_first);
+
+  pdl_wait();
+  trace_begin(a.trace);
+  if (active && !a.preload) load_groups(t_first);
+  // ---- the producer's outputs: raw q and the new k/v, loaded into registers before the first shared-memory store ----
+  float rq[QPT], rk[KPT], rv[KPT];
 #pragma unroll
   for (int u = 0; u < QPT; ++u) {
     const int i = tid + u * NT;
-    rq[u] = (i < G * D) ? a.q[(size_t)b * a.q_stride + (size_t)(hk * G) * D + i] : 0.f;
+    rq[u] = (i < G * D) ? __ldcg(a.q + (size_t)b * a.q_stride + (size_t)(hk * G) * D + i) : 0.f;
   }
 #pragma unroll
   for (int u = 0; u < KPT; ++u) {
     const int j = tid + u * NT;
     const bool ok = !a.is_cross && j < D;
-    rk[u] = ok ? a.kv_new[(size_t)b * a.kv_stride + (size_t)hk * D + j] : 0.f;
-    rv[u] = ok ? a.kv_new[(size_t)b * a.kv_stride + (size_t)(a.Hkv + hk) * D + j] : 0.f;
+    rk[u] = ok ? __ldcg(a.kv_new + (size_t)b * a.kv_stride + (size_t)hk * D + j) : 0.f;
+    rv[u] = ok ? __ldcg(a.kv_new + (size_t)b * a.kv_stride + (size_t)(a.Hkv + hk) * D + j) : 0.f;
   }
-#pragma unroll
-  for (int u = 0; u < RPT; ++u) {
-    const int i = tid + u * NT;
-    const bool ok = a.rope_cs && i < D / 2;
-    rc[u] = ok ? a.rope_cs[(size_t)b * D + i] : 1.f;
-    rs[u] = ok ? a.rope_cs[(size_t)b * D + D / 2 + i] : 0.f;
-  }
-  const int bt_v = (tid < ATD_BT_CACHE && tid < a.bt_stride) ? bt[tid] : 0;
   if (!active) return;                             // uniform over the whole cluster (same b)
 #pragma unroll
   for (int u = 0; u < QPT; ++u) { const int i = tid + u * NT; if (i < G * D) qs[i / D][i % D] = rq[u]; }
@@ -161,21 +204,6 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
     const int j = tid + u * NT;
     if (j < D) { knew[j] = rk[u]; vnew[j] = __bfloat162float(__float2bfloat16(rv[u])); }
   }
-#pragma unroll
-  for (int u = 0; u < RPT; ++u) { const int i = tid + u * NT; if (i < D / 2) { cs[i] = rc[u]; sn[i] = rs[u]; } }
-  if (tid < ATD_BT_CACHE) bt_s[tid] = bt_v;
-  if (!a.rope_cs) {
-    for (int i = tid; i < D / 2; i += blockDim.x) {
-      float s, c;
-      sincosf(pos * a.inv_freq[i], &s, &c);
-      cs[i] = c; sn[i] = s;
-    }
-  }
-  const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
-  int chunk = (L - lo + NS - 1) / NS;
-  chunk = (chunk + TPW - 1) / TPW * TPW;
-  const int t_begin = lo + split * chunk, t_end = min(L, t_begin + chunk);
-  const bool has_new = (!a.is_cross) && (t_end == L) && (t_end > t_begin);
   __syncthreads();
   cluster.barrier_arrive();                        // "this CTA is running": waited on before the first remote store
   // rotate in place: element pairs (j, j+D/2)
@@ -193,7 +221,6 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
     }
   }
   __syncthreads();
-  auto page_of = [&](int t) -> int { const int pi = t / PT; return pi < ATD_BT_CACHE ? bt_s[pi] : bt[pi]; };
   if (has_new) {   // append to the page (K post-RoPE), visible to later steps
     const int t = L - 1, page = page_of(t), off = t % PT;
     bf16* kd = a.pool.ptr(a.layer, 0, page) + ((size_t)hk * PT + off) * D;
@@ -201,7 +228,6 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
     for (int j = tid; j < D; j += blockDim.x) { kd[j] = __float2bfloat16(knew[j]); vd[j] = __float2bfloat16(vnew[j]); }
   }
 
-  const int grp = lane / LPT, l8 = lane % LPT;
   float qreg[G][DPL];
 #pragma unroll
   for (int g = 0; g < G; ++g)
@@ -211,30 +237,18 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   GroupState<G, DPL> st;
   st.init();
   // two token groups per iteration: both K/V row loads are in flight before either is consumed
-  for (int t0 = t_begin + warp * TPW; t0 < t_end; t0 += 2 * ATD_WARPS * TPW) {
-    uint4 ku[2][NV], vu[2][NV];
-    bool valid[2], fresh[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int t = t0 + u * ATD_WARPS * TPW + grp;
-      valid[u] = t < t_end;
-      fresh[u] = valid[u] && has_new && t == L - 1;
-      if (valid[u] && !fresh[u]) {
-        const int page = page_of(t), off = t % PT;
-        const bf16* kp = a.pool.ptr(a.layer, 0, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
-        const bf16* vp = a.pool.ptr(a.layer, 1, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) { ku[u][i] = *reinterpret_cast<const uint4*>(kp + i * 8); vu[u][i] = *reinterpret_cast<const uint4*>(vp + i * 8); }
-      }
-    }
+  for (int t0 = t_first; t0 < t_end; t0 += 2 * ATD_WARPS * TPW) {
+    if (t0 != t_first) load_groups(t0);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (t0 + u * ATD_WARPS * TPW >= t_end) break;      // warp-uniform
+      const int t = t0 + u * ATD_WARPS * TPW + grp;
+      const bool valid = t < t_end, fresh = valid && has_new && t == L - 1;
       float kf[DPL], vf[DPL];
-      if (fresh[u]) {
+      if (fresh) {
 #pragma unroll
         for (int i = 0; i < DPL; ++i) { kf[i] = knew[l8 * DPL + i]; vf[i] = vnew[l8 * DPL + i]; }
-      } else if (valid[u]) {
+      } else if (valid) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) { bf16x8_to_f32(ku[u][i], kf + i * 8); bf16x8_to_f32(vu[u][i], vf + i * 8); }
       } else {
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
         for (int i = 0; i < DPL; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
       }
       // all lanes execute the shuffles; invalid groups contribute nothing
-      group_update<G, D>(st, qreg, kf, vf, a.scale, a.softcap, valid[u]);
+      group_update<G, D>(st, qreg, kf, vf, a.scale, a.softcap, valid);
     }
   }
   warp_merge<G, D>(st);

@@ -78,7 +78,7 @@ struct T5GEngine {
   float *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_memory = nullptr, *p_ckv = nullptr, *p_final = nullptr;
   bf16 *p_xn = nullptr, *p_q = nullptr, *p_k = nullptr, *p_v = nullptr, *p_att = nullptr, *p_act = nullptr,
        *p_mem_bf = nullptr, *p_ck = nullptr, *p_cv = nullptr, *p_vt = nullptr;
-  int vt_ld = 0; bool use_tc_attn = true;
+  int vt_ld = 0; bool use_tc_attn = true; int attn_preload = 1;
   int *p_vt_off_e = nullptr, *p_vt_off_d = nullptr;          // 8-aligned V^T column offsets per request (encoder / decoder tokens)
   float* p_logits = nullptr; int logits_chunk = 128;
   int *p_ids = nullptr, *p_seg_of = nullptr, *p_seg_off_e = nullptr, *p_seg_off_d = nullptr, *p_tok_slot = nullptr,
@@ -297,6 +297,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   e->vt_ld = (int)((T + 8 * (size_t)B + 64 + 7) & ~(size_t)7); DM(e->p_vt, (size_t)KD * e->vt_ld);
   DM(e->p_vt_off_e, B + 1); DM(e->p_vt_off_d, B + 1);
   if (const char* s = getenv("T5G_ATTN_TC")) e->use_tc_attn = atoi(s) != 0;
+  if (const char* s = getenv("T5G_ATTN_PRELOAD")) e->attn_preload = atoi(s) != 0;
   DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
   DM(e->p_ids, T); DM(e->p_seg_of, T); DM(e->p_seg_off_e, B + 1); DM(e->p_seg_off_d, B + 1); DM(e->p_tok_slot, T); DM(e->p_tok_idx, T);
   DM(e->p_last_rows, B); DM(e->p_pos, T);
@@ -310,6 +311,8 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
     e->ns_self = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
     while (D % e->ns_self) e->ns_self >>= 1;
     e->ns_cross = std::min(2, e->ns_self);
+    if (const char* v = getenv("T5G_NS_SELF")) e->ns_self = atoi(v);
+    if (const char* v = getenv("T5G_NS_CROSS")) e->ns_cross = atoi(v);
   }
   DM(e->d_hA, (size_t)B * d); DM(e->d_hB, (size_t)B * d); DM(e->d_y, (size_t)B * d); DM(e->d_qkv, (size_t)B * QKV);
   DM(e->d_qc, (size_t)B * QD); DM(e->d_act, (size_t)B * I); DM(e->d_t1, (size_t)B * d); DM(e->d_logits, (size_t)B * e->Vpad);
@@ -667,7 +670,7 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
     return e->d_trace + (kidx++);
   };
   // batch rows are processed in groups of <= 4 by the GEMV family
-  auto gemv_all = [&](GemvArgs a, int P, int E, size_t in_stride, size_t out_stride) -> cudaError_t {
+  auto gemv_all = [&](GemvArgs a, int P, int E, size_t in_stride, size_t out_stride, bool overlap = true) -> cudaError_t {
     for (int b0 = 0; b0 < B; b0 += 4) {
       GemvArgs g = a;
       g.B = std::min(4, B - b0); g.slot0 = b0;
@@ -677,7 +680,7 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
       if (g.h_out) g.h_out += (size_t)b0 * d;
       g.out += (size_t)b0 * out_stride;
       g.trace = next_trace();
-      cudaError_t er = launch_gemv(g, P, E, e->num_sms, st, pdl);
+      cudaError_t er = launch_gemv(g, P, E, e->num_sms, st, pdl && overlap);
       if (er != cudaSuccess) return er;
       nl++;
     }
@@ -716,12 +719,14 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
     { GemvArgs a = z; a.W = L.wqkv; a.N = QKV; a.K = d; a.g_pre = L.g_pre_sa; a.out = e->d_qkv; a.out_stride = QKV;
-      if (l == 0) { a.emb = e->audio_emb; a.emb_scale = sqrtf((float)d); a.h_out = hbuf[0]; t = 0; CU(gemv_all(a, P_EMBED_NORM, E_STORE, 0, QKV)); }
+      // the first kernel after the sampler starts only when the sampler has COMPLETED (no programmatic overlap): every later
+      // kernel may then read the slot state / RoPE table the sampler wrote before its own griddepcontrol.wait
+      if (l == 0) { a.emb = e->audio_emb; a.emb_scale = sqrtf((float)d); a.h_out = hbuf[0]; t = 0; CU(gemv_all(a, P_EMBED_NORM, E_STORE, 0, QKV, false)); }
       else { a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = e->dec[l - 1].g_post_ff; a.h_out = hbuf[t ^ 1]; t ^= 1; CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QKV)); } }
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.out = e->d_attn; a.trace = next_trace();
+      a.out = e->d_attn; a.preload = e->attn_preload; a.trace = next_trace();
       CU(launch_attn_decode(a, st, pdl)); nl++; }
     { GemvArgs a = z; a.W = L.wo; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
       a.pf[0] = PF(L.wq_c, (size_t)QD * d);                 // issued while this kernel waits on the attention kernel
@@ -732,7 +737,7 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
       a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.out = e->d_attn; a.trace = next_trace();
+      a.out = e->d_attn; a.preload = e->attn_preload; a.trace = next_trace();
       CU(launch_attn_decode(a, st, pdl)); nl++; }
     { GemvArgs a = z; a.W = L.wo_c; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
       a.pf[0] = PF(L.wgu, GU, 0, std::min(GU, e->l2pf_gu_elems));
@@ -777,7 +782,8 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
     s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
     s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32;
     CU(launch_sampler(s, st, pdl_samp)); nl++; }
-  CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st, pdl_emb)); nl++;
+  // no programmatic overlap with the sampler: later kernels read the slot state before their griddepcontrol.wait
+  CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st, false)); nl++; (void)pdl_emb;
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
     if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d));
@@ -787,7 +793,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.out = nullptr; a.out_bf = e->d_attn_bf;
+      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload;
       CU(launch_attn_decode(a, st, pdl_attn)); nl++; }
     CU(G(e->d_attn_bf, L.wo, d, QD, GE_F32, nullptr, e->d_y, d));
     CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qc, QD, e->d_y, d)); nl++;
@@ -795,7 +801,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
       a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.out = nullptr; a.out_bf = e->d_attn_bf;
+      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload;
       CU(launch_attn_decode(a, st, pdl_attn)); nl++; }
     CU(G(e->d_attn_bf, L.wo_c, d, QD, GE_F32, nullptr, e->d_y, d));
     CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_y, d, nullptr, 0)); nl++;

@@ -108,21 +108,40 @@ __global__ void __launch_bounds__(GV_THREADS, (NB == 1) ? 2 : 1) gemv_kernel(Gem
       gpost[i] = (P == P_RES_NORM && k < K) ? a.g_post[k] : 0.f;
     }
   }
+  // slot activity was settled by the sampler, which completed before any kernel that can overlap this one was
+  // launched (engine.cu: the first kernel after the sampler has no programmatic overlap): read it before the wait
+  int any = 1;
+  if (a.slots) {
+    any = 0;
+    for (int b = 0; b < a.B; ++b) any |= a.slots[a.slot0 + b].active;
+  }
   pdl_launch_dependents();
   pdl_wait();
   trace_begin(a.trace);
-
-  if (a.slots) {
-    int any = 0;
-    for (int b = 0; b < a.B; ++b) any |= a.slots[a.slot0 + b].active;
-    if (!any) return;
-  }
+  if (!any) return;
 
   // ---- prologue: build x[NB][K] in shared memory --------------------------------------------------------
   for (int b = 0; b < NB; ++b) {
     const bool valid = b < a.B;
     if (P == P_PLAIN) {
-      for (int k = threadIdx.x; k < K; k += GV_THREADS) xs.store(b, k, valid ? a.x[(size_t)b * K + k] : 0.f);
+      // 16-byte loads, a batch of them in registers before the first shared-memory store (a load->store loop
+      // would pay one L2 round trip per iteration); float4 #i is the lo (i even) / hi (i odd) half of chunk i/2
+      const float4* xv = reinterpret_cast<const float4*>(a.x + (size_t)b * K);
+      const int n4 = K >> 2;
+      constexpr int XB = 3;
+      for (int base = 0; base < n4; base += GV_THREADS * XB) {
+        float4 r[XB];
+#pragma unroll
+        for (int u = 0; u < XB; ++u) {
+          const int i = base + threadIdx.x + u * GV_THREADS;
+          r[u] = (valid && i < n4) ? __ldcg(xv + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < XB; ++u) {
+          const int i = base + threadIdx.x + u * GV_THREADS;
+          if (i < n4) ((i & 1) ? xs.hi : xs.lo)[b * xs.nchunks + (i >> 1)] = r[u];
+        }
+      }
     } else {
       // RMSNorm sandwich in fp32: h = h_in + rmsnorm(y)*g_post ; x = rmsnorm(h)*g_pre
       constexpr int per = NP;

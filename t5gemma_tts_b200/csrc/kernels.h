@@ -39,6 +39,7 @@ struct AttnDecodeArgs {
   KVPool pool; int layer;
   const int* block_table; int bt_stride;   // [slot][bt_stride] page ids
   const float* q; int q_stride;            // [B, q_stride] raw (pre-RoPE) queries, Hq*D used
+  int preload;                             // 1: issue the first K/V row loads before griddepcontrol.wait
   const float* kv_new; int kv_stride;      // self: raw k at kv_new[b*kv_stride + 0..KD), v at +KD ; null for cross
   const SlotDev* slots;
   int B, Hq, Hkv, D;

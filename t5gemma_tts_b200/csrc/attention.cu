@@ -399,6 +399,13 @@ cudaError_t launch_decode_gd(const AttnDecodeArgs& a, cudaStream_t st, bool pdl)
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = step_carveout(attn_decode_kernel<G, D, 8>);
+    if (e == cudaSuccess) e = step_carveout(attn_decode_kernel<G, D, 4>);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
   if (wide) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D, 8>, a);
   return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D, 4>, a);
 }

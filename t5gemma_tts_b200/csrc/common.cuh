@@ -158,3 +158,15 @@ struct SlotDev {
   int n_silence;
   int pad_;
 };
+
+// Experiment hook: force one shared-memory carve-out (percent) on every kernel of the decode step (T5G_CARVEOUT;
+// default -1 = driver's choice).  Measured: the maximum carve-out slows the weight-streaming GEMVs (gate|up 15.5 ->
+// 19.8 us) because in-flight global loads are tracked in L1; kernels of the step therefore keep their shared memory
+// under the 100 KB configuration.
+template <typename KernelT>
+inline cudaError_t step_carveout(KernelT kern) {
+  static int pct = -2;
+  if (pct == -2) { const char* e = getenv("T5G_CARVEOUT"); pct = e ? atoi(e) : -1; }
+  if (pct < 0) return cudaSuccess;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}

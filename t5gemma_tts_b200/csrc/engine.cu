@@ -96,6 +96,10 @@ struct T5GEngine {
   int ns_self = 8, ns_cross = 2;
   int h_end = 0;                                               // which h buffer holds the residual at step end
   cudaGraphExec_t step_graph = nullptr; cudaStream_t graph_built_for = nullptr; int nodes_per_step = 0;
+  cudaGraphExec_t step_graph_fx = nullptr; int nodes_per_step_fx = 0;   // variant with cross-attention fused into its o_proj
+  int last_nodes_per_step = 0;
+  int xf_max_keys = 0; bool use_xf = false;                              // capacity (encoder keys over live rows) of that kernel; opt-in (T5G_FUSE_XATTN=1):
+                                                                         // measured 11.9 us vs 9.4 us for the two separate kernels (profiles/r1_gemv_design_experiments.md)
   int64_t launches = 0;
   cudaEvent_t ev[6] = {};
   float timings[4] = {0, 0, 0, 0};
@@ -298,6 +302,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   DM(e->p_vt_off_e, B + 1); DM(e->p_vt_off_d, B + 1);
   if (const char* s = getenv("T5G_ATTN_TC")) e->use_tc_attn = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_PRELOAD")) e->attn_preload = atoi(s) != 0;
+  if (const char* s = getenv("T5G_FUSE_XATTN")) e->use_xf = atoi(s) != 0;
   DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
   DM(e->p_ids, T); DM(e->p_seg_of, T); DM(e->p_seg_off_e, B + 1); DM(e->p_seg_off_d, B + 1); DM(e->p_tok_slot, T); DM(e->p_tok_idx, T);
   DM(e->p_last_rows, B); DM(e->p_pos, T);
@@ -314,6 +319,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
     if (const char* v = getenv("T5G_NS_SELF")) e->ns_self = atoi(v);
     if (const char* v = getenv("T5G_NS_CROSS")) e->ns_cross = atoi(v);
   }
+  e->xf_max_keys = (B <= 4) ? xattn_oproj_max_keys(B, e->Hq, e->Hkv, D, QD, e->PT, e->num_sms) : 0;
   DM(e->d_hA, (size_t)B * d); DM(e->d_hB, (size_t)B * d); DM(e->d_y, (size_t)B * d); DM(e->d_qkv, (size_t)B * QKV);
   DM(e->d_qc, (size_t)B * QD); DM(e->d_act, (size_t)B * I); DM(e->d_t1, (size_t)B * d); DM(e->d_logits, (size_t)B * e->Vpad);
   DM(e->d_rope, (size_t)B * D);
@@ -334,6 +340,7 @@ extern "C" int t5g_destroy(T5GEngine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
+  if (e->step_graph_fx) cudaGraphExecDestroy(e->step_graph_fx);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_mirror) cudaFreeHost(e->h_mirror);
   if (e->h_tokens) cudaFreeHost(e->h_tokens);
@@ -657,7 +664,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
+int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) {
   const T5GConfig& c = e->c;
   const int d = e->d, I = e->I, QD = e->QD, KD = e->KD, QKV = e->QKV, D = e->D;
   const int B = c.max_slots;
@@ -734,14 +741,21 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
     { GemvArgs a = z; a.W = L.wq_c; a.N = QD; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_sa; a.g_pre = L.g_pre_ca; a.h_out = hbuf[t ^ 1]; t ^= 1;
       a.out = e->d_qc; a.out_stride = QD;
       CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QD)); }
-    { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
-      a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
-      a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.out = e->d_attn; a.preload = e->attn_preload; a.trace = next_trace();
-      CU(launch_attn_decode(a, st, pdl)); nl++; }
-    { GemvArgs a = z; a.W = L.wo_c; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
-      a.pf[0] = PF(L.wgu, GU, 0, std::min(GU, e->l2pf_gu_elems));
-      CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
+    if (fuse_cross) {   // cross-attention + o_proj in one kernel (short texts)
+      XAttnOprojArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
+      a.slots = e->d_slots; a.slot0 = 0; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.scale = c.attn_scale; a.softcap = c.attn_softcap;
+      a.rope_cs = e->d_rope; a.max_keys = e->xf_max_keys; a.W = L.wo_c; a.N = d; a.K = QD; a.out = e->d_y; a.out_stride = d; a.trace = next_trace();
+      CU(launch_xattn_oproj(a, e->num_sms, st, pdl)); nl++;
+    } else {
+      { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
+        a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
+        a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
+        a.out = e->d_attn; a.preload = e->attn_preload; a.trace = next_trace();
+        CU(launch_attn_decode(a, st, pdl)); nl++; }
+      { GemvArgs a = z; a.W = L.wo_c; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
+        a.pf[0] = PF(L.wgu, GU, 0, std::min(GU, e->l2pf_gu_elems));
+        CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
+    }
     { GemvArgs a = z; a.W = L.wgu; a.N = 2 * I; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_ca; a.g_pre = L.g_pre_ff; a.h_out = hbuf[t ^ 1]; t ^= 1;
       a.out = e->d_act; a.out_stride = I;
       CU(gemv_all(a, P_RES_NORM, E_GEGLU, 0, I)); }
@@ -820,31 +834,44 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
   T5G_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream_;
   CU(cudaEventRecord(e->ev[3], st));
+  // cross-attention fused into o_proj when the encoder keys of all rows in use fit its shared-memory staging
+  bool fuse = false;
+  if (e->c.max_slots <= 4 && e->use_xf && e->xf_max_keys > 0) {
+    int keys = 0;
+    for (int s = 0; s < e->c.max_slots; ++s) if (e->hslots[s].in_use) keys += e->hslots[s].n_text;
+    fuse = keys > 0 && keys <= e->xf_max_keys;
+  }
+  auto enqueue = [&](cudaStream_t s_, int* nl) -> int {
+    return (e->c.max_slots > 4) ? enqueue_step_batched(e, s_, nl) : enqueue_step(e, s_, nl, fuse);
+  };
   if (e->use_graph) {
-    if (!e->step_graph) {
+    cudaGraphExec_t& graph = fuse ? e->step_graph_fx : e->step_graph;
+    int& nodes = fuse ? e->nodes_per_step_fx : e->nodes_per_step;
+    if (!graph) {
       cudaStream_t cs;
       CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      // warm the lazily-set function attributes outside capture
       int nl = 0;
       cudaGraph_t g = nullptr;
       CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
-      int rc = (e->c.max_slots > 4) ? enqueue_step_batched(e, cs, &nl) : enqueue_step(e, cs, &nl);
+      int rc = enqueue(cs, &nl);
       cudaError_t er = cudaStreamEndCapture(cs, &g);
       if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cs); return rc; }
       CU(er);
-      CU(cudaGraphInstantiate(&e->step_graph, g, 0));
+      CU(cudaGraphInstantiate(&graph, g, 0));
       cudaGraphDestroy(g);
       cudaStreamDestroy(cs);
-      e->nodes_per_step = nl;
+      nodes = nl;
     }
-    for (int i = 0; i < max_steps; ++i) CU(cudaGraphLaunch(e->step_graph, st));
-    e->launches += (int64_t)e->nodes_per_step * max_steps;
+    for (int i = 0; i < max_steps; ++i) CU(cudaGraphLaunch(graph, st));
+    e->launches += (int64_t)nodes * max_steps;
+    e->last_nodes_per_step = nodes;
   } else {
     for (int i = 0; i < max_steps; ++i) {
       int nl = 0;
-      int rc = (e->c.max_slots > 4) ? enqueue_step_batched(e, st, &nl) : enqueue_step(e, st, &nl);
+      int rc = enqueue(st, &nl);
       if (rc) return rc;
       e->launches += nl;
+      e->last_nodes_per_step = nl;
     }
   }
   CU(cudaEventRecord(e->ev[4], st));
@@ -1024,7 +1051,7 @@ extern "C" int t5g_debug_trace(T5GEngine* e, uint64_t* begin_ns, uint64_t* end_n
   T5G_CHECK(e->use_trace, T5G_ERR_STATE, "tracing is off (set T5G_TRACE=1 before creating the engine)");
   T5G_CUDA(cudaSetDevice(e->device));
   CU(cudaDeviceSynchronize());
-  const int n = std::min(std::min(max_entries, e->nodes_per_step > 0 ? e->nodes_per_step : T5G_TRACE_STRIDE), T5G_TRACE_STRIDE);
+  const int n = std::min(std::min(max_entries, e->last_nodes_per_step > 0 ? e->last_nodes_per_step : T5G_TRACE_STRIDE), T5G_TRACE_STRIDE);
   CU(cudaMemcpy(begin_ns, e->d_trace, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(end_ns, e->d_trace + T5G_TRACE_STRIDE, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
   *n_out = n;

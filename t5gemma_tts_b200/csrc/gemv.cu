@@ -271,6 +271,7 @@ cudaError_t launch_one(const GemvArgs& a, int grid, size_t smem, cudaStream_t st
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
+    if ((e = step_carveout(kern)) != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -314,7 +315,10 @@ cudaError_t launch_gemv(const GemvArgs& a, int P, int E, int num_sms, cudaStream
   if (a.N % unit_rows) return cudaErrorInvalidValue;
   const int nchunks = a.K / 8, kseg = (nchunks + SEG_CHUNKS - 1) / SEG_CHUNKS, parts = kseg * unit_rows;
   const int n_out = a.N / unit_rows;
-  const int grid = (NB == 1 ? 2 : 1) * num_sms;
+  static int mult = -1;
+  // CTAs per SM; 1 was measured (room for the next kernel to become resident early): gate|up 15.6 -> 22.4 us, too few bytes in flight
+  if (mult < 0) { const char* e = getenv("T5G_GEMV_GRID_MULT"); mult = e ? atoi(e) : 2; }
+  const int grid = (NB == 1 ? mult : 1) * num_sms;
   const int outs_per_cta = (n_out + grid - 1) / grid;
   const size_t part_floats = (parts == 1) ? 0 : (size_t)outs_per_cta * parts * NB;
   if (part_floats > MAX_PARTS_PER_CTA * 4) return cudaErrorInvalidValue;

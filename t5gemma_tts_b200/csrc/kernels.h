@@ -55,6 +55,22 @@ struct AttnDecodeArgs {
 };
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
 
+// ---------------- cross-attention fused into its output projection, bs<=4 decode (xattn_fused.cu) ----------------
+struct XAttnOprojArgs {
+  KVPool pool; int layer;
+  const int* block_table; int bt_stride;   // cross block table [slot][bt_stride]
+  const float* q; int q_stride;            // raw (pre-RoPE) cross queries [B, q_stride]
+  const SlotDev* slots; int slot0; int B;
+  int Hq, Hkv, D; float scale, softcap;
+  const float* rope_cs;                    // [slot][D]: cos | sin of the row's PM-RoPE angle (written by the sampler)
+  int max_keys;                            // shared-memory capacity in encoder keys (sum over live rows)
+  const bf16* W; int N; int K;             // o_proj [N, K = Hq*D]
+  float* out; int out_stride;
+  unsigned long long* trace;
+};
+int xattn_oproj_max_keys(int B, int Hq, int Hkv, int D, int K, int page_tokens, int num_sms);
+cudaError_t launch_xattn_oproj(const XAttnOprojArgs& a, int num_sms, cudaStream_t st, bool pdl);
+
 // ---------------- prefill-side kernels (prefill.cu) ----------------
 // varlen packing: token t belongs to request seg_of[t]; seg_off[r]..seg_off[r+1] are its tokens
 cudaError_t launch_embed(const bf16* table, const int* ids, float scale, float* h, int M, int d, cudaStream_t st);

@@ -594,6 +594,7 @@ cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st, bool pdl) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+    if (e == cudaSuccess) e = step_carveout(sampler_kernel);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }

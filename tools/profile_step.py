@@ -39,7 +39,10 @@ if os.environ.get("T5G_TRACE") == "1":
     n = n.value
     b, e_ = b[:n].astype(np.int64), e_[:n].astype(np.int64)
     t0 = b[0]
-    names = ["head1", "head2", "sampler"] + ["qkv", "sattn", "o", "qc", "cattn", "oc", "gu", "down"] * 26
+    per_layer = ["qkv", "sattn", "o", "qc", "cattn", "oc", "gu", "down"]
+    if (n - 3) % 7 == 0 and (n - 3) % 8 != 0:
+        per_layer = ["qkv", "sattn", "o", "qc", "xattn+oc", "gu", "down"]     # cross-attention fused into o_proj
+    names = ["head1", "head2", "sampler"] + per_layer * 26
     print("step span us", (e_.max() - t0) / 1000.0)
     agg = {}
     for i in range(n):

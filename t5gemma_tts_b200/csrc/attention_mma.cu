@@ -1,0 +1,395 @@
+// Decode attention for BATCHED rows (B > 4): tile kernel over the paged KV pool.
+//
+// The CUDA-core kernel of attention.cu spends ~360 instructions per two cached tokens (per-token shuffles, exps and
+// accumulator rescaling), which at 64 rows makes the step's attention instruction-latency-bound (ncu: 7 k
+// instructions per warp, 1-2 warps per scheduler, < 1 % of the time waiting on memory).  Here the CTA of a
+// (request, kv head, split) walks its key range in tiles of 32 tokens:
+//   * K/V rows travel with cp.async into a 2-stage shared-memory ring (first tiles issued BEFORE
+//     griddepcontrol.wait; rows padded by 16 bytes so ldmatrix is conflict-free);
+//   * scores  S^T[token, head] = K_tile . Q^T  on mma.sync m16n8k16 (the G query heads of the group sit in the
+//     n = 8 columns), scale / softcap / mask in the accumulator registers;
+//   * one online-softmax update per tile and head (warp h owns head h), probabilities rounded to bf16 like the
+//     reference's `attn_weights.to(dtype)` (HF:modeling_t5gemma.py:235);
+//   * O^T[dim, head] += V_tile^T . P^T  on mma.sync, the D dims dealt over the 4 warps.
+// ~120 instructions per warp per 32 tokens.  tcgen05 is not used: the useful M is G = 2 rows and the work is
+// bandwidth / latency bound.  Same fused glue as attention.cu: PM-RoPE of q and of the new k, in-place KV
+// append, split-KV merge of the NS CTAs of a cluster through distributed shared memory.
+#include "kernels.h"
+#include <cooperative_groups.h>
+
+namespace {
+
+constexpr int AM_NT = 128, AM_WARPS = 4;
+constexpr int AM_TT = 32;                 // tokens per tile
+constexpr int AM_NST = 2;                 // ring stages
+constexpr int AM_MAX_NS = 8;
+constexpr int AM_BT_CACHE = 256;
+
+__device__ __forceinline__ void am_cp_async16(void* dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;          // src-size 0: zero fill (rows past the key range must not hold NaN bit patterns)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int D> struct AmGeo {
+  static constexpr int LD = D + 8;                         // padded row (elements): 16-byte skew per row
+  static constexpr int KS = D / 16;                        // k-steps of the score MMA
+  static constexpr int NMT = D / 16;                       // 16-dim m-tiles of the output MMA
+  static constexpr int MTW = (NMT + AM_WARPS - 1) / AM_WARPS;   // m-tiles per warp
+  static constexpr size_t stage_elems = (size_t)2 * AM_TT * LD; // K tile + V tile
+  static constexpr size_t dyn_bytes = (AM_NST * stage_elems + (size_t)8 * LD + (size_t)8 * (AM_TT + 8)) * sizeof(bf16);
+};
+
+// grid (Hkv, NS, B), cluster (1, NS, 1), 128 threads
+template <int G, int D>
+__global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a) {
+  using Geo = AmGeo<D>;
+  constexpr int LD = Geo::LD, KS = Geo::KS, NMT = Geo::NMT, MTW = Geo::MTW;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char am_dyn[];
+  bf16* ring = reinterpret_cast<bf16*>(am_dyn);                         // [NST][2][TT][LD]
+  bf16* qb = ring + AM_NST * Geo::stage_elems;                          // [8][LD]   rotated q (rows >= G are zero)
+  bf16* pb = qb + 8 * LD;                                               // [8][TT+8] probabilities of the tile
+  __shared__ float qs[G][D];
+  __shared__ float cs[D / 2], sn[D / 2];
+  __shared__ float knew[D], vnew[D];
+  __shared__ int bt_s[AM_BT_CACHE];
+  __shared__ float sc[G][AM_TT];
+  __shared__ float corr_s[8];
+  __shared__ unsigned rowoff[AM_NST][AM_TT];                            // row offsets (elements) inside the layer's K plane
+  __shared__ __align__(16) float o_s[G][D];
+  __shared__ float ml_s[G][2];
+  __shared__ __align__(16) float recv_o[AM_MAX_NS][G][D];               // [src rank][g][dslice] (D/NS used per rank)
+  __shared__ float recv_ml[AM_MAX_NS][G][2];
+  __shared__ float f_wt[AM_MAX_NS][G];
+
+  pdl_launch_dependents();
+  const int hk = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
+  unsigned long long* probe = (a.probe && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && blockIdx.z < 64) ? a.probe + blockIdx.z * 11 : nullptr;
+#define AM_PROBE(k) do { if (probe) probe[k] = globaltimer_ns(); } while (0)
+  AM_PROBE(0);
+  const int NS = a.n_splits;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int PT = a.pool.page_tokens;
+  const int* bt = a.block_table + (size_t)b * a.bt_stride;
+  // ---- before the dependency resolves: state of earlier steps only (see attention.cu / engine.cu) ----
+  const SlotDev& sl = a.slots[b];
+  const int active = sl.active;
+  const int L = a.is_cross ? sl.n_text : sl.cur_len;
+  const float pos = sl.pos;
+  for (int i = tid; i < D / 2; i += AM_NT) {
+    if (a.rope_cs) { cs[i] = a.rope_cs[(size_t)b * D + i]; sn[i] = a.rope_cs[(size_t)b * D + D / 2 + i]; }
+    else { float s_, c_; sincosf(pos * a.inv_freq[i], &s_, &c_); cs[i] = c_; sn[i] = s_; }
+  }
+  for (int i = tid; i < AM_BT_CACHE; i += AM_NT) bt_s[i] = (i < a.bt_stride) ? bt[i] : 0;
+  for (int i = tid; i < 8 * LD; i += AM_NT) qb[i] = __float2bfloat16(0.f);
+  for (int i = tid; i < 8 * (AM_TT + 8); i += AM_NT) pb[i] = __float2bfloat16(0.f);
+  const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
+  int chunk = (L - lo + NS - 1) / NS;
+  chunk = (chunk + 15) / 16 * 16;
+  const int t_begin = lo + split * chunk, t_end = min(L, t_begin + chunk);
+  const bool has_new = (!a.is_cross) && (t_end == L) && (t_end > t_begin);
+  const int n_tiles = (t_end > t_begin) ? (t_end - t_begin + AM_TT - 1) / AM_TT : 0;
+  __syncthreads();
+  auto page_of = [&](int t) -> int { const int pi = t / PT; return pi < AM_BT_CACHE ? bt_s[pi] : bt[pi]; };
+  auto stage_ptr = [&](int stage, int kv) -> bf16* { return ring + (size_t)stage * Geo::stage_elems + (size_t)kv * AM_TT * LD; };
+  // tile ti = tokens [t_begin + ti*TT, +TT) -> ring stage ti % NST.  One thread per token resolves the page (an integer
+  // division and a block-table lookup) into a row offset; the 16-byte copies then cost a handful of instructions each
+  // (the naive per-chunk address computation made the ISSUE loop the critical path: 3.7 us per 32-token tile).
+  const bf16* kbase = a.pool.ptr(a.layer, 0, 0);
+  const size_t kv_stride = (size_t)a.pool.n_pages * a.pool.page_elems();
+  auto issue_tile = [&](int ti) {
+    if (ti < n_tiles) {                                       // CTA-uniform
+      const int stage = ti % AM_NST;
+      if (tid < AM_TT) {
+        const int t = t_begin + ti * AM_TT + tid;
+        const bool valid = t < t_end && !(has_new && t == L - 1);
+        unsigned ro = 0xFFFFFFFFu;
+        if (valid) { const int page = page_of(t), off = t % PT; ro = (unsigned)((size_t)page * a.pool.page_elems() + ((size_t)hk * PT + off) * D); }
+        rowoff[stage][tid] = ro;
+      }
+      __syncthreads();
+      constexpr int CPR = D / 8;                              // 16-byte chunks per row
+      bf16* kst = stage_ptr(stage, 0);
+#pragma unroll 4
+      for (int c = tid; c < AM_TT * CPR * 2; c += AM_NT) {
+        const int tok = c / (2 * CPR), rem = c - tok * (2 * CPR), kv = rem / CPR, col = rem - kv * CPR;
+        const unsigned ro = rowoff[stage][tok];
+        const bool valid = ro != 0xFFFFFFFFu;                 // rows past the range / the new token: zero fill
+        am_cp_async16(kst + (size_t)kv * AM_TT * LD + (size_t)tok * LD + col * 8,
+                      kbase + (kv ? kv_stride : 0) + (valid ? ro : 0u) + col * 8, valid);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // one group per tile, empty ones included
+  };
+  if (active) {
+#pragma unroll
+    for (int s_ = 0; s_ < AM_NST; ++s_) issue_tile(s_);
+  }
+
+  AM_PROBE(1);
+  pdl_wait();
+  trace_begin(a.trace);
+  AM_PROBE(2);
+  // ---- the producer's outputs: raw q and the new k/v ----
+  constexpr int QPT = (G * D + AM_NT - 1) / AM_NT, KPT = (D + AM_NT - 1) / AM_NT;
+  {
+    float rq[QPT], rk[KPT], rv[KPT];
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+      const int i = tid + u * AM_NT;
+      rq[u] = (i < G * D) ? __ldcg(a.q + (size_t)b * a.q_stride + (size_t)(hk * G) * D + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < KPT; ++u) {
+      const int j = tid + u * AM_NT;
+      const bool ok = !a.is_cross && j < D;
+      rk[u] = ok ? __ldcg(a.kv_new + (size_t)b * a.kv_stride + (size_t)hk * D + j) : 0.f;
+      rv[u] = ok ? __ldcg(a.kv_new + (size_t)b * a.kv_stride + (size_t)(a.Hkv + hk) * D + j) : 0.f;
+    }
+    if (!active) return;                             // uniform over the whole cluster (same b)
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) { const int i = tid + u * AM_NT; if (i < G * D) qs[i / D][i % D] = rq[u]; }
+#pragma unroll
+    for (int u = 0; u < KPT; ++u) {
+      const int j = tid + u * AM_NT;
+      if (j < D) { knew[j] = rk[u]; vnew[j] = rv[u]; }
+    }
+  }
+  __syncthreads();
+  AM_PROBE(3);
+  cluster.barrier_arrive();                          // "this CTA is running": waited on before the first remote store
+  // rotate (pairs j, j + D/2) and round to bf16: q into the MMA operand buffer, the new k in place
+  for (int i = tid; i < G * D / 2; i += AM_NT) {
+    const int g = i / (D / 2), j = i - g * (D / 2);
+    const float x1 = qs[g][j], x2 = qs[g][j + D / 2];
+    qb[g * LD + j] = __float2bfloat16(x1 * cs[j] - x2 * sn[j]);
+    qb[g * LD + j + D / 2] = __float2bfloat16(x2 * cs[j] + x1 * sn[j]);
+  }
+  if (has_new) {
+    for (int j = tid; j < D / 2; j += AM_NT) {
+      const float x1 = knew[j], x2 = knew[j + D / 2];
+      knew[j] = x1 * cs[j] - x2 * sn[j];
+      knew[j + D / 2] = x2 * cs[j] + x1 * sn[j];
+    }
+  }
+  __syncthreads();
+  if (has_new) {   // append to the page (K post-RoPE), visible to later steps
+    const int t = L - 1, page = page_of(t), off = t % PT;
+    bf16* kd = a.pool.ptr(a.layer, 0, page) + ((size_t)hk * PT + off) * D;
+    bf16* vd = a.pool.ptr(a.layer, 1, page) + ((size_t)hk * PT + off) * D;
+    for (int j = tid; j < D; j += AM_NT) { kd[j] = __float2bfloat16(knew[j]); vd[j] = __float2bfloat16(vnew[j]); }
+  }
+  // q fragments (B operand of the score MMA): B[k = dim][n = head] from qb[head][dim]
+  uint32_t qf[KS][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) ldsm_x2(qf[ks], qb + (size_t)(lane & 7) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
+
+  AM_PROBE(4);
+  const float inv_cap = a.softcap > 0.f ? 1.f / a.softcap : 0.f;
+  float m_run = -INFINITY, l_run = 0.f;              // warp h < G: running max / sum of head h (lane-replicated)
+  float acc[MTW][4];
+#pragma unroll
+  for (int i = 0; i < MTW; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+  const int g8 = lane >> 2, t4 = lane & 3;
+
+  for (int ti = 0; ti < n_tiles; ++ti) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(AM_NST - 1) : "memory");   // tile ti has landed (groups retire in order)
+    __syncthreads();
+    if (ti == 0) AM_PROBE(5);
+    if (ti == 1) AM_PROBE(6);
+    if (ti == 2) AM_PROBE(7);
+    bf16* kb = stage_ptr(ti % AM_NST, 0);
+    bf16* vb = stage_ptr(ti % AM_NST, 1);
+    const int tile_t0 = t_begin + ti * AM_TT;
+    if (has_new && L - 1 >= tile_t0 && L - 1 < tile_t0 + AM_TT) {       // CTA-uniform: the new token's row comes from registers
+      const int tok = L - 1 - tile_t0;
+      for (int j = tid; j < D; j += AM_NT) { kb[(size_t)tok * LD + j] = __float2bfloat16(knew[j]); vb[(size_t)tok * LD + j] = __float2bfloat16(vnew[j]); }
+      __syncthreads();
+    }
+    // ---- scores: warp w < TT/16 owns tokens [16w, 16w+16) of the tile ----
+    if (warp < AM_TT / 16 && tile_t0 + warp * 16 < t_end) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      const bf16* arow = kb + (size_t)(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t af[4];
+        ldsm_x4(af, arow + ks * 16);
+        mma_bf16_16816(c, af, qf[ks]);
+      }
+      // c0,c1: token g8, heads 2*t4, 2*t4+1 ; c2,c3: token g8+8
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int head = 2 * t4 + (r & 1), tok = warp * 16 + g8 + (r >> 1) * 8;
+        if (head < G) {
+          float s = c[r] * a.scale;
+          if (a.softcap > 0.f) {
+            const float e2 = __expf(2.f * s * inv_cap);
+            s = a.softcap * (1.f - __fdividef(2.f, e2 + 1.f));
+          }
+          sc[head][tok] = (tile_t0 + tok < t_end) ? s : -INFINITY;
+        }
+      }
+    } else if (warp < AM_TT / 16) {
+      for (int i = lane; i < G * 16; i += 32) sc[i / 16][warp * 16 + (i & 15)] = -INFINITY;
+    }
+    __syncthreads();
+    // ---- online softmax: warp h owns head h, lane = token of the tile ----
+    if (warp < G) {
+      const float s = sc[warp][lane];
+      float tm = s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+      const float mn = fmaxf(m_run, tm);
+      const float corr = (m_run == -INFINITY) ? 0.f : __expf(m_run - mn);
+      const bf16 pq = __float2bfloat16((s == -INFINITY) ? 0.f : __expf(s - mn));
+      pb[warp * (AM_TT + 8) + lane] = pq;
+      const float ps = warp_sum(__bfloat162float(pq));         // the sum uses the rounded weights the MMA will see
+      l_run = l_run * corr + ps;
+      m_run = mn;
+      if (lane == 0) corr_s[warp] = corr;
+    }
+    __syncthreads();
+    // ---- O^T[dim, head] = corr * O^T + V^T P^T : m-tiles (16 dims) dealt over the warps ----
+    {
+      const float c0 = (2 * t4 < G) ? corr_s[2 * t4] : 0.f, c1 = (2 * t4 + 1 < G) ? corr_s[2 * t4 + 1] : 0.f;
+      uint32_t pf[AM_TT / 16][2];
+#pragma unroll
+      for (int kk = 0; kk < AM_TT / 16; ++kk) ldsm_x2(pf[kk], pb + (size_t)(lane & 7) * (AM_TT + 8) + kk * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int i = 0; i < MTW; ++i) {
+        const int mt = warp + i * AM_WARPS;
+        if (mt < NMT) {
+          acc[i][0] *= c0; acc[i][1] *= c1; acc[i][2] *= c0; acc[i][3] *= c1;
+#pragma unroll
+          for (int kk = 0; kk < AM_TT / 16; ++kk) {
+            uint32_t vf[4];
+            ldsm_x4_t(vf, vb + (size_t)(kk * 16 + (lane & 7) + (lane >> 4) * 8) * LD + mt * 16 + ((lane >> 3) & 1) * 8);
+            mma_bf16_16816(acc[i], vf, pf[kk]);
+          }
+        }
+      }
+    }
+    __syncthreads();                                       // stage, sc and pb are free again
+    issue_tile(ti + AM_NST);
+  }
+
+  AM_PROBE(8);
+  // ---- CTA partial -> shared memory: o_s[head][dim] (unnormalised), ml_s[head] ----
+#pragma unroll
+  for (int i = 0; i < MTW; ++i) {
+    const int mt = warp + i * AM_WARPS;
+    if (mt < NMT) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int head = 2 * t4 + (r & 1), dim = mt * 16 + g8 + (r >> 1) * 8;
+        if (head < G) o_s[head][dim] = acc[i][r];
+      }
+    }
+  }
+  if (warp < G && lane == 0) { ml_s[warp][0] = m_run; ml_s[warp][1] = l_run; }
+  __syncthreads();
+  // ---- split-KV merge across the cluster (same scheme as attention.cu): push the slice rank r finalises ----
+  const int dslice = D / NS;
+  cluster.barrier_wait();                                  // every peer has started: its shared memory may be written
+  for (int i = tid; i < G * D; i += AM_NT) {
+    const int g = i / D, d = i - g * D;
+    const int dst = d / dslice;
+    float* ro = cluster.map_shared_rank(&recv_o[0][0][0], dst);
+    ro[((size_t)split * G + g) * D + (d - dst * dslice)] = o_s[g][d];
+  }
+  if (tid < G * NS) {
+    const int g = tid % G, dst = tid / G;
+    float* rm = cluster.map_shared_rank(&recv_ml[0][0][0], dst);
+    rm[(split * G + g) * 2] = ml_s[g][0]; rm[(split * G + g) * 2 + 1] = ml_s[g][1];
+  }
+  cluster.sync();                                          // all pushes have landed
+  AM_PROBE(9);
+  if (tid < G) {
+    float M = -INFINITY;
+    for (int r = 0; r < NS; ++r) M = fmaxf(M, recv_ml[r][tid][0]);
+    float den = 0.f;
+    for (int r = 0; r < NS; ++r) {
+      const float m = recv_ml[r][tid][0];
+      const float wt = (m == -INFINITY) ? 0.f : __expf(m - M);
+      den = fmaf(wt, recv_ml[r][tid][1], den);
+      f_wt[r][tid] = wt;
+    }
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    for (int r = 0; r < NS; ++r) f_wt[r][tid] *= inv;
+  }
+  __syncthreads();
+  for (int i = tid; i < G * dslice; i += AM_NT) {
+    const int g = i / dslice, dd = i - g * dslice;
+    float o = 0.f;
+    for (int r = 0; r < NS; ++r) o = fmaf(f_wt[r][g], recv_o[r][g][dd], o);
+    const int d = split * dslice + dd;
+    if (a.out) a.out[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = o;
+    if (a.out_bf) a.out_bf[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = __float2bfloat16(o);
+  }
+  AM_PROBE(10);
+  trace_end(a.trace);
+#undef AM_PROBE
+}
+
+template <int G, int D>
+cudaError_t launch_am(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
+  auto kern = attn_decode_mma_kernel<G, D>;
+  const size_t smem = AmGeo<D>::dyn_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(a.Hkv, a.n_splits, a.B);
+  cfg.blockDim = dim3(AM_NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = a.n_splits; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+}  // namespace
+
+bool attn_decode_mma_supported(const AttnDecodeArgs& a) {
+  const int G = a.Hkv > 0 ? a.Hq / a.Hkv : 0;
+  const bool d_ok = a.D == 16 || a.D == 32 || a.D == 64 || a.D == 128 || a.D == 256;
+  return d_ok && (G == 1 || G == 2 || G == 4) && a.n_splits >= 1 && a.n_splits <= AM_MAX_NS &&
+         !(a.n_splits & (a.n_splits - 1)) && a.D % a.n_splits == 0;
+}
+
+cudaError_t launch_attn_decode_mma(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
+  if (!attn_decode_mma_supported(a)) return cudaErrorNotSupported;
+  const int G = a.Hq / a.Hkv;
+#define AM_CASE(GG, DD) if (G == GG && a.D == DD) return launch_am<GG, DD>(a, st, pdl)
+  AM_CASE(1, 16); AM_CASE(1, 32); AM_CASE(1, 64); AM_CASE(1, 128); AM_CASE(1, 256);
+  AM_CASE(2, 16); AM_CASE(2, 32); AM_CASE(2, 64); AM_CASE(2, 128); AM_CASE(2, 256);
+  AM_CASE(4, 16); AM_CASE(4, 32); AM_CASE(4, 64); AM_CASE(4, 128); AM_CASE(4, 256);
+#undef AM_CASE
+  return cudaErrorNotSupported;
+}

@@ -78,7 +78,7 @@ struct T5GEngine {
   float *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_memory = nullptr, *p_ckv = nullptr, *p_final = nullptr;
   bf16 *p_xn = nullptr, *p_q = nullptr, *p_k = nullptr, *p_v = nullptr, *p_att = nullptr, *p_act = nullptr,
        *p_mem_bf = nullptr, *p_ck = nullptr, *p_cv = nullptr, *p_vt = nullptr;
-  int vt_ld = 0; bool use_tc_attn = true; int attn_preload = 1;
+  int vt_ld = 0; bool use_tc_attn = true; int attn_preload = 1, attn_mma = 1;
   int *p_vt_off_e = nullptr, *p_vt_off_d = nullptr;          // 8-aligned V^T column offsets per request (encoder / decoder tokens)
   float* p_logits = nullptr; int logits_chunk = 128;
   int *p_ids = nullptr, *p_seg_of = nullptr, *p_seg_off_e = nullptr, *p_seg_off_d = nullptr, *p_tok_slot = nullptr,
@@ -303,6 +303,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_ATTN_TC")) e->use_tc_attn = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_PRELOAD")) e->attn_preload = atoi(s) != 0;
   if (const char* s = getenv("T5G_FUSE_XATTN")) e->use_xf = atoi(s) != 0;
+  if (const char* s = getenv("T5G_ATTN_MMA")) e->attn_mma = atoi(s) != 0;
   DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
   DM(e->p_ids, T); DM(e->p_seg_of, T); DM(e->p_seg_off_e, B + 1); DM(e->p_seg_off_d, B + 1); DM(e->p_tok_slot, T); DM(e->p_tok_idx, T);
   DM(e->p_last_rows, B); DM(e->p_pos, T);
@@ -666,7 +667,7 @@ namespace {
 
 int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) {
   const T5GConfig& c = e->c;
-  const int d = e->d, I = e->I, QD = e->QD, KD = e->KD, QKV = e->QKV, D = e->D;
+  const int d = e->d, I = e->I, QD = e->QD, QKV = e->QKV, D = e->D;
   const int B = c.max_slots;
   const bool pdl = e->use_pdl;
   int nl = 0;
@@ -778,8 +779,19 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
   const bool pdl = e->use_pdl;
   int mask = 31; if (const char* m = getenv("T5G_PDL_MASK")) mask = atoi(m);
   const bool pdl_norm = pdl && (mask & 1), pdl_gemm = pdl && (mask & 2), pdl_attn = pdl && (mask & 4), pdl_samp = pdl && (mask & 8), pdl_emb = pdl && (mask & 16);
+  int kidx = 0;
+  auto next_trace = [&]() -> unsigned long long* {
+    if (!e->use_trace || kidx >= T5G_TRACE_STRIDE) return nullptr;
+    return e->d_trace + (kidx++);
+  };
+  if (e->use_trace) {
+    CU(cudaMemsetAsync(e->d_trace, 0xFF, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
+    CU(cudaMemsetAsync(e->d_trace + T5G_TRACE_STRIDE, 0, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
+  }
   auto G = [&](const bf16* A, const bf16* W, int N, int K, int epi, const float* bias, void* out, int ldo) -> cudaError_t {
     GemmArgs g{A, W, B, N, K, epi, bias, out, ldo, 1};   // fp32 outputs are pre-zeroed by the preceding norm kernel
+    g.trace = next_trace();
+    if (g.trace && kidx - 1 == 4 + 5 * 11 + 9) g.probe = e->d_trace + 1016;   // layer 5 gate|up: in-kernel checkpoints
     nl += 1;
     if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms, pdl_gemm);
     return launch_gemm_simt(g, st);
@@ -787,38 +799,41 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
   float* h = e->d_hA;
   const DecLayer& Llast = e->dec[c.n_dec_layers - 1];
   // head: h += post_ff(y) ; xn = final_norm(h)
-  CU(launch_norm(h, e->d_y, Llast.g_post_ff, e->g_dec_final, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm)); nl++;
+  CU(launch_norm(h, e->d_y, Llast.g_post_ff, e->g_dec_final, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, nullptr, 0, nullptr, 0, next_trace())); nl++;
   CU(G(e->d_xn, e->head_w1, d, d, GE_BIAS_GELU_BF16, e->head_b1, e->d_t1_bf, d));
   CU(G(e->d_t1_bf, e->head_w2, e->Vpad, d, GE_BIAS_F32, e->head_b2, e->d_logits, e->Vpad));
   { SamplerArgs s{}; s.logits = e->d_logits; s.ld = e->Vpad; s.V = e->V; s.slots = e->d_slots; s.topk_sched_pool = e->d_topk_pool;
     s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
     s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = B; s.host_mirror = e->d_mirror;
     s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
-    s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32;
+    s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32; s.trace = next_trace();
     CU(launch_sampler(s, st, pdl_samp)); nl++; }
   // no programmatic overlap with the sampler: later kernels read the slot state before their griddepcontrol.wait
   CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st, false)); nl++; (void)pdl_emb;
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
-    if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d));
-    else CU(launch_norm(h, e->d_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d));
+    if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d, next_trace()));
+    else CU(launch_norm(h, e->d_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d, next_trace()));
     nl++;
     CU(G(e->d_xn, L.wqkv, QKV, d, GE_F32, nullptr, e->d_qkv, QKV));
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload;
-      CU(launch_attn_decode(a, st, pdl_attn)); nl++; }
+      a.probe = (e->use_trace && l == 5) ? e->d_trace + 300 : nullptr;
+      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload; a.mma = e->attn_mma; a.trace = next_trace();
+      if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
+      nl++; }
     CU(G(e->d_attn_bf, L.wo, d, QD, GE_F32, nullptr, e->d_y, d));
-    CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qc, QD, e->d_y, d)); nl++;
+    CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qc, QD, e->d_y, d, next_trace())); nl++;
     CU(G(e->d_xn, L.wq_c, QD, d, GE_F32, nullptr, e->d_qc, QD));
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
       a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload;
-      CU(launch_attn_decode(a, st, pdl_attn)); nl++; }
+      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload; a.mma = e->attn_mma; a.trace = next_trace();
+      if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
+      nl++; }
     CU(G(e->d_attn_bf, L.wo_c, d, QD, GE_F32, nullptr, e->d_y, d));
-    CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_y, d, nullptr, 0)); nl++;
+    CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_y, d, nullptr, 0, next_trace())); nl++;
     CU(G(e->d_xn, L.wgu, 2 * I, d, GE_GEGLU_BF16, nullptr, e->d_act_bf, I));
     CU(G(e->d_act_bf, L.wd, d, I, GE_F32, nullptr, e->d_y, d));
   }
@@ -1052,8 +1067,9 @@ extern "C" int t5g_debug_trace(T5GEngine* e, uint64_t* begin_ns, uint64_t* end_n
   T5G_CUDA(cudaSetDevice(e->device));
   CU(cudaDeviceSynchronize());
   const int n = std::min(std::min(max_entries, e->last_nodes_per_step > 0 ? e->last_nodes_per_step : T5G_TRACE_STRIDE), T5G_TRACE_STRIDE);
-  CU(cudaMemcpy(begin_ns, e->d_trace, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(end_ns, e->d_trace + T5G_TRACE_STRIDE, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+  const int ncopy = std::min(max_entries, T5G_TRACE_STRIDE);   // entries past the kernel count hold optional in-kernel probes
+  CU(cudaMemcpy(begin_ns, e->d_trace, sizeof(uint64_t) * ncopy, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(end_ns, e->d_trace + T5G_TRACE_STRIDE, sizeof(uint64_t) * ncopy, cudaMemcpyDeviceToHost));
   *n_out = n;
   return T5G_OK;
 }

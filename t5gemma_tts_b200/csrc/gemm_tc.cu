@@ -37,7 +37,18 @@ struct TcParams {
   int k_blocks_per_split;     // K-slabs handled by one CTA (blockIdx.z selects the split)
   int split_k;
   int atomic;                 // split-K partials reduced with red.global.add.f32 into a zeroed fp32 output (GE_F32)
+  unsigned long long* trace;
+  unsigned long long* probe;
 };
+
+// GeGLU in the bf16 epilogues: tanh.approx.f32 (MUFU, rel. error ~2^-11, far inside bf16's 2^-8) -- the batched
+// epilogue is instruction-issue bound (64 values per thread), the libm tanhf path costs ~40 instructions per value
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(k0 * (x + k1 * x * x * x)));
+  return 0.5f * x * (1.f + t);
+}
 
 __device__ __forceinline__ void epilogue_store(const TcParams& p, int t, int f, float val, float up, float bias, bool even) {
   if (t >= p.M || f >= p.N) return;
@@ -48,8 +59,28 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, int t, int f, 
     case GE_BIAS_GELU_BF16:
       reinterpret_cast<bf16*>(p.out)[(size_t)t * p.ldo + f] = __float2bfloat16(gelu_erf_f(val + bias)); break;
     case GE_GEGLU_BF16:     // even feature = gate row, `up` = the odd neighbour
-      if (even) reinterpret_cast<bf16*>(p.out)[(size_t)t * p.ldo + (f >> 1)] = __float2bfloat16(gelu_tanh_f(val) * up);
+      if (even) reinterpret_cast<bf16*>(p.out)[(size_t)t * p.ldo + (f >> 1)] = __float2bfloat16(gelu_tanh_fast(val) * up);
       break;
+  }
+}
+
+// one 16-token chunk of a TMEM lane (= output feature f) -> global, epilogue kind resolved at compile time
+template <int EPI>
+__device__ __forceinline__ void store_chunk(const TcParams& p, const float (&v)[16], int tbase, int f, float bias, bool even) {
+  const bool fok = f < p.N;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int t = tbase + j;
+    if (t >= p.M) break;                                   // warp-uniform
+    if (EPI == GE_GEGLU_BF16) {
+      const float up = __shfl_xor_sync(0xffffffffu, v[j], 1);
+      if (even && fok) reinterpret_cast<bf16*>(p.out)[(size_t)t * p.ldo + (f >> 1)] = __float2bfloat16(gelu_tanh_fast(v[j]) * up);
+    } else if (fok) {
+      if (EPI == GE_F32) reinterpret_cast<float*>(p.out)[(size_t)t * p.ldo + f] = v[j];
+      else if (EPI == GE_BF16) reinterpret_cast<bf16*>(p.out)[(size_t)t * p.ldo + f] = __float2bfloat16(v[j]);
+      else if (EPI == GE_BIAS_F32) reinterpret_cast<float*>(p.out)[(size_t)t * p.ldo + f] = v[j] + bias;
+      else if (EPI == GE_BIAS_GELU_BF16) reinterpret_cast<bf16*>(p.out)[(size_t)t * p.ldo + f] = __float2bfloat16(gelu_erf_f(v[j] + bias));
+    }
   }
 }
 
@@ -203,12 +234,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 // depth (profiles/r1_gemv_design_experiments.md).  Completion is tracked with cp.async.mbarrier.arrive.noinc, so
 // producers never block; the four producer warps become the epilogue warps once their loads are issued.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int ST_THREADS = 160;     // warps 0-3: cp.async producers, then epilogue; warp 4: MMA issuer + TMEM alloc
+constexpr int ST_THREADS = 288;     // warps 0-3: cp.async producers, then epilogue; warp 4: MMA issuer + TMEM alloc;
+                                    // warps 5-8: producers only (the producer side is instruction-issue bound: two
+                                    // producer warps per scheduler and 3-4 instructions per 16-byte copy)
+constexpr int ST_PROD = 256;
 
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill (rows beyond N / M)
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
-}
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -224,9 +254,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) gemm_stream_kernel(const bf16* 
   const int kb_total = p.K / TC_BK;
   const int kb0 = blockIdx.z * p.k_blocks_per_split;
   const int nkb = min(p.k_blocks_per_split, kb_total - kb0);
+  unsigned long long* probe = (p.probe && blockIdx.x == gridDim.x / 2 && blockIdx.z == 0) ? p.probe : nullptr;
+#define GS_PROBE(k) do { if (probe && lane == 0) probe[k] = globaltimer_ns(); } while (0)
+  if (warp == 0) GS_PROBE(0);
 
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&S.full[i], 128); mbar_init(&S.empty[i], 1); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&S.full[i], ST_PROD / 4); mbar_init(&S.empty[i], 1); }
     mbar_init(&S.acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -239,46 +272,68 @@ __global__ void __launch_bounds__(ST_THREADS, 1) gemm_stream_kernel(const bf16* 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = S.tmem_base;
 
-  if (warp < 4) {
-    // ===== producers: thread t copies chunks t, t+128, ... of every tile (8 consecutive threads = one 128 B row) =====
-    auto load_w = [&](int i, int s) {
-      const int kc = (kb0 + i) * TC_BK;
+  if (warp != 4) {
+    // ===== producers.  HBM locality decides this kernel: fetching one 128-byte K-slab of 128 different weight rows per
+    //       stage touches 128 DRAM pages for 128 bytes each (measured 3.2 TB/s on gate|up).  Stages are therefore filled
+    //       in GROUPS of 4 consecutive k-blocks: a warp copies 512 contiguous bytes of one weight row (4 swizzle atoms,
+    //       one per ring stage of the group), 8 rows per warp-instruction column.  Lanes 8j..8j+7 of every warp feed
+    //       stage j of the group, so each stage's "full" barrier counts 64 threads.  Per-thread constants keep a
+    //       16-byte copy at ~3 instructions. =====
+    const int ptid = warp < 4 ? tid : tid - 32;
+    const int j = (ptid & 31) >> 3, col = ptid & 7, row0 = ptid >> 5;          // stage of the group, 16-byte column, first row
+    const uint32_t swz = (uint32_t)((col ^ (row0 & 7)) << 4);                   // (row & 7) == (row0 & 7) for rows row0 + 8u
+    const uint32_t wdst0 = smem_u32(S.w[0]) + row0 * 128 + swz, xdst0 = smem_u32(S.x[0]) + row0 * 128 + swz;
+    constexpr uint32_t W_STAGE = TC_BM * TC_BK * 2, X_STAGE = TOKT * TC_BK * 2;
+    const bf16* wbase = W + (size_t)kb0 * TC_BK + col * 8;
+    const bf16* xbase = X + (size_t)kb0 * TC_BK + col * 8;
+    auto load_w = [&](int i, int s) {                                            // k-block i (relative to kb0) -> ring stage s
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int c = tid + u * 128, row = c >> 3, col = c & 7;
-        const int n = f0 + row;
-        cp_async16(S.w[s] + row * 128 + ((col ^ (row & 7)) << 4), W + (size_t)min(n, p.N - 1) * p.K + kc + col * 8, n < p.N);
+      for (int u = 0; u < TC_BM / 8; ++u) {
+        const int n = f0 + row0 + 8 * u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(wdst0 + s * W_STAGE + u * 1024),
+                     "l"(wbase + (size_t)min(n, p.N - 1) * p.K + (size_t)i * TC_BK), "r"(n < p.N ? 16 : 0) : "memory");
       }
     };
     auto load_x = [&](int i, int s) {
-      const int kc = (kb0 + i) * TC_BK;
 #pragma unroll
-      for (int u = 0; u < (TOKT * 8 + 127) / 128; ++u) {
-        const int c = tid + u * 128, row = c >> 3, col = c & 7;
-        if (c < TOKT * 8) {
-          const int m = t0 + row;
-          cp_async16(S.x[s] + row * 128 + ((col ^ (row & 7)) << 4), X + (size_t)min(m, p.M - 1) * p.K + kc + col * 8, m < p.M);
-        }
+      for (int u = 0; u < (TOKT + 7) / 8; ++u) {
+        const int r = row0 + 8 * u, m = t0 + r;
+        if (r < TOKT)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xdst0 + s * X_STAGE + u * 1024),
+                       "l"(xbase + (size_t)min(m, p.M - 1) * p.K + (size_t)i * TC_BK), "r"(m < p.M ? 16 : 0) : "memory");
       }
     };
-    const int pre = min(nkb, NSTAGE);
-    for (int i = 0; i < pre; ++i) load_w(i, i);          // weights are immutable: before the PDL dependency resolves
+    static_assert(NSTAGE % 4 == 0, "ring stages are filled in groups of 4");
+    constexpr int NGRP = NSTAGE / 4;                                             // groups in the ring
+    const int ngroups = (nkb + 3) / 4;
+    // weights are immutable: the first ring-full is requested before the PDL dependency resolves
+    for (int g = 0; g < min(ngroups, NGRP); ++g) { const int i = g * 4 + j; if (i < nkb) load_w(i, i); }
     pdl_launch_dependents();
     pdl_wait();
-    for (int i = 0; i < pre; ++i) { load_x(i, i); cp_async_arrive(&S.full[i]); }
-    for (int i = NSTAGE; i < nkb; ++i) {
-      const int s = i % NSTAGE;
-      mbar_wait(&S.empty[s], ((i / NSTAGE) - 1) & 1);
-      load_w(i, s);
-      load_x(i, s);
-      cp_async_arrive(&S.full[s]);
+    trace_begin(p.trace);
+    if (warp == 0) GS_PROBE(1);
+    for (int g = 0; g < min(ngroups, NGRP); ++g) { const int i = g * 4 + j; if (i < nkb) { load_x(i, i); cp_async_arrive(&S.full[i]); } }
+    for (int g = NGRP; g < ngroups; ++g) {
+      // tcgen05.commit releases stages in order: once the LAST stage of the group is free all four are, and the
+      // whole warp issues its 512-byte row segments together (no divergence on four different barriers)
+      const int ilast = min(g * 4 + 3, nkb - 1);
+      mbar_wait(&S.empty[ilast % NSTAGE], ((ilast / NSTAGE) - 1) & 1);
+      const int i = g * 4 + j, s = i % NSTAGE;
+      if (i < nkb) {
+        load_w(i, s);
+        load_x(i, s);
+        cp_async_arrive(&S.full[s]);
+      }
     }
+    if (warp == 0) GS_PROBE(2);
   } else if (lane == 0) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TOKT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     for (int i = 0; i < nkb; ++i) {
       const int s = i % NSTAGE;
       mbar_wait(&S.full[s], (i / NSTAGE) & 1);
+      if (i == 0) GS_PROBE(5);
+      if (i == nkb / 2) GS_PROBE(6);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // cp.async (generic proxy) -> tcgen05 (async proxy)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t wa = smem_u32(S.w[s]), xa = smem_u32(S.x[s]);
@@ -288,34 +343,43 @@ __global__ void __launch_bounds__(ST_THREADS, 1) gemm_stream_kernel(const bf16* 
       umma_commit(&S.empty[s]);
     }
     umma_commit(&S.acc_full);
+    GS_PROBE(7);
   }
-  if (warp < 4) {
-    // ===== epilogue (same warps): TMEM lane quarter = warp index =====
-    const int q = warp, fl = q * 32 + lane, f = f0 + fl;
+  if (warp != 4) {
+    // ===== epilogue: all 8 producer warps.  A warp may only read the TMEM lane quarter (warp id % 4); warps 0-3 take the
+    //       first half of the token columns, warps 5-8 the second half (one 16-column chunk is the granule). =====
+    const int q = warp & 3, fl = q * 32 + lane, f = f0 + fl;
+    constexpr int NCH = TOKT / 16;
+    const int ch0 = (NCH >= 2) ? (warp < 4 ? 0 : NCH / 2) : 0;
+    const int ch1 = (NCH >= 2) ? (warp < 4 ? NCH / 2 : NCH) : (warp < 4 ? NCH : 0);
     mbar_wait(&S.acc_full, 0);
+    if (warp == 0) GS_PROBE(3);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* red = reinterpret_cast<float*>(&S.w[0][0]);
+    const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
+    const bool even = (lane & 1) == 0;
 #pragma unroll 1
-    for (int c = 0; c < TOKT; c += 16) {
+    for (int ch = ch0; ch < ch1; ++ch) {
+      const int c = ch * 16;
       if (t0 + c >= p.M) break;
       float v[16];
       tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
       if (p.atomic) {
+        float* o = reinterpret_cast<float*>(p.out) + (size_t)(t0 + c) * p.ldo + f;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (t0 + c + j < p.M && f < p.N) atomicAdd(reinterpret_cast<float*>(p.out) + (size_t)(t0 + c + j) * p.ldo + f, v[j]);
-        continue;
-      }
-      if (p.split_k > 1) {
+          if (t0 + c + j < p.M && f < p.N) atomicAdd(o + (size_t)j * p.ldo, v[j]);
+      } else if (p.split_k > 1) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) red[(c + j) * TC_BM + fl] = v[j];
-        continue;
-      }
-      const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float other = (p.epilogue == GE_GEGLU_BF16) ? __shfl_xor_sync(0xffffffffu, v[j], 1) : 0.f;
-        epilogue_store(p, t0 + c + j, f, v[j], other, bias, (lane & 1) == 0);
+      } else {
+        switch (p.epilogue) {
+          case GE_F32: store_chunk<GE_F32>(p, v, t0 + c, f, bias, even); break;
+          case GE_BF16: store_chunk<GE_BF16>(p, v, t0 + c, f, bias, even); break;
+          case GE_BIAS_F32: store_chunk<GE_BIAS_F32>(p, v, t0 + c, f, bias, even); break;
+          case GE_BIAS_GELU_BF16: store_chunk<GE_BIAS_GELU_BF16>(p, v, t0 + c, f, bias, even); break;
+          default: store_chunk<GE_GEGLU_BF16>(p, v, t0 + c, f, bias, even); break;
+        }
       }
     }
   }
@@ -340,6 +404,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) gemm_stream_kernel(const bf16* 
     }
     cluster.sync();
   }
+  if (warp == 0) GS_PROBE(4);
+  trace_end(p.trace);
+#undef GS_PROBE
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 4) {
@@ -425,7 +492,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
     if (e != cudaSuccess) return e;
     pdl = false;
   }
-  TcParams p{a.M, a.N, a.K, a.epilogue, a.bias, a.out, a.ldo, kbps, split, atomic};
+  TcParams p{a.M, a.N, a.K, a.epilogue, a.bias, a.out, a.ldo, kbps, split, atomic, a.trace, a.probe};
   dim3 grid((a.N + TC_BM - 1) / TC_BM, (a.M + tokt - 1) / tokt, split);
   static int use_stream = -1;
   if (use_stream < 0) { const char* e = getenv("T5G_GEMM_STREAM"); use_stream = e ? atoi(e) : 1; }
@@ -433,7 +500,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
     switch (tokt) {
       case 16: return launch_stream<16, 8>(a, p, grid, st, pdl);
       case 32: return launch_stream<32, 8>(a, p, grid, st, pdl);
-      default: return launch_stream<64, 6>(a, p, grid, st, pdl);
+      default: return launch_stream<64, 8>(a, p, grid, st, pdl);
     }
   }
   switch (tokt) {

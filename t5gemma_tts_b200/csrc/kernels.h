@@ -40,6 +40,7 @@ struct AttnDecodeArgs {
   const int* block_table; int bt_stride;   // [slot][bt_stride] page ids
   const float* q; int q_stride;            // [B, q_stride] raw (pre-RoPE) queries, Hq*D used
   int preload;                             // 1: issue the first K/V row loads before griddepcontrol.wait
+  int mma;                                 // 1 (batched rows): tile kernel of attention_mma.cu (cp.async ring + mma.sync)
   const float* kv_new; int kv_stride;      // self: raw k at kv_new[b*kv_stride + 0..KD), v at +KD ; null for cross
   const SlotDev* slots;
   int B, Hq, Hkv, D;
@@ -52,8 +53,11 @@ struct AttnDecodeArgs {
   bf16* out_bf;                            // bf16 copy for the tensor-core o_proj of the batched path (either may be null)
   PrefetchRange pf[2];
   unsigned long long* trace;
+  unsigned long long* probe;               // optional [B][11] in-kernel checkpoints of the (kv head 0, split 0) CTAs (debug)
 };
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
+bool attn_decode_mma_supported(const AttnDecodeArgs& a);
+cudaError_t launch_attn_decode_mma(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);   // attention_mma.cu
 
 // ---------------- cross-attention fused into its output projection, bs<=4 decode (xattn_fused.cu) ----------------
 struct XAttnOprojArgs {
@@ -77,7 +81,8 @@ cudaError_t launch_embed(const bf16* table, const int* ids, float scale, float* 
 // h_out = h_in + rmsnorm(y)*g_post (if y) ; xn = bf16(rmsnorm(h_out)*g_pre) (if xn) ; hf32 = fp32 normed (if xf)
 cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, const float* g_pre, float* h_out,
                         bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st, bool pdl = false,
-                        float* zero_a = nullptr, int na = 0, float* zero_b = nullptr, int nb = 0);
+                        float* zero_a = nullptr, int na = 0, float* zero_b = nullptr, int nb = 0,
+                        unsigned long long* trace = nullptr);
 // qkv fp32 [M, ld] -> RoPE(q,k) at pos[M]; q_out bf16 [M,Hq*D]; k_out/v_out bf16 [M,Hkv*D]; optional page append
 struct RopeSplitArgs {
   const float* qkv; int ld; int q_off, k_off, v_off;   // column offsets (negative = absent)
@@ -110,6 +115,8 @@ struct GemmArgs {
   int epilogue; const float* bias;
   void* out; int ldo;     // GE_GEGLU: N counts interleaved rows, out is [M, N/2]
   int out_zeroed;         // GE_F32 split-K: the caller guarantees `out` is already zero (no memset node is inserted)
+  unsigned long long* trace = nullptr;   // optional in-step timestamps (T5G_TRACE)
+  unsigned long long* probe = nullptr;   // optional [8] in-kernel checkpoints of one CTA (debug)
 };
 cudaError_t launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool pdl = false);   // tcgen05/TMEM/TMA path (gemm_tc.cu)

@@ -32,7 +32,8 @@ constexpr int NK_MAXV = 8;                       // float4 per thread: d <= 128*
 __global__ void __launch_bounds__(NK_THREADS) norm_kernel(const float* h_in, const float* y,
                                                           const float* __restrict__ g_post, const float* __restrict__ g_pre,
                                                           float* h_out, bf16* xn, float* xf, int d, float eps,
-                                                          float* zero_a, int na, float* zero_b, int nb) {
+                                                          float* zero_a, int na, float* zero_b, int nb,
+                                                          unsigned long long* trace) {
   __shared__ float red[128];
   const size_t base = (size_t)blockIdx.x * d;
   const int nv = d >> 2;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(NK_THREADS) norm_kernel(const float* h_in, con
   }
   pdl_launch_dependents();
   pdl_wait();
+  trace_begin(trace);
   float4 hv[NK_MAXV], yv[NK_MAXV];
   float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
 #pragma unroll
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(NK_THREADS) norm_kernel(const float* h_in, con
       }
     }
   }
+  trace_end(trace);
 }
 
 // one CTA per token; threads over (head, j<D/2)
@@ -252,7 +255,7 @@ cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float sc
 
 cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, const float* g_pre, float* h_out,
                         bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st, bool pdl,
-                        float* zero_a, int na, float* zero_b, int nb) {
+                        float* zero_a, int na, float* zero_b, int nb, unsigned long long* trace) {
   if (M <= 0) return cudaSuccess;
   if (d % 4 != 0 || d > NK_THREADS * 4 * NK_MAXV || (na & 3) || (nb & 3)) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg{};
@@ -265,7 +268,7 @@ cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, norm_kernel, h_in, y, g_post, g_pre, h_out, xn, xf, d, eps, zero_a, na, zero_b, nb);
+  return cudaLaunchKernelEx(&cfg, norm_kernel, h_in, y, g_post, g_pre, h_out, xn, xf, d, eps, zero_a, na, zero_b, nb, trace);
 }
 
 cudaError_t launch_rope_split(const RopeSplitArgs& a, cudaStream_t st) {

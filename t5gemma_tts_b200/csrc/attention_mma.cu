@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int AM_NT = 128, AM_WARPS = 4;
+constexpr int AM_NT = 256, AM_WARPS = 8;  // the kernel is instruction-issue bound: two warps per scheduler
 constexpr int AM_TT = 32;                 // tokens per tile
 constexpr int AM_NST = 2;                 // ring stages
 constexpr int AM_MAX_NS = 8;
@@ -50,28 +50,29 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 template <int D> struct AmGeo {
   static constexpr int LD = D + 8;                         // padded row (elements): 16-byte skew per row
   static constexpr int KS = D / 16;                        // k-steps of the score MMA
+  static constexpr int KSH = (KS + 1) / 2;                 // ... per k-half (two warps share a 16-token group)
   static constexpr int NMT = D / 16;                       // 16-dim m-tiles of the output MMA
   static constexpr int MTW = (NMT + AM_WARPS - 1) / AM_WARPS;   // m-tiles per warp
   static constexpr size_t stage_elems = (size_t)2 * AM_TT * LD; // K tile + V tile
   static constexpr size_t dyn_bytes = (AM_NST * stage_elems + (size_t)8 * LD + (size_t)8 * (AM_TT + 8)) * sizeof(bf16);
 };
 
-// grid (Hkv, NS, B), cluster (1, NS, 1), 128 threads
+// grid (Hkv, NS, B), cluster (1, NS, 1), 256 threads
 template <int G, int D>
 __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a) {
   using Geo = AmGeo<D>;
-  constexpr int LD = Geo::LD, KS = Geo::KS, NMT = Geo::NMT, MTW = Geo::MTW;
+  constexpr int LD = Geo::LD, KS = Geo::KS, KSH = Geo::KSH, NMT = Geo::NMT, MTW = Geo::MTW;
+  static_assert(AM_TT == 32, "one token per lane in the softmax phase, two 16-token groups");
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char am_dyn[];
   bf16* ring = reinterpret_cast<bf16*>(am_dyn);                         // [NST][2][TT][LD]
   bf16* qb = ring + AM_NST * Geo::stage_elems;                          // [8][LD]   rotated q (rows >= G are zero)
   bf16* pb = qb + 8 * LD;                                               // [8][TT+8] probabilities of the tile
-  __shared__ float qs[G][D];
   __shared__ float cs[D / 2], sn[D / 2];
   __shared__ float knew[D], vnew[D];
   __shared__ int bt_s[AM_BT_CACHE];
-  __shared__ float sc[G][AM_TT];
+  __shared__ float scp[2][G][AM_TT];                                    // partial q.k of the two k-halves
   __shared__ float corr_s[8];
   __shared__ unsigned rowoff[AM_NST][AM_TT];                            // row offsets (elements) inside the layer's K plane
   __shared__ __align__(16) float o_s[G][D];
@@ -94,11 +95,17 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   const int active = sl.active;
   const int L = a.is_cross ? sl.n_text : sl.cur_len;
   const float pos = sl.pos;
-  for (int i = tid; i < D / 2; i += AM_NT) {
-    if (a.rope_cs) { cs[i] = a.rope_cs[(size_t)b * D + i]; sn[i] = a.rope_cs[(size_t)b * D + D / 2 + i]; }
-    else { float s_, c_; sincosf(pos * a.inv_freq[i], &s_, &c_); cs[i] = c_; sn[i] = s_; }
+  {
+    // loads first, shared-memory stores after: one round trip for the slot, the RoPE table and the block table
+    float rc = 1.f, rs = 0.f;
+    const bool rope_tab = a.rope_cs != nullptr && tid < D / 2;
+    if (rope_tab) { rc = a.rope_cs[(size_t)b * D + tid]; rs = a.rope_cs[(size_t)b * D + D / 2 + tid]; }
+    const int btv = (tid < a.bt_stride) ? bt[tid] : 0;                  // AM_BT_CACHE == AM_NT entries
+    if (rope_tab) { cs[tid] = rc; sn[tid] = rs; }
+    if (!a.rope_cs) for (int i = tid; i < D / 2; i += AM_NT) { float s_, c_; sincosf(pos * a.inv_freq[i], &s_, &c_); cs[i] = c_; sn[i] = s_; }
+    bt_s[tid] = btv;
   }
-  for (int i = tid; i < AM_BT_CACHE; i += AM_NT) bt_s[i] = (i < a.bt_stride) ? bt[i] : 0;
+  static_assert(AM_BT_CACHE == AM_NT && D / 2 <= AM_NT, "prologue mapping");
   for (int i = tid; i < 8 * LD; i += AM_NT) qb[i] = __float2bfloat16(0.f);
   for (int i = tid; i < 8 * (AM_TT + 8); i += AM_NT) pb[i] = __float2bfloat16(0.f);
   const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
@@ -148,61 +155,61 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   pdl_wait();
   trace_begin(a.trace);
   AM_PROBE(2);
-  // ---- the producer's outputs: raw q and the new k/v ----
-  constexpr int QPT = (G * D + AM_NT - 1) / AM_NT, KPT = (D + AM_NT - 1) / AM_NT;
+  if (!active) return;                               // uniform over the whole cluster (same b)
+  // ---- the producer's outputs: raw q and the new k/v.  A thread loads both elements of a rotation pair (j, j + D/2),
+  //      rotates in registers (PM-RoPE at the row's progress position) and stores the MMA operand directly. ----
   {
-    float rq[QPT], rk[KPT], rv[KPT];
+    constexpr int QP = (G * D / 2 + AM_NT - 1) / AM_NT;
+    float x1[QP], x2[QP];
+    float k1 = 0.f, k2 = 0.f, vv = 0.f;
+    const float* qp = a.q + (size_t)b * a.q_stride + (size_t)(hk * G) * D;
 #pragma unroll
-    for (int u = 0; u < QPT; ++u) {
-      const int i = tid + u * AM_NT;
-      rq[u] = (i < G * D) ? __ldcg(a.q + (size_t)b * a.q_stride + (size_t)(hk * G) * D + i) : 0.f;
+    for (int u = 0; u < QP; ++u) {
+      const int i = tid + u * AM_NT, g = i / (D / 2), j = i - g * (D / 2);
+      const bool ok = i < G * D / 2;
+      x1[u] = ok ? __ldcg(qp + g * D + j) : 0.f;
+      x2[u] = ok ? __ldcg(qp + g * D + j + D / 2) : 0.f;
+    }
+    if (has_new) {
+      const float* kp = a.kv_new + (size_t)b * a.kv_stride + (size_t)hk * D;
+      const float* vp = a.kv_new + (size_t)b * a.kv_stride + (size_t)(a.Hkv + hk) * D;
+      if (tid < D / 2) { k1 = __ldcg(kp + tid); k2 = __ldcg(kp + tid + D / 2); }
+      if (tid < D) vv = __ldcg(vp + tid);
     }
 #pragma unroll
-    for (int u = 0; u < KPT; ++u) {
-      const int j = tid + u * AM_NT;
-      const bool ok = !a.is_cross && j < D;
-      rk[u] = ok ? __ldcg(a.kv_new + (size_t)b * a.kv_stride + (size_t)hk * D + j) : 0.f;
-      rv[u] = ok ? __ldcg(a.kv_new + (size_t)b * a.kv_stride + (size_t)(a.Hkv + hk) * D + j) : 0.f;
+    for (int u = 0; u < QP; ++u) {
+      const int i = tid + u * AM_NT, g = i / (D / 2), j = i - g * (D / 2);
+      if (i < G * D / 2) {
+        qb[g * LD + j] = __float2bfloat16(x1[u] * cs[j] - x2[u] * sn[j]);
+        qb[g * LD + j + D / 2] = __float2bfloat16(x2[u] * cs[j] + x1[u] * sn[j]);
+      }
     }
-    if (!active) return;                             // uniform over the whole cluster (same b)
-#pragma unroll
-    for (int u = 0; u < QPT; ++u) { const int i = tid + u * AM_NT; if (i < G * D) qs[i / D][i % D] = rq[u]; }
-#pragma unroll
-    for (int u = 0; u < KPT; ++u) {
-      const int j = tid + u * AM_NT;
-      if (j < D) { knew[j] = rk[u]; vnew[j] = rv[u]; }
+    if (has_new) {
+      if (tid < D / 2) { knew[tid] = k1 * cs[tid] - k2 * sn[tid]; knew[tid + D / 2] = k2 * cs[tid] + k1 * sn[tid]; }
+      if (tid < D) vnew[tid] = vv;
     }
   }
+  static_assert(D <= AM_NT, "one thread per element of the new k/v row");
   __syncthreads();
   AM_PROBE(3);
-  cluster.barrier_arrive();                          // "this CTA is running": waited on before the first remote store
-  // rotate (pairs j, j + D/2) and round to bf16: q into the MMA operand buffer, the new k in place
-  for (int i = tid; i < G * D / 2; i += AM_NT) {
-    const int g = i / (D / 2), j = i - g * (D / 2);
-    const float x1 = qs[g][j], x2 = qs[g][j + D / 2];
-    qb[g * LD + j] = __float2bfloat16(x1 * cs[j] - x2 * sn[j]);
-    qb[g * LD + j + D / 2] = __float2bfloat16(x2 * cs[j] + x1 * sn[j]);
-  }
-  if (has_new) {
-    for (int j = tid; j < D / 2; j += AM_NT) {
-      const float x1 = knew[j], x2 = knew[j + D / 2];
-      knew[j] = x1 * cs[j] - x2 * sn[j];
-      knew[j + D / 2] = x2 * cs[j] + x1 * sn[j];
-    }
-  }
-  __syncthreads();
+  if (NS > 1) cluster.barrier_arrive();              // "this CTA is running": waited on before the first remote store
   if (has_new) {   // append to the page (K post-RoPE), visible to later steps
     const int t = L - 1, page = page_of(t), off = t % PT;
     bf16* kd = a.pool.ptr(a.layer, 0, page) + ((size_t)hk * PT + off) * D;
     bf16* vd = a.pool.ptr(a.layer, 1, page) + ((size_t)hk * PT + off) * D;
-    for (int j = tid; j < D; j += AM_NT) { kd[j] = __float2bfloat16(knew[j]); vd[j] = __float2bfloat16(vnew[j]); }
+    if (tid < D) { kd[tid] = __float2bfloat16(knew[tid]); vd[tid] = __float2bfloat16(vnew[tid]); }
   }
-  // q fragments (B operand of the score MMA): B[k = dim][n = head] from qb[head][dim]
-  uint32_t qf[KS][2];
+  // q fragments (B operand of the score MMA): B[k = dim][n = head] from qb[head][dim]; this warp's k-half only
+  const int tg = warp & 1, kh = (warp >> 1) & 1;      // score phase (warps 0-3): 16-token group, k-half
+  uint32_t qf[KSH][2];
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) ldsm_x2(qf[ks], qb + (size_t)(lane & 7) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
-
+  for (int i = 0; i < KSH; ++i) {
+    const int ks = kh * KSH + i;
+    if (ks < KS) ldsm_x2(qf[i], qb + (size_t)(lane & 7) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
+    else { qf[i][0] = 0u; qf[i][1] = 0u; }
+  }
   AM_PROBE(4);
+
   const float inv_cap = a.softcap > 0.f ? 1.f / a.softcap : 0.f;
   float m_run = -INFINITY, l_run = 0.f;              // warp h < G: running max / sum of head h (lane-replicated)
   float acc[MTW][4];
@@ -221,39 +228,37 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
     const int tile_t0 = t_begin + ti * AM_TT;
     if (has_new && L - 1 >= tile_t0 && L - 1 < tile_t0 + AM_TT) {       // CTA-uniform: the new token's row comes from registers
       const int tok = L - 1 - tile_t0;
-      for (int j = tid; j < D; j += AM_NT) { kb[(size_t)tok * LD + j] = __float2bfloat16(knew[j]); vb[(size_t)tok * LD + j] = __float2bfloat16(vnew[j]); }
+      if (tid < D) { kb[(size_t)tok * LD + tid] = __float2bfloat16(knew[tid]); vb[(size_t)tok * LD + tid] = __float2bfloat16(vnew[tid]); }
       __syncthreads();
     }
-    // ---- scores: warp w < TT/16 owns tokens [16w, 16w+16) of the tile ----
-    if (warp < AM_TT / 16 && tile_t0 + warp * 16 < t_end) {
+    // ---- partial scores: warps 0-3 = (16-token group tg) x (k-half kh); rows past the range are zero-filled ----
+    if (warp < 4) {
       float c[4] = {0.f, 0.f, 0.f, 0.f};
-      const bf16* arow = kb + (size_t)(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8;
+      const bf16* arow = kb + (size_t)(tg * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (lane >> 4) * 8 + kh * KSH * 16;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        uint32_t af[4];
-        ldsm_x4(af, arow + ks * 16);
-        mma_bf16_16816(c, af, qf[ks]);
+      for (int i = 0; i < KSH; ++i) {
+        if (kh * KSH + i < KS) {
+          uint32_t af[4];
+          ldsm_x4(af, arow + i * 16);
+          mma_bf16_16816(c, af, qf[i]);
+        }
       }
       // c0,c1: token g8, heads 2*t4, 2*t4+1 ; c2,c3: token g8+8
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const int head = 2 * t4 + (r & 1), tok = warp * 16 + g8 + (r >> 1) * 8;
-        if (head < G) {
-          float s = c[r] * a.scale;
-          if (a.softcap > 0.f) {
-            const float e2 = __expf(2.f * s * inv_cap);
-            s = a.softcap * (1.f - __fdividef(2.f, e2 + 1.f));
-          }
-          sc[head][tok] = (tile_t0 + tok < t_end) ? s : -INFINITY;
-        }
+        const int head = 2 * t4 + (r & 1), tok = tg * 16 + g8 + (r >> 1) * 8;
+        if (head < G) scp[kh][head][tok] = c[r];
       }
-    } else if (warp < AM_TT / 16) {
-      for (int i = lane; i < G * 16; i += 32) sc[i / 16][warp * 16 + (i & 15)] = -INFINITY;
     }
     __syncthreads();
-    // ---- online softmax: warp h owns head h, lane = token of the tile ----
+    // ---- scale / softcap / mask + online softmax: warp h owns head h, lane = token of the tile ----
     if (warp < G) {
-      const float s = sc[warp][lane];
+      float s = (scp[0][warp][lane] + scp[1][warp][lane]) * a.scale;
+      if (a.softcap > 0.f) {
+        const float e2 = __expf(2.f * s * inv_cap);
+        s = a.softcap * (1.f - __fdividef(2.f, e2 + 1.f));
+      }
+      if (tile_t0 + lane >= t_end) s = -INFINITY;
       float tm = s;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
@@ -287,12 +292,38 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
         }
       }
     }
-    __syncthreads();                                       // stage, sc and pb are free again
+    __syncthreads();                                       // stage, scp and pb are free again
     issue_tile(ti + AM_NST);
   }
-
   AM_PROBE(8);
-  // ---- CTA partial -> shared memory: o_s[head][dim] (unnormalised), ml_s[head] ----
+
+  if (warp < G && lane == 0) { ml_s[warp][0] = m_run; ml_s[warp][1] = l_run; }
+  if (NS == 1) {
+    // ---- no split: normalise and store straight from the accumulator registers ----
+    __syncthreads();
+    const float i0 = (2 * t4 < G && ml_s[2 * t4][1] > 0.f) ? 1.f / ml_s[2 * t4][1] : 0.f;
+    const float i1 = (2 * t4 + 1 < G && ml_s[2 * t4 + 1][1] > 0.f) ? 1.f / ml_s[2 * t4 + 1][1] : 0.f;
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) {
+      const int mt = warp + i * AM_WARPS;
+      if (mt < NMT) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int head = 2 * t4 + (r & 1), dim = mt * 16 + g8 + (r >> 1) * 8;
+          if (head < G) {
+            const float o = acc[i][r] * ((r & 1) ? i1 : i0);
+            const size_t idx = (size_t)b * a.Hq * D + (size_t)(hk * G + head) * D + dim;
+            if (a.out) a.out[idx] = o;
+            if (a.out_bf) a.out_bf[idx] = __float2bfloat16(o);
+          }
+        }
+      }
+    }
+    AM_PROBE(10);
+    trace_end(a.trace);
+    return;
+  }
+  // ---- CTA partial -> shared memory: o_s[head][dim] (unnormalised) ----
 #pragma unroll
   for (int i = 0; i < MTW; ++i) {
     const int mt = warp + i * AM_WARPS;
@@ -304,7 +335,6 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
       }
     }
   }
-  if (warp < G && lane == 0) { ml_s[warp][0] = m_run; ml_s[warp][1] = l_run; }
   __syncthreads();
   // ---- split-KV merge across the cluster (same scheme as attention.cu): push the slice rank r finalises ----
   const int dslice = D / NS;

@@ -78,7 +78,7 @@ struct T5GEngine {
   float *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_memory = nullptr, *p_ckv = nullptr, *p_final = nullptr;
   bf16 *p_xn = nullptr, *p_q = nullptr, *p_k = nullptr, *p_v = nullptr, *p_att = nullptr, *p_act = nullptr,
        *p_mem_bf = nullptr, *p_ck = nullptr, *p_cv = nullptr, *p_vt = nullptr;
-  int vt_ld = 0; bool use_tc_attn = true; int attn_preload = 1, attn_mma = 1;
+  int vt_ld = 0; bool use_tc_attn = true; int attn_preload = 1, attn_mma = 1, attn_mma_small = 0;
   int *p_vt_off_e = nullptr, *p_vt_off_d = nullptr;          // 8-aligned V^T column offsets per request (encoder / decoder tokens)
   float* p_logits = nullptr; int logits_chunk = 128;
   int *p_ids = nullptr, *p_seg_of = nullptr, *p_seg_off_e = nullptr, *p_seg_off_d = nullptr, *p_tok_slot = nullptr,
@@ -304,6 +304,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_ATTN_PRELOAD")) e->attn_preload = atoi(s) != 0;
   if (const char* s = getenv("T5G_FUSE_XATTN")) e->use_xf = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA")) e->attn_mma = atoi(s) != 0;
+  if (const char* s = getenv("T5G_ATTN_MMA_SMALL")) e->attn_mma_small = atoi(s) != 0;
   DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
   DM(e->p_ids, T); DM(e->p_seg_of, T); DM(e->p_seg_off_e, B + 1); DM(e->p_seg_off_d, B + 1); DM(e->p_tok_slot, T); DM(e->p_tok_idx, T);
   DM(e->p_last_rows, B); DM(e->p_pos, T);
@@ -735,7 +736,8 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
       a.out = e->d_attn; a.preload = e->attn_preload; a.trace = next_trace();
-      CU(launch_attn_decode(a, st, pdl)); nl++; }
+      if (e->attn_mma_small && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl)); else CU(launch_attn_decode(a, st, pdl));
+      nl++; }
     { GemvArgs a = z; a.W = L.wo; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
       a.pf[0] = PF(L.wq_c, (size_t)QD * d);                 // issued while this kernel waits on the attention kernel
       CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
@@ -752,7 +754,8 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
         a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
         a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
         a.out = e->d_attn; a.preload = e->attn_preload; a.trace = next_trace();
-        CU(launch_attn_decode(a, st, pdl)); nl++; }
+        if (e->attn_mma_small && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl)); else CU(launch_attn_decode(a, st, pdl));
+      nl++; }
       { GemvArgs a = z; a.W = L.wo_c; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
         a.pf[0] = PF(L.wgu, GU, 0, std::min(GU, e->l2pf_gu_elems));
         CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }

@@ -219,3 +219,63 @@ def test_from_pretrained_hf_dir(tmp_path):
     assert rel_err(eng.prefill_logits(0, npre), c["tf_logits"][:npre]) <= TOL_REF
     assert eng.config.audio_vocab_size == 200          # reference-facing config passes through
     eng.close()
+
+
+@pytest.mark.parametrize("max_slots,env", [(1, {}), (8, {}), (1, {"T5G_FUSE_XATTN": "1"}), (1, {"T5G_ATTN_MMA_SMALL": "1"})],
+                         ids=["single", "batched-mma", "single-fused-xattn", "single-mma"])
+def test_head_dim_256_decode_matches_oracle(max_slots, env, monkeypatch):
+    """The production head geometry (head_dim 256, 2 query heads per KV head) on a narrow 2+2-layer model with a
+    sliding window of 48: exercises the D=256 instantiations of both decode attention kernels (CUDA-core for
+    max_slots <= 4, cp.async + mma.sync tile kernel for batched rows) with contexts that cross the 32-token tile
+    and the window, teacher-forced along the oracle's greedy sequences; logits within the bf16 tolerance.  The opt-in
+    kernels (cross-attention fused into o_proj; the tile kernel on the single-row path) run the same check."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)                     # read by t5g_create
+    from oracle.t5gemma_voice_oracle import Oracle, OracleConfig
+    from t5gemma_tts_b200 import EngineConfig, T5GemmaVoiceEngine
+    from t5gemma_tts_b200.random_init import iter_random_state_dict
+    cfg = EngineConfig(hidden=512, inter=1024, n_enc_layers=2, n_dec_layers=2, n_heads=2, n_kv_heads=1, head_dim=256,
+                       query_pre_attn_scalar=256.0, sliding_window=48, text_vocab=300, audio_vocab=400,
+                       max_slots=max_slots, max_text_len=96, max_dec_len=512, max_prefill_tokens=1024)
+    sd = {k: v.float().cpu() for k, v in iter_random_state_dict(cfg, seed=3, device="cuda")}
+    ocfg = OracleConfig(hidden=cfg.hidden, inter=cfg.inter, n_enc_layers=cfg.n_enc_layers, n_dec_layers=cfg.n_dec_layers,
+                        n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, head_dim=cfg.head_dim,
+                        sliding_window=cfg.sliding_window, query_pre_attn_scalar=cfg.query_pre_attn_scalar,
+                        attn_softcap=cfg.attn_softcap, text_vocab=cfg.text_vocab, audio_vocab=cfg.audio_vocab,
+                        n_special=cfg.n_special)
+    orc = Oracle(ocfg, sd)
+    eng = T5GemmaVoiceEngine(cfg)
+    eng.load_state_dict(iter_random_state_dict(cfg, seed=3, device="cuda"))
+    rng = np.random.default_rng(11)
+    shapes = [(40, 0), (70, 40), (33, 75)] if max_slots > 1 else [(70, 40)]     # (text tokens, prompt tokens)
+    slots = [5, 0, 2] if max_slots > 1 else [0]
+    N_NEW = 40
+    refs, reqs = [], []
+    for S, P in shapes:
+        x = torch.from_numpy(rng.integers(2, cfg.text_vocab, S))[None]
+        y = torch.from_numpy(rng.integers(0, cfg.audio_vocab, P))[None, :, None]
+        if P:
+            y = torch.cat([y, torch.tensor([[[cfg.y_sep_token]]])], dim=1)
+        tgt = torch.tensor([y.shape[1] + 100])
+        with torch.no_grad():
+            _, gen, logits = orc.inference_tts(x, torch.tensor([S]), y, tgt, top_k=1, prompt_frames=y.shape[1],
+                                               max_new_tokens=N_NEW, return_logits=True)
+        refs.append((gen[0, 0].numpy(), logits.numpy()))
+        reqs.append(GenerationRequest(text_ids=x[0].numpy(), prompt_ids=y[0, :, 0].numpy(), target_total=int(tgt[0]),
+                                      prompt_frames=y.shape[1], top_k=1, forced_tokens=gen[0, 0].numpy()))
+    eng.prefill(reqs, slots)
+    eos = cfg.stop_token
+    worst = 0.0
+    for step in range(N_NEW):
+        eng.decode(1)
+        eng.poll()
+        for (gen, logits), s in zip(refs, slots):
+            if step < len(gen):
+                got = eng.read_logits(s)
+                ref = logits[step].copy()
+                got[eos] = ref[eos] = 0.0
+                worst = max(worst, rel_err(got, ref))
+    assert worst <= TOL_REF, worst
+    for (gen, _), s in zip(refs, slots):
+        assert np.array_equal(eng.read_tokens(s)[:len(gen)], gen)
+    eng.close()

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) gemm_stream_kernel(const bf16* 
   if (warp == 0) GS_PROBE(0);
 
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&S.full[i], ST_PROD / 4); mbar_init(&S.empty[i], 1); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&S.full[i], ST_PROD / ((NSTAGE % 4 == 0) ? 4 : 2)); mbar_init(&S.empty[i], 1); }
     mbar_init(&S.acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -275,50 +275,52 @@ __global__ void __launch_bounds__(ST_THREADS, 1) gemm_stream_kernel(const bf16* 
   if (warp != 4) {
     // ===== producers.  HBM locality decides this kernel: fetching one 128-byte K-slab of 128 different weight rows per
     //       stage touches 128 DRAM pages for 128 bytes each (measured 3.2 TB/s on gate|up).  Stages are therefore filled
-    //       in GROUPS of 4 consecutive k-blocks: a warp copies 512 contiguous bytes of one weight row (4 swizzle atoms,
-    //       one per ring stage of the group), 8 rows per warp-instruction column.  Lanes 8j..8j+7 of every warp feed
-    //       stage j of the group, so each stage's "full" barrier counts 64 threads.  Per-thread constants keep a
+    //       in GROUPS of 4 (2 for the 128-token tile) consecutive k-blocks: a warp copies 512 contiguous bytes of one
+    //       weight row (one swizzle atom per ring stage of the group).  Lanes 8j..8j+7 feed stage j of the group, so each
+    //       stage's "full" barrier counts ST_PROD / GRP threads.  Per-thread constants keep a
     //       16-byte copy at ~3 instructions. =====
     const int ptid = warp < 4 ? tid : tid - 32;
-    const int j = (ptid & 31) >> 3, col = ptid & 7, row0 = ptid >> 5;          // stage of the group, 16-byte column, first row
-    const uint32_t swz = (uint32_t)((col ^ (row0 & 7)) << 4);                   // (row & 7) == (row0 & 7) for rows row0 + 8u
+    constexpr int GRP = (NSTAGE % 4 == 0) ? 4 : 2;                               // k-blocks (ring stages) filled together
+    constexpr int CPG = 8 * GRP, RSTEP = ST_PROD / CPG;                          // 16-byte chunks per row per group; rows per pass
+    static_assert(NSTAGE % GRP == 0 && RSTEP % 8 == 0, "ring/group geometry");
+    const int j = (ptid % CPG) >> 3, col = ptid & 7, row0 = ptid / CPG;          // stage of the group, 16-byte column, first row
+    const uint32_t swz = (uint32_t)((col ^ (row0 & 7)) << 4);                   // (row & 7) == (row0 & 7) for rows row0 + RSTEP*u
     const uint32_t wdst0 = smem_u32(S.w[0]) + row0 * 128 + swz, xdst0 = smem_u32(S.x[0]) + row0 * 128 + swz;
     constexpr uint32_t W_STAGE = TC_BM * TC_BK * 2, X_STAGE = TOKT * TC_BK * 2;
     const bf16* wbase = W + (size_t)kb0 * TC_BK + col * 8;
     const bf16* xbase = X + (size_t)kb0 * TC_BK + col * 8;
     auto load_w = [&](int i, int s) {                                            // k-block i (relative to kb0) -> ring stage s
 #pragma unroll
-      for (int u = 0; u < TC_BM / 8; ++u) {
-        const int n = f0 + row0 + 8 * u;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(wdst0 + s * W_STAGE + u * 1024),
+      for (int u = 0; u < TC_BM / RSTEP; ++u) {
+        const int n = f0 + row0 + RSTEP * u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(wdst0 + s * W_STAGE + u * (RSTEP * 128)),
                      "l"(wbase + (size_t)min(n, p.N - 1) * p.K + (size_t)i * TC_BK), "r"(n < p.N ? 16 : 0) : "memory");
       }
     };
     auto load_x = [&](int i, int s) {
 #pragma unroll
-      for (int u = 0; u < (TOKT + 7) / 8; ++u) {
-        const int r = row0 + 8 * u, m = t0 + r;
+      for (int u = 0; u < (TOKT + RSTEP - 1) / RSTEP; ++u) {
+        const int r = row0 + RSTEP * u, m = t0 + r;
         if (r < TOKT)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xdst0 + s * X_STAGE + u * 1024),
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xdst0 + s * X_STAGE + u * (RSTEP * 128)),
                        "l"(xbase + (size_t)min(m, p.M - 1) * p.K + (size_t)i * TC_BK), "r"(m < p.M ? 16 : 0) : "memory");
       }
     };
-    static_assert(NSTAGE % 4 == 0, "ring stages are filled in groups of 4");
-    constexpr int NGRP = NSTAGE / 4;                                             // groups in the ring
-    const int ngroups = (nkb + 3) / 4;
+    constexpr int NGRP = NSTAGE / GRP;                                           // groups in the ring
+    const int ngroups = (nkb + GRP - 1) / GRP;
     // weights are immutable: the first ring-full is requested before the PDL dependency resolves
-    for (int g = 0; g < min(ngroups, NGRP); ++g) { const int i = g * 4 + j; if (i < nkb) load_w(i, i); }
+    for (int g = 0; g < min(ngroups, NGRP); ++g) { const int i = g * GRP + j; if (i < nkb) load_w(i, i); }
     pdl_launch_dependents();
     pdl_wait();
     trace_begin(p.trace);
     if (warp == 0) GS_PROBE(1);
-    for (int g = 0; g < min(ngroups, NGRP); ++g) { const int i = g * 4 + j; if (i < nkb) { load_x(i, i); cp_async_arrive(&S.full[i]); } }
+    for (int g = 0; g < min(ngroups, NGRP); ++g) { const int i = g * GRP + j; if (i < nkb) { load_x(i, i); cp_async_arrive(&S.full[i]); } }
     for (int g = NGRP; g < ngroups; ++g) {
       // tcgen05.commit releases stages in order: once the LAST stage of the group is free all four are, and the
       // whole warp issues its 512-byte row segments together (no divergence on four different barriers)
-      const int ilast = min(g * 4 + 3, nkb - 1);
+      const int ilast = min(g * GRP + GRP - 1, nkb - 1);
       mbar_wait(&S.empty[ilast % NSTAGE], ((ilast / NSTAGE) - 1) & 1);
-      const int i = g * 4 + j, s = i % NSTAGE;
+      const int i = g * GRP + j, s = i % NSTAGE;
       if (i < nkb) {
         load_w(i, s);
         load_x(i, s);
@@ -496,11 +498,12 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
   dim3 grid((a.N + TC_BM - 1) / TC_BM, (a.M + tokt - 1) / tokt, split);
   static int use_stream = -1;
   if (use_stream < 0) { const char* e = getenv("T5G_GEMM_STREAM"); use_stream = e ? atoi(e) : 1; }
-  if (use_stream && tokt <= 64) {
+  if (use_stream && tokt <= 128) {
     switch (tokt) {
       case 16: return launch_stream<16, 8>(a, p, grid, st, pdl);
       case 32: return launch_stream<32, 8>(a, p, grid, st, pdl);
-      default: return launch_stream<64, 8>(a, p, grid, st, pdl);
+      case 64: return launch_stream<64, 8>(a, p, grid, st, pdl);
+      default: return launch_stream<128, 6>(a, p, grid, st, pdl);
     }
   }
   switch (tokt) {

@@ -318,7 +318,12 @@ cudaError_t launch_gemv(const GemvArgs& a, int P, int E, int num_sms, cudaStream
   static int mult = -1;
   // CTAs per SM; 1 was measured (room for the next kernel to become resident early): gate|up 15.6 -> 22.4 us, too few bytes in flight
   if (mult < 0) { const char* e = getenv("T5G_GEMV_GRID_MULT"); mult = e ? atoi(e) : 2; }
-  const int grid = (NB == 1 ? mult : 1) * num_sms;
+  // experiment (T5G_GEMV_SMALL_1CTA=1): projections whose units fit one per warp at ONE CTA per SM would leave half of every
+  // SM's registers free, so the next kernel's CTAs become resident and pre-load their weights while this one runs
+  static int small_one = -1;
+  if (small_one < 0) { const char* e = getenv("T5G_GEMV_SMALL_1CTA"); small_one = e ? atoi(e) : 0; }   // measured: 1.571 -> 1.604 ms/step (cross-attention +0.8 us), off
+  const bool one_per_sm = small_one && NB == 1 && (long long)n_out * parts <= (long long)num_sms * GV_WARPS;
+  const int grid = (NB == 1 ? (one_per_sm ? 1 : mult) : 1) * num_sms;
   const int outs_per_cta = (n_out + grid - 1) / grid;
   const size_t part_floats = (parts == 1) ? 0 : (size_t)outs_per_cta * parts * NB;
   if (part_floats > MAX_PARTS_PER_CTA * 4) return cudaErrorInvalidValue;

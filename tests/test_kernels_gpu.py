@@ -43,7 +43,7 @@ def test_gemm_simt_vs_torch(M, N, K):
     assert err < 1e-5, err
 
 
-@pytest.mark.parametrize("M,N,K", [(16, 128, 64), (5, 100, 128), (64, 2304, 2304), (64, 18432, 2304), (152, 4096, 2304),
+@pytest.mark.parametrize("M,N,K", [(16, 128, 64), (5, 100, 128), (64, 2304, 2304), (64, 18432, 2304), (100, 1000, 576), (128, 2304, 9216), (152, 4096, 2304),
                                    (1000, 2304, 9216), (33, 65664, 256)])
 def test_gemm_tcgen05_vs_torch(M, N, K):
     """tcgen05/TMEM/TMA GEMM (incl. TMA out-of-bounds tiles and the split-K reduction) vs torch."""

@@ -7,7 +7,7 @@ from bench_batched import make_requests
 from t5gemma_tts_b200 import EngineConfig, T5GemmaVoiceEngine
 from t5gemma_tts_b200.random_init import iter_random_state_dict
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-cfg = EngineConfig(max_slots=B, max_text_len=128, max_dec_len=1536, max_prefill_tokens=8192)
+cfg = EngineConfig(max_slots=B, max_text_len=128, max_dec_len=1536, max_prefill_tokens=max(8192, 160 * B))
 eng = T5GemmaVoiceEngine(cfg)
 eng.load_state_dict(iter_random_state_dict(cfg, seed=0, device="cuda"))
 reqs = make_requests(B, cfg)

@@ -26,7 +26,7 @@ namespace {
 
 constexpr int TC_BM = 128;          // output features per tile (UMMA M)
 constexpr int TC_BK = 64;           // K elements per stage (one 128-byte swizzle atom of bf16)
-constexpr int TC_THREADS = 192;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int TC_THREADS = 320;     // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue (two per TMEM lane quarter)
 
 using namespace tc;
 
@@ -165,35 +165,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       umma_commit(&S.acc_full);                       // accumulator complete
     }
   } else {
-    // ===== epilogue warps: TMEM -> registers -> global (or -> shared memory for the cluster split-K reduce) =====
+    // ===== epilogue warps: TMEM -> registers -> global (or -> shared memory for the cluster split-K reduce).
+    //       Warps 2-5 take the first half of the token columns, warps 6-9 the second half; the epilogue kind is
+    //       resolved once (a per-element switch + libm tanhf made the epilogue as long as the main loop). =====
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
     const int fl = q * 32 + lane;                     // feature inside the tile
     const int f = f0 + fl;
+    constexpr int NCH = TOKT / 16;
+    const int hsel = (warp - 2) >> 2;
+    const int ch0 = (NCH >= 2) ? hsel * (NCH / 2) : 0;
+    const int ch1 = (NCH >= 2) ? (hsel + 1) * (NCH / 2) : (hsel == 0 ? NCH : 0);
     pdl_wait();                                       // the output buffer may still be read by the previous kernel
     mbar_wait(&S.acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* red = reinterpret_cast<float*>(&S.w[0][0]);   // ring storage is free once acc_full has fired
+    const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
+    const bool even = (lane & 1) == 0;
 #pragma unroll 1
-    for (int c = 0; c < TOKT; c += 16) {
+    for (int ch = ch0; ch < ch1; ++ch) {
+      const int c = ch * 16;
       if (t0 + c >= p.M) break;                       // warp-uniform
       float v[16];
       tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
       if (p.atomic) {
+        float* o = reinterpret_cast<float*>(p.out) + (size_t)(t0 + c) * p.ldo + f;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (t0 + c + j < p.M && f < p.N) atomicAdd(reinterpret_cast<float*>(p.out) + (size_t)(t0 + c + j) * p.ldo + f, v[j]);
-        continue;
-      }
-      if (p.split_k > 1) {
+          if (t0 + c + j < p.M && f < p.N) atomicAdd(o + (size_t)j * p.ldo, v[j]);
+      } else if (p.split_k > 1) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) red[(c + j) * TC_BM + fl] = v[j];
-        continue;
-      }
-      const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float other = (p.epilogue == GE_GEGLU_BF16) ? __shfl_xor_sync(0xffffffffu, v[j], 1) : 0.f;
-        epilogue_store(p, t0 + c + j, f, v[j], other, bias, (lane & 1) == 0);
+      } else {
+        switch (p.epilogue) {
+          case GE_F32: store_chunk<GE_F32>(p, v, t0 + c, f, bias, even); break;
+          case GE_BF16: store_chunk<GE_BF16>(p, v, t0 + c, f, bias, even); break;
+          case GE_BIAS_F32: store_chunk<GE_BIAS_F32>(p, v, t0 + c, f, bias, even); break;
+          case GE_BIAS_GELU_BF16: store_chunk<GE_BIAS_GELU_BF16>(p, v, t0 + c, f, bias, even); break;
+          default: store_chunk<GE_GEGLU_BF16>(p, v, t0 + c, f, bias, even); break;
+        }
       }
     }
   }
@@ -201,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     cluster.sync();                                   // all partial tiles are parked in shared memory
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
       const int rank = (int)cluster.block_rank(), nr = p.split_k;
       const int fl = (warp - 2) * 32 + lane, f = f0 + fl;
       const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;

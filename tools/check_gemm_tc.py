@@ -12,7 +12,7 @@ cfg = EngineConfig(hidden=64, inter=128, n_enc_layers=1, n_dec_layers=1, n_heads
                    text_vocab=32, audio_vocab=64, max_slots=1, max_text_len=16, max_dec_len=64, max_prefill_tokens=64)
 eng = T5GemmaVoiceEngine(cfg)
 shapes = [(16, 128, 64), (5, 100, 128), (64, 2304, 2304), (64, 18432, 2304), (64, 2304, 9216), (152, 4096, 2304),
-          (1024, 2304, 2048), (8192, 2304, 2304), (300, 65664, 2304), (33, 4096, 2304)]
+          (1024, 2304, 2048), (8192, 2304, 2304), (8192, 18432, 2304), (8192, 2304, 9216), (300, 65664, 2304), (33, 4096, 2304)]
 if len(sys.argv) > 1:
     shapes = shapes[: int(sys.argv[1])]
 for (M, N, K) in shapes:

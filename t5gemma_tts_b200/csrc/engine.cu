@@ -96,6 +96,7 @@ struct T5GEngine {
   int ns_self = 8, ns_cross = 2;
   int h_end = 0;                                               // which h buffer holds the residual at step end
   cudaGraphExec_t step_graph = nullptr; cudaStream_t graph_built_for = nullptr; int nodes_per_step = 0;
+  cudaGraphExec_t multi_graph = nullptr, multi_graph_fx = nullptr; int nodes_multi = 0, nodes_multi_fx = 0, graph_steps = 4;
   cudaGraphExec_t step_graph_fx = nullptr; int nodes_per_step_fx = 0;   // variant with cross-attention fused into its o_proj
   int last_nodes_per_step = 0;
   int xf_max_keys = 0; bool use_xf = false;                              // capacity (encoder keys over live rows) of that kernel; opt-in (T5G_FUSE_XATTN=1):
@@ -231,6 +232,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   e->V = cfg->n_audio_tokens; e->Vpad = cdiv(e->V, 64) * 64; e->PT = cfg->kv_page_tokens;
   if (const char* s = getenv("T5G_PDL")) e->use_pdl = atoi(s) != 0;
   if (const char* s = getenv("T5G_GRAPH")) e->use_graph = atoi(s) != 0;
+  if (const char* s = getenv("T5G_GRAPH_STEPS")) e->graph_steps = atoi(s);
   if (const char* s = getenv("T5G_GEMM")) e->gemm_impl = atoi(s);
   if (const char* s = getenv("T5G_TRACE")) e->use_trace = atoi(s) != 0;
   if (const char* s = getenv("T5G_L2PF")) e->use_l2pf = atoi(s) != 0;
@@ -343,6 +345,8 @@ extern "C" int t5g_destroy(T5GEngine* e) {
   cudaDeviceSynchronize();
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
   if (e->step_graph_fx) cudaGraphExecDestroy(e->step_graph_fx);
+  if (e->multi_graph) cudaGraphExecDestroy(e->multi_graph);
+  if (e->multi_graph_fx) cudaGraphExecDestroy(e->multi_graph_fx);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_mirror) cudaFreeHost(e->h_mirror);
   if (e->h_tokens) cudaFreeHost(e->h_tokens);
@@ -721,7 +725,7 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
     s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = B; s.host_mirror = e->d_mirror;
     s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
     s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32;
-    s.trace = next_trace();
+    s.trace = next_trace(); s.probe = e->use_trace ? e->d_trace + 1000 : nullptr;
     CU(launch_sampler(s, st, pdl)); nl++; }
   // ---- 26 decoder layers at q_len = 1 ----
   int t = 0;   // hbuf[t] holds the current residual
@@ -863,26 +867,46 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
     return (e->c.max_slots > 4) ? enqueue_step_batched(e, s_, nl) : enqueue_step(e, s_, nl, fuse);
   };
   if (e->use_graph) {
-    cudaGraphExec_t& graph = fuse ? e->step_graph_fx : e->step_graph;
-    int& nodes = fuse ? e->nodes_per_step_fx : e->nodes_per_step;
-    if (!graph) {
+    // one graph = one step, plus a graph of `graph_steps` consecutive steps: inside it the head of step t+1 is a
+    // programmatic dependent of the last kernel of step t, which removes the ~20 us gap between graph launches
+    auto get_graph = [&](cudaGraphExec_t& graph, int& nodes, int steps) -> int {
+      if (graph) return T5G_OK;
       cudaStream_t cs;
       CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      int nl = 0;
+      int nl_total = 0;
       cudaGraph_t g = nullptr;
       CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
-      int rc = enqueue(cs, &nl);
+      int rc = T5G_OK;
+      for (int i = 0; i < steps && rc == T5G_OK; ++i) { int nl = 0; rc = enqueue(cs, &nl); nl_total += nl; }
       cudaError_t er = cudaStreamEndCapture(cs, &g);
       if (rc) { if (g) cudaGraphDestroy(g); cudaStreamDestroy(cs); return rc; }
       CU(er);
       CU(cudaGraphInstantiate(&graph, g, 0));
       cudaGraphDestroy(g);
       cudaStreamDestroy(cs);
-      nodes = nl;
+      nodes = nl_total;
+      return T5G_OK;
+    };
+    const int MS = (e->use_trace || e->graph_steps < 2) ? 1 : e->graph_steps;
+    cudaGraphExec_t& g1 = fuse ? e->step_graph_fx : e->step_graph;
+    int& n1 = fuse ? e->nodes_per_step_fx : e->nodes_per_step;
+    cudaGraphExec_t& gm = fuse ? e->multi_graph_fx : e->multi_graph;
+    int& nm = fuse ? e->nodes_multi_fx : e->nodes_multi;
+    int done = 0;
+    if (MS > 1 && max_steps >= MS) {
+      int rc = get_graph(gm, nm, MS);
+      if (rc) return rc;
+      for (; max_steps - done >= MS; done += MS) CU(cudaGraphLaunch(gm, st));
+      e->launches += (int64_t)nm * (done / MS);
+      e->last_nodes_per_step = nm / MS;
     }
-    for (int i = 0; i < max_steps; ++i) CU(cudaGraphLaunch(graph, st));
-    e->launches += (int64_t)nodes * max_steps;
-    e->last_nodes_per_step = nodes;
+    if (done < max_steps) {
+      int rc = get_graph(g1, n1, 1);
+      if (rc) return rc;
+      e->launches += (int64_t)n1 * (max_steps - done);
+      for (; done < max_steps; ++done) CU(cudaGraphLaunch(g1, st));
+      e->last_nodes_per_step = n1;
+    }
   } else {
     for (int i = 0; i < max_steps; ++i) {
       int nl = 0;

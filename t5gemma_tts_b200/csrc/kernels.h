@@ -150,5 +150,6 @@ struct SamplerArgs {
   int* picks_out;                     // optional [slot][tokens_stride]: engine's own sampled id per step
   const int* forced_pool;             // optional [slot][tokens_stride]: teacher-forced ids
   int rows;
+  unsigned long long* probe;      // optional [12] in-kernel checkpoints of row 0 (debug)
 };
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st, bool pdl);

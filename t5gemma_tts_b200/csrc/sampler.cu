@@ -217,14 +217,26 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
   pdl_wait();
   trace_begin(a.trace);
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  SlotDev& sl = a.slots[row];
+#define SP_PROBE(k) do { if (a.probe && row == 0 && tid == 0) a.probe[k] = globaltimer_ns(); } while (0)
+  SP_PROBE(0);
+  // the slot record is staged in shared memory (one coalesced load) and written back once at the end: the stop-rule /
+  // state-update code of thread 0 otherwise pays one L2 round trip per field (loads cannot move above its stores)
+  __shared__ SlotDev sl_s;
+  constexpr int SLOT_WORDS = sizeof(SlotDev) / 4;
+  static_assert(sizeof(SlotDev) % 4 == 0 && SLOT_WORDS <= SAMP_THREADS, "SlotDev is copied word-wise");
+  if (tid < SLOT_WORDS) reinterpret_cast<int*>(&sl_s)[tid] = reinterpret_cast<const int*>(&a.slots[row])[tid];
+  __syncthreads();
+  SlotDev& sl = sl_s;
   if (!sl.active) return;
+  SP_PROBE(1);
   float* lg = a.logits + (size_t)row * a.ld;
   const int V = a.V, eos = a.eos;
 
   // (1) in-place eos edits (models/t5gemma.py:986-997)
   const int n_gen = sl.n_generated, cur_len = sl.cur_len;
   const int eff_len = max(0, cur_len - sl.prompt_offset);
+  float u_draw = 0.5f;                                   // this step's uniform: requested now, consumed after the filters
+  if (tid == 0 && sl.uniforms) u_draw = sl.uniforms[min(n_gen, max(sl.n_uniforms - 1, 0))];
   if (tid == 0) {
     if (eff_len == 0) lg[eos] = -1e9f;
     if (n_gen <= a.encodec_sr / 5) lg[eos] = -10000.0f;
@@ -242,29 +254,74 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
   }
   __syncthreads();
 
+  SP_PROBE(2);
   // (2) one pipelined global pass: argmax of the adjusted logits (first index on ties), and -- for the
   //     top-k fast path -- the top 16 bits of every key into shared memory + per-thread max key
   const float T = sl.temperature;
   const bool scaled = (T != 1.0f);
   auto zof = [&](int i) -> float { float v = lg[i]; return scaled ? __fdiv_rn(v, T) : v; };
   const bool use_hi = V <= HI_CAP;
+  // Keys of this pass are taken from the RAW logits: dividing by T > 0 is monotone, so the order (hence every maximum
+  // and the lower bound derived from them) is that of z = v / T, and the pass saves an IEEE division per element (it is
+  // instruction-issue bound: 64 elements per thread).  Distinct raw values may round to EQUAL z, and ties at the k-th
+  // value must survive: the candidate filter below therefore lowers its bound by 2 keys (adjacent floats differ by 1 in
+  // key space; values 3 ulps apart cannot collide); candidates are re-read and compared exactly in z.
+  const bool vspace = !scaled || T > 0.f;
   float bv = -INFINITY; int bi = 0x7fffffff;
   unsigned mk = 0u;
-  for (int i0 = tid; i0 < V; i0 += SAMP_THREADS * 8) {
-    float v[8];
+  if (vspace && (a.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(lg) & 15) == 0) {
+    // 16-byte loads, 8 in flight per thread; elements of a thread are visited in increasing index order, so a strict
+    // `>` keeps the first index of the maximum
+    const float4* lg4 = reinterpret_cast<const float4*>(lg);
+    const int n4 = (V + 3) >> 2;
+    constexpr int PB = 8;
+    for (int g0 = tid; g0 < n4; g0 += SAMP_THREADS * PB) {
+      float4 v4[PB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int i = i0 + j * SAMP_THREADS; v[j] = (i < V) ? lg[i] : -INFINITY; }
+      for (int j = 0; j < PB; ++j) { const int g = g0 + j * SAMP_THREADS; v4[j] = (g < n4) ? lg4[g] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = i0 + j * SAMP_THREADS;
-      if (i < V) {
-        if (v[j] > bv || (v[j] == bv && i < bi)) { bv = v[j]; bi = i; }
-        const unsigned key = key_of(scaled ? __fdiv_rn(v[j], T) : v[j]);
-        mk = max(mk, key);
-        if (use_hi) S.hi16[i] = (unsigned short)(key >> 16);
+      for (int j = 0; j < PB; ++j) {
+        const int g = g0 + j * SAMP_THREADS;
+        if (g < n4) {
+          const float e4[4] = {v4[j].x, v4[j].y, v4[j].z, v4[j].w};
+          unsigned kk[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = g * 4 + c;
+            const bool ok = i < V;                         // the padded tail of the row is not part of the vocabulary
+            const float v = ok ? e4[c] : -INFINITY;
+            if (v > bv) { bv = v; bi = i; }
+            kk[c] = ok ? key_of(v) : 0u;
+            mk = max(mk, kk[c]);
+          }
+          if (use_hi) {
+            uint2 pk;
+            pk.x = (kk[0] >> 16) | (kk[1] & 0xffff0000u);
+            pk.y = (kk[2] >> 16) | (kk[3] & 0xffff0000u);
+            *reinterpret_cast<uint2*>(&S.hi16[g * 4]) = pk;
+          }
+        }
+      }
+    }
+  } else {
+    constexpr int PB = 16;
+    for (int i0 = tid; i0 < V; i0 += SAMP_THREADS * PB) {
+      float v[PB];
+#pragma unroll
+      for (int j = 0; j < PB; ++j) { const int i = i0 + j * SAMP_THREADS; v[j] = (i < V) ? lg[i] : -INFINITY; }
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int i = i0 + j * SAMP_THREADS;
+        if (i < V) {
+          if (v[j] > bv || (v[j] == bv && i < bi)) { bv = v[j]; bi = i; }
+          const unsigned key = key_of(scaled ? __fdiv_rn(v[j], T) : v[j]);
+          mk = max(mk, key);
+          if (use_hi) S.hi16[i] = (unsigned short)(key >> 16);
+        }
       }
     }
   }
+  SP_PROBE(3);
   S.tmax[tid] = mk;
   {
     unsigned wk = mk;
@@ -287,6 +344,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
   }
   __syncthreads();
   const float zmax = scaled ? __fdiv_rn(S.zmax, T) : S.zmax;
+  SP_PROBE(4);
 
   int top_k = sl.top_k;
   if (sl.topk_sched_off >= 0 && sl.n_topk_sched > 0)
@@ -362,32 +420,65 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
       if (tid == 0) S.lb = S.tmax[k - 1];
     }
     __syncthreads();
-    const unsigned short thr16 = (unsigned short)(S.lb >> 16);
-    for (int i = tid; i < V; i += SAMP_THREADS) {
-      if (S.hi16[i] >= thr16) {
-        const unsigned slot = atomicAdd(&S.n_cand, 1u);
-        if (slot < CAND_CAP) S.cand[slot] = ((unsigned long long)key_of(zof(i)) << 32) | (0xffffffffu - (unsigned)i);
-        else S.overflow = 1;
+    SP_PROBE(5);
+    unsigned thr16 = S.lb >> 16;
+    // raw-logit keys: values up to 2 keys below the bound can still round to the same z = v / T (3 ulps cannot), and ties
+    // at the k-th value must survive
+    if (vspace && scaled) thr16 = (S.lb - min(S.lb, 2u)) >> 16;
+    for (int g = tid; g * 8 < V; g += SAMP_THREADS) {        // 8 keys per 16-byte shared-memory load
+      const uint4 h = *reinterpret_cast<const uint4*>(&S.hi16[g * 8]);
+      const unsigned w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const unsigned k16 = (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xffffu);
+        const int i = g * 8 + c;
+        if (k16 >= thr16 && i < V) {
+          const unsigned slot = atomicAdd(&S.n_cand, 1u);
+          if (slot < CAND_CAP) S.cand[slot] = ((unsigned long long)key_of(zof(i)) << 32) | (0xffffffffu - (unsigned)i);
+          else S.overflow = 1;
+        }
       }
     }
     __syncthreads();
+    SP_PROBE(6);
     if (!S.overflow) {
       const int n = (int)S.n_cand;
+      if (a.probe && row == 0 && tid == 0) a.probe[11] = (unsigned long long)n;
       int np2 = 1; while (np2 < n) np2 <<= 1;
       for (int i = n + tid; i < np2; i += SAMP_THREADS) S.cand[i] = 0ull;
       __syncthreads();
-      for (int size = 2; size <= np2; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-          for (int i = tid; i < np2; i += SAMP_THREADS) {
-            const int j = i ^ stride;
-            if (j > i) {
-              const bool desc = ((i & size) == 0);
-              unsigned long long x = S.cand[i], y = S.cand[j];
-              if ((x < y) == desc) { S.cand[i] = y; S.cand[j] = x; }
+      if (np2 <= 1024) {
+        // a few dozen candidates: one compare-exchange per thread per bitonic stage, and the barrier spans only the
+        // warps that hold pairs (a 1024-thread __syncthreads per stage cost 0.25 us x 28 stages)
+        const int npairs = np2 >> 1;
+        const int nthr = max(32, (npairs + 31) & ~31);
+        if (tid < nthr) {
+          for (int size = 2; size <= np2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+              if (tid < npairs) {
+                const int i = ((tid & ~(stride - 1)) << 1) | (tid & (stride - 1)), j = i | stride;
+                const bool desc = ((i & size) == 0);
+                const unsigned long long x = S.cand[i], y = S.cand[j];
+                if ((x < y) == desc) { S.cand[i] = y; S.cand[j] = x; }
+              }
+              asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
             }
-          }
-          __syncthreads();
         }
+        __syncthreads();
+      } else {
+        for (int size = 2; size <= np2; size <<= 1)
+          for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < np2; i += SAMP_THREADS) {
+              const int j = i ^ stride;
+              if (j > i) {
+                const bool desc = ((i & size) == 0);
+                unsigned long long x = S.cand[i], y = S.cand[j];
+                if ((x < y) == desc) { S.cand[i] = y; S.cand[j] = x; }
+              }
+            }
+            __syncthreads();
+          }
+      }
       const unsigned thr_key = (unsigned)(S.cand[k - 1] >> 32);
       for (int i = tid; i < n; i += SAMP_THREADS) {
         const bool in = (unsigned)(S.cand[i] >> 32) >= thr_key;
@@ -445,6 +536,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
     if (S.overflow) large = true; else filtered = true;       // > CAND_CAP ties at the k-th value: full sort
   }
 
+  SP_PROBE(7);
   int token = 0;
   if (large) {
     if (!a.scratch_u64) { if (tid == 0) sl.error |= 2; token = S.amax; }
@@ -491,7 +583,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
         }
       }
       // (6) inverse-CDF draw over the kept prefix
-      const float u = sl.uniforms ? sl.uniforms[min(n_gen, max(sl.n_uniforms - 1, 0))] : 0.5f;
+      const float u = u_draw;
       float s2 = 0.f;
       for (int i = 0; i < n_keep; ++i) s2 = __fadd_rn(s2, S.e[i]);
       float c = 0.f; int pick = n_keep - 1;
@@ -517,7 +609,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
     if (tid == 0) {
       float s = 0.f;
       for (int c = 0; c < nchunk; ++c) s = __fadd_rn(s, S.csum[c]);
-      const float u = sl.uniforms ? sl.uniforms[min(n_gen, max(sl.n_uniforms - 1, 0))] : 0.5f;
+      const float u = u_draw;
       const float t = __fmul_rn(u, s);
       float cc = 0.f, base = 0.f; int cidx = -1;
       for (int c = 0; c < nchunk; ++c) { base = cc; cc = __fadd_rn(cc, S.csum[c]); if (t < cc) { cidx = c; break; } }
@@ -536,6 +628,7 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
     token = S.n_keep;
   }
 
+  SP_PROBE(8);
   // (7) stop rules + state update (models/t5gemma.py:1020-1048, 1075-1099)
   if (tid == 0) {
     const int amax = S.amax;
@@ -572,9 +665,11 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
     }
     S.total = sl.pos;
   }
+  SP_PROBE(9);
+  __syncthreads();
+  if (tid < SLOT_WORDS) reinterpret_cast<int*>(&a.slots[row])[tid] = reinterpret_cast<const int*>(&sl_s)[tid];
   if (a.rope_out) {
     // cos/sin of the new token's PM-RoPE angle, once per step instead of once per attention kernel
-    __syncthreads();
     const float pos = S.total;
     const int half = a.head_dim / 2;
     for (int i = tid; i < half; i += SAMP_THREADS) {
@@ -584,7 +679,9 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
       a.rope_out[(size_t)row * a.head_dim + half + i] = sn;
     }
   }
+  SP_PROBE(10);
   trace_end(a.trace);
+#undef SP_PROBE
 }
 
 }  // namespace

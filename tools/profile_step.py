@@ -52,3 +52,8 @@ if os.environ.get("T5G_TRACE") == "1":
         a = agg.setdefault(nm, [0, 0.0, 0.0]); a[0] += 1; a[1] += dur; a[2] += gap
     for nm, (c, d, g) in agg.items():
         print(f"{nm:8s} n={c:3d} body avg {d/c:7.2f} us   gap avg {g/c:6.2f} us   total {(d+g):8.1f} us")
+    sp = np.zeros(1024, dtype=np.uint64); se = np.zeros(1024, dtype=np.uint64); nn = C.c_int(0)
+    L.check(eng.lib, eng.lib.t5g_debug_trace(eng._h, sp.ctypes.data_as(C.POINTER(C.c_uint64)), se.ctypes.data_as(C.POINTER(C.c_uint64)), 1024, C.byref(nn)))
+    pr = sp[1000:1012].astype(np.int64)
+    lab = ["post-wait", "slot staged", "eos edits", "logits pass", "argmax", "lower bound", "candidates", "top-k done", "drawn", "state updated", "exit"]
+    print("sampler probes (us after post-wait):", ", ".join(f"{l} {(pr[i] - pr[0]) / 1000.0:.2f}" for i, l in enumerate(lab) if 0 < pr[i] < 2**62), f"| candidates {int(pr[11])}")

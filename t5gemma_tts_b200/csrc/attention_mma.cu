@@ -54,7 +54,13 @@ template <int D> struct AmGeo {
   static constexpr int NMT = D / 16;                       // 16-dim m-tiles of the output MMA
   static constexpr int MTW = (NMT + AM_WARPS - 1) / AM_WARPS;   // m-tiles per warp
   static constexpr size_t stage_elems = (size_t)2 * AM_TT * LD; // K tile + V tile
-  static constexpr size_t dyn_bytes = (AM_NST * stage_elems + (size_t)8 * LD + (size_t)8 * (AM_TT + 8)) * sizeof(bf16);
+  // q / probability operand tiles hold G real rows + one shared zero row (the MMA's n = 8 columns beyond G read it)
+  static constexpr size_t ring_bytes(int G) { return (AM_NST * stage_elems + (size_t)(G + 1) * LD + (size_t)(G + 1) * (AM_TT + 8)) * sizeof(bf16); }
+  // split-KV receive buffers live in dynamic shared memory and only exist when the key range is split (NS > 1): an
+  // unsplit CTA then needs 80 KB in total and fits next to a resident 145 KB GEMM CTA, so its pre-wait work (slot /
+  // block table / first K/V tiles) overlaps the producer GEMM instead of starting when that kernel exits
+  static constexpr size_t split_bytes(int G, int NS) { return NS > 1 ? ((size_t)NS * G * D + (size_t)NS * G * 2 + (size_t)NS * G + (size_t)G * D) * sizeof(float) : 0; }
+  static constexpr size_t dyn_bytes(int G, int NS) { return ring_bytes(G) + split_bytes(G, NS); }
 };
 
 // grid (Hkv, NS, B), cluster (1, NS, 1), 256 threads
@@ -67,19 +73,19 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char am_dyn[];
   bf16* ring = reinterpret_cast<bf16*>(am_dyn);                         // [NST][2][TT][LD]
-  bf16* qb = ring + AM_NST * Geo::stage_elems;                          // [8][LD]   rotated q (rows >= G are zero)
-  bf16* pb = qb + 8 * LD;                                               // [8][TT+8] probabilities of the tile
+  bf16* qb = ring + AM_NST * Geo::stage_elems;                          // [G+1][LD]   rotated q, row G is zero
+  bf16* pb = qb + (G + 1) * LD;                                         // [G+1][TT+8] probabilities of the tile, row G is zero
   __shared__ float cs[D / 2], sn[D / 2];
   __shared__ float knew[D], vnew[D];
   __shared__ int bt_s[AM_BT_CACHE];
   __shared__ float scp[2][G][AM_TT];                                    // partial q.k of the two k-halves
   __shared__ float corr_s[8];
   __shared__ unsigned rowoff[AM_NST][AM_TT];                            // row offsets (elements) inside the layer's K plane
-  __shared__ __align__(16) float o_s[G][D];
   __shared__ float ml_s[G][2];
-  __shared__ __align__(16) float recv_o[AM_MAX_NS][G][D];               // [src rank][g][dslice] (D/NS used per rank)
-  __shared__ float recv_ml[AM_MAX_NS][G][2];
-  __shared__ float f_wt[AM_MAX_NS][G];
+  float* recv_o = reinterpret_cast<float*>(am_dyn + Geo::ring_bytes(G)); // [NS][G][D]  (src rank, g, dslice; NS > 1 only)
+  float* recv_ml = recv_o + (size_t)a.n_splits * G * D;                 // [NS][G][2]
+  float* f_wt = recv_ml + (size_t)a.n_splits * G * 2;                   // [NS][G]
+  float* o_s = f_wt + (size_t)a.n_splits * G;                           // [G][D] unnormalised partial of this CTA
 
   pdl_launch_dependents();
   const int hk = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
@@ -106,8 +112,8 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
     bt_s[tid] = btv;
   }
   static_assert(AM_BT_CACHE == AM_NT && D / 2 <= AM_NT, "prologue mapping");
-  for (int i = tid; i < 8 * LD; i += AM_NT) qb[i] = __float2bfloat16(0.f);
-  for (int i = tid; i < 8 * (AM_TT + 8); i += AM_NT) pb[i] = __float2bfloat16(0.f);
+  for (int i = tid; i < (G + 1) * LD; i += AM_NT) qb[i] = __float2bfloat16(0.f);
+  for (int i = tid; i < (G + 1) * (AM_TT + 8); i += AM_NT) pb[i] = __float2bfloat16(0.f);
   const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
   int chunk = (L - lo + NS - 1) / NS;
   chunk = (chunk + 15) / 16 * 16;
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
 #pragma unroll
   for (int i = 0; i < KSH; ++i) {
     const int ks = kh * KSH + i;
-    if (ks < KS) ldsm_x2(qf[i], qb + (size_t)(lane & 7) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
+    if (ks < KS) ldsm_x2(qf[i], qb + (size_t)min(lane & 7, G) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
     else { qf[i][0] = 0u; qf[i][1] = 0u; }
   }
   AM_PROBE(4);
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
       const float c0 = (2 * t4 < G) ? corr_s[2 * t4] : 0.f, c1 = (2 * t4 + 1 < G) ? corr_s[2 * t4 + 1] : 0.f;
       uint32_t pf[AM_TT / 16][2];
 #pragma unroll
-      for (int kk = 0; kk < AM_TT / 16; ++kk) ldsm_x2(pf[kk], pb + (size_t)(lane & 7) * (AM_TT + 8) + kk * 16 + ((lane >> 3) & 1) * 8);
+      for (int kk = 0; kk < AM_TT / 16; ++kk) ldsm_x2(pf[kk], pb + (size_t)min(lane & 7, G) * (AM_TT + 8) + kk * 16 + ((lane >> 3) & 1) * 8);
 #pragma unroll
       for (int i = 0; i < MTW; ++i) {
         const int mt = warp + i * AM_WARPS;
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int head = 2 * t4 + (r & 1), dim = mt * 16 + g8 + (r >> 1) * 8;
-        if (head < G) o_s[head][dim] = acc[i][r];
+        if (head < G) o_s[head * D + dim] = acc[i][r];
       }
     }
   }
@@ -342,34 +348,34 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   for (int i = tid; i < G * D; i += AM_NT) {
     const int g = i / D, d = i - g * D;
     const int dst = d / dslice;
-    float* ro = cluster.map_shared_rank(&recv_o[0][0][0], dst);
-    ro[((size_t)split * G + g) * D + (d - dst * dslice)] = o_s[g][d];
+    float* ro = cluster.map_shared_rank(recv_o, dst);
+    ro[((size_t)split * G + g) * D + (d - dst * dslice)] = o_s[g * D + d];
   }
   if (tid < G * NS) {
     const int g = tid % G, dst = tid / G;
-    float* rm = cluster.map_shared_rank(&recv_ml[0][0][0], dst);
+    float* rm = cluster.map_shared_rank(recv_ml, dst);
     rm[(split * G + g) * 2] = ml_s[g][0]; rm[(split * G + g) * 2 + 1] = ml_s[g][1];
   }
   cluster.sync();                                          // all pushes have landed
   AM_PROBE(9);
   if (tid < G) {
     float M = -INFINITY;
-    for (int r = 0; r < NS; ++r) M = fmaxf(M, recv_ml[r][tid][0]);
+    for (int r = 0; r < NS; ++r) M = fmaxf(M, recv_ml[(r * G + tid) * 2]);
     float den = 0.f;
     for (int r = 0; r < NS; ++r) {
-      const float m = recv_ml[r][tid][0];
+      const float m = recv_ml[(r * G + tid) * 2];
       const float wt = (m == -INFINITY) ? 0.f : __expf(m - M);
-      den = fmaf(wt, recv_ml[r][tid][1], den);
-      f_wt[r][tid] = wt;
+      den = fmaf(wt, recv_ml[(r * G + tid) * 2 + 1], den);
+      f_wt[r * G + tid] = wt;
     }
     const float inv = den > 0.f ? 1.f / den : 0.f;
-    for (int r = 0; r < NS; ++r) f_wt[r][tid] *= inv;
+    for (int r = 0; r < NS; ++r) f_wt[r * G + tid] *= inv;
   }
   __syncthreads();
   for (int i = tid; i < G * dslice; i += AM_NT) {
     const int g = i / dslice, dd = i - g * dslice;
     float o = 0.f;
-    for (int r = 0; r < NS; ++r) o = fmaf(f_wt[r][g], recv_o[r][g][dd], o);
+    for (int r = 0; r < NS; ++r) o = fmaf(f_wt[r * G + g], recv_o[((size_t)r * G + g) * D + dd], o);
     const int d = split * dslice + dd;
     if (a.out) a.out[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = o;
     if (a.out_bf) a.out_bf[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = __float2bfloat16(o);
@@ -382,12 +388,14 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
 template <int G, int D>
 cudaError_t launch_am(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   auto kern = attn_decode_mma_kernel<G, D>;
-  const size_t smem = AmGeo<D>::dyn_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  const size_t smem = AmGeo<D>::dyn_bytes(G, a.n_splits);
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    // batched-step kernels all ask for the maximum shared-memory carve-out: CTAs of consecutive kernels can then share an SM
+    if (batched_carveout() >= 0 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, batched_carveout())) != cudaSuccess) return e;
+    attr_set = smem;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.Hkv, a.n_splits, a.B);

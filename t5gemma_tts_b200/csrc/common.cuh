@@ -163,6 +163,11 @@ struct SlotDev {
 // default -1 = driver's choice).  Measured: the maximum carve-out slows the weight-streaming GEMVs (gate|up 15.5 ->
 // 19.8 us) because in-flight global loads are tracked in L1; kernels of the step therefore keep their shared memory
 // under the 100 KB configuration.
+inline int batched_carveout() {
+  static int pct = -2;
+  if (pct == -2) { const char* e = getenv("T5G_BATCHED_CARVEOUT"); pct = e ? atoi(e) : 100; }
+  return pct;
+}
 template <typename KernelT>
 inline cudaError_t step_carveout(KernelT kern) {
   static int pct = -2;

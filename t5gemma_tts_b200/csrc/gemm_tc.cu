@@ -434,6 +434,8 @@ cudaError_t launch_stream(const GemmArgs& a, const TcParams& p, dim3 grid, cudaS
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // batched-step kernels all ask for the maximum shared-memory carve-out: CTAs of consecutive kernels can then share an SM
+    if (batched_carveout() >= 0 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, batched_carveout())) != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -459,6 +461,8 @@ cudaError_t launch_tc(const CUtensorMap& mw, const CUtensorMap& mx, const TcPara
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // batched-step kernels all ask for the maximum shared-memory carve-out: CTAs of consecutive kernels can then share an SM
+    if (batched_carveout() >= 0 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, batched_carveout())) != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -511,7 +515,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
     switch (tokt) {
       case 16: return launch_stream<16, 8>(a, p, grid, st, pdl);
       case 32: return launch_stream<32, 8>(a, p, grid, st, pdl);
-      case 64: return launch_stream<64, 8>(a, p, grid, st, pdl);
+      case 64: return launch_stream<64, 6>(a, p, grid, st, pdl);   // 145 KB: an 80 KB attention CTA of the next kernel fits beside it
       default: return launch_stream<128, 6>(a, p, grid, st, pdl);
     }
   }

@@ -12,10 +12,10 @@ eng = T5GemmaVoiceEngine(cfg)
 eng.load_state_dict(iter_random_state_dict(cfg, seed=0, device="cuda"))
 reqs = make_requests(B, cfg)
 eng.prefill(reqs, list(range(B)))
-eng.decode(3); eng.poll()
+eng.decode(8); eng.poll()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); eng.decode(3); e1.record(); eng.poll()
-print("ms/step", e0.elapsed_time(e1) / 3)
+e0.record(); eng.decode(24); e1.record(); eng.poll()
+print("ms/step", e0.elapsed_time(e1) / 24)
 if os.environ.get("T5G_TRACE") == "1":
     import ctypes as C
     import numpy as np

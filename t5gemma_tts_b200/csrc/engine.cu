@@ -99,6 +99,7 @@ struct T5GEngine {
   cudaGraphExec_t multi_graph = nullptr, multi_graph_fx = nullptr; int nodes_multi = 0, nodes_multi_fx = 0, graph_steps = 4;
   cudaGraphExec_t step_graph_fx = nullptr; int nodes_per_step_fx = 0;   // variant with cross-attention fused into its o_proj
   int last_nodes_per_step = 0;
+  unsigned long long* d_barrier = nullptr; bool use_pair = true;         // o_proj + cross q_proj in one kernel (gemv_pair.cu)
   int xf_max_keys = 0; bool use_xf = false;                              // capacity (encoder keys over live rows) of that kernel; opt-in (T5G_FUSE_XATTN=1):
                                                                          // measured 11.9 us vs 9.4 us for the two separate kernels (profiles/r1_gemv_design_experiments.md)
   int64_t launches = 0;
@@ -305,6 +306,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_ATTN_TC")) e->use_tc_attn = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_PRELOAD")) e->attn_preload = atoi(s) != 0;
   if (const char* s = getenv("T5G_FUSE_XATTN")) e->use_xf = atoi(s) != 0;
+  if (const char* s = getenv("T5G_GEMV_PAIR")) e->use_pair = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA")) e->attn_mma = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA_SMALL")) e->attn_mma_small = atoi(s) != 0;
   DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
@@ -334,6 +336,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   e->samp_scratch_rows = std::max(B, 16);
   { const size_t V8 = ((size_t)e->V + 7) & ~(size_t)7; DM(e->d_samp_u64, (size_t)e->samp_scratch_rows * 2 * V8); DM(e->d_samp_f32, (size_t)e->samp_scratch_rows * 2 * V8); }
   DM(e->d_attn, (size_t)B * QD); DM(e->d_trace, 2 * T5G_TRACE_STRIDE);
+  DM(e->d_barrier, 2); T5G_CUDA(cudaMemset(e->d_barrier, 0, 2 * sizeof(unsigned long long)));
   DM(e->d_xn, (size_t)B * d); DM(e->d_attn_bf, (size_t)B * QD); DM(e->d_act_bf, (size_t)B * I); DM(e->d_t1_bf, (size_t)B * d);
   T5G_CUDA(cudaDeviceSynchronize());
   return T5G_OK;
@@ -742,12 +745,21 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
       a.out = e->d_attn; a.preload = e->attn_preload; a.trace = next_trace();
       if (e->attn_mma_small && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl)); else CU(launch_attn_decode(a, st, pdl));
       nl++; }
-    { GemvArgs a = z; a.W = L.wo; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
-      a.pf[0] = PF(L.wq_c, (size_t)QD * d);                 // issued while this kernel waits on the attention kernel
-      CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
-    { GemvArgs a = z; a.W = L.wq_c; a.N = QD; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_sa; a.g_pre = L.g_pre_ca; a.h_out = hbuf[t ^ 1]; t ^= 1;
-      a.out = e->d_qc; a.out_stride = QD;
-      CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QD)); }
+    GemvPairArgs gp{};
+    gp.W1 = L.wo; gp.N1 = d; gp.K1 = QD; gp.x = e->d_attn; gp.y = e->d_y; gp.W2 = L.wq_c; gp.N2 = QD; gp.K2 = d;
+    gp.h_in = hbuf[t]; gp.g_post = L.g_post_sa; gp.g_pre = L.g_pre_ca; gp.h_out = hbuf[t ^ 1]; gp.eps = c.rms_eps;
+    gp.out = e->d_qc; gp.out_stride = QD; gp.B = B; gp.slots = e->d_slots; gp.barrier = e->d_barrier;
+    if (e->use_pair && B <= 4 && gemv_pair_supported(gp)) {
+      gp.trace = next_trace();
+      CU(launch_gemv_pair(gp, e->num_sms, st, pdl)); nl++; t ^= 1;
+    } else {
+      { GemvArgs a = z; a.W = L.wo; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
+        a.pf[0] = PF(L.wq_c, (size_t)QD * d);                 // issued while this kernel waits on the attention kernel
+        CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
+      { GemvArgs a = z; a.W = L.wq_c; a.N = QD; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_sa; a.g_pre = L.g_pre_ca; a.h_out = hbuf[t ^ 1]; t ^= 1;
+        a.out = e->d_qc; a.out_stride = QD;
+        CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QD)); }
+    }
     if (fuse_cross) {   // cross-attention + o_proj in one kernel (short texts)
       XAttnOprojArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.slots = e->d_slots; a.slot0 = 0; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.scale = c.attn_scale; a.softcap = c.attn_softcap;

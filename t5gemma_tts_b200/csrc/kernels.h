@@ -25,6 +25,21 @@ struct GemvArgs {
 };
 cudaError_t launch_gemv(const GemvArgs& a, int P, int E, int num_sms, cudaStream_t st, bool pdl);
 
+// ---------------- o_proj -> (grid barrier) -> cross q_proj in one kernel, bs<=4 decode (gemv_pair.cu) ----------------
+struct GemvPairArgs {
+  const bf16* W1; int N1, K1;        // phase A: y[B,N1] = W1 . x[B,K1]
+  const float* x; float* y;
+  const bf16* W2; int N2, K2;        // phase B: out[B,N2] = W2 . norm_pre(h_in + norm_post(y)),  K2 == N1
+  const float* h_in; const float* g_post; const float* g_pre; float* h_out;
+  float eps;
+  float* out; int out_stride;
+  int B; const SlotDev* slots;
+  unsigned long long* barrier;       // ticket counter of the grid-wide barrier (zeroed once at engine creation)
+  unsigned long long* trace;
+};
+bool gemv_pair_supported(const GemvPairArgs& a);
+cudaError_t launch_gemv_pair(const GemvPairArgs& a, int num_sms, cudaStream_t st, bool pdl);
+
 // ---------------- decode attention over the paged KV pool (attention.cu) ----------------
 struct KVPool {
   bf16* base;            // [layer][2][page][Hkv][page_tokens][D]

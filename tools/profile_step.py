@@ -41,7 +41,10 @@ if os.environ.get("T5G_TRACE") == "1":
     t0 = b[0]
     per_layer = ["qkv", "sattn", "o", "qc", "cattn", "oc", "gu", "down"]
     if (n - 3) % 7 == 0 and (n - 3) % 8 != 0:
-        per_layer = ["qkv", "sattn", "o", "qc", "xattn+oc", "gu", "down"]     # cross-attention fused into o_proj
+        if os.environ.get("T5G_FUSE_XATTN") == "1":
+            per_layer = ["qkv", "sattn", "o", "qc", "xattn+oc", "gu", "down"]     # cross-attention fused into o_proj
+        else:
+            per_layer = ["qkv", "sattn", "o+qc", "cattn", "oc", "gu", "down"]     # o_proj + cross q_proj in one kernel
     names = ["head1", "head2", "sampler"] + per_layer * 26
     print("step span us", (e_.max() - t0) / 1000.0)
     agg = {}

@@ -346,7 +346,7 @@ def main():
         "roofline": None,
         "step_roofline": {"bound": "hbm", "achieved": float(achieved), "peak": peak, "unit": "GB/s",
                           "frac": float(achieved / peak), "peak_source": peak_src,
-                          "what": "whole decode step (one CUDA-graph replay = 212 launches): (weights + KV bytes) / ms_per_token",
+                          "what": "whole decode step (186 kernel launches, 4 steps per CUDA-graph replay): (weights + KV bytes) / ms_per_token",
                           "algorithmic_bytes_per_step": float(alg_bytes)},
     }
     kbytes, kus = time_dominant_kernel(eng, cfg, dev)

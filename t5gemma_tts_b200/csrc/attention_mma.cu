@@ -88,8 +88,10 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   float* o_s = f_wt + (size_t)a.n_splits * G;                           // [G][D] unnormalised partial of this CTA
 
   pdl_launch_dependents();
-  const int hk = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
-  unsigned long long* probe = (a.probe && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && blockIdx.z < 64) ? a.probe + blockIdx.z * 11 : nullptr;
+  // rows in descending key count (host-maintained, written before the launch): CTAs are scheduled in blockIdx order, so
+  // the long rows start first -- beside the producer GEMM's CTAs -- instead of defining the tail of the kernel
+  const int hk = blockIdx.x, split = blockIdx.y, b = a.row_order ? a.row_order[blockIdx.z] : (int)blockIdx.z;
+  unsigned long long* probe = (a.probe && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && b < 64) ? a.probe + b * 11 : nullptr;
 #define AM_PROBE(k) do { if (probe) probe[k] = globaltimer_ns(); } while (0)
   AM_PROBE(0);
   const int NS = a.n_splits;

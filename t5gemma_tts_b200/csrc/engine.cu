@@ -99,6 +99,7 @@ struct T5GEngine {
   cudaGraphExec_t multi_graph = nullptr, multi_graph_fx = nullptr; int nodes_multi = 0, nodes_multi_fx = 0, graph_steps = 4;
   cudaGraphExec_t step_graph_fx = nullptr; int nodes_per_step_fx = 0;   // variant with cross-attention fused into its o_proj
   int last_nodes_per_step = 0;
+  int *d_order_self = nullptr, *d_order_cross = nullptr; bool use_row_order = true;   // batched attention: rows by descending length
   unsigned long long* d_barrier = nullptr; bool use_pair = true;         // o_proj + cross q_proj in one kernel (gemv_pair.cu)
   int xf_max_keys = 0; bool use_xf = false;                              // capacity (encoder keys over live rows) of that kernel; opt-in (T5G_FUSE_XATTN=1):
                                                                          // measured 11.9 us vs 9.4 us for the two separate kernels (profiles/r1_gemv_design_experiments.md)
@@ -307,6 +308,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_ATTN_PRELOAD")) e->attn_preload = atoi(s) != 0;
   if (const char* s = getenv("T5G_FUSE_XATTN")) e->use_xf = atoi(s) != 0;
   if (const char* s = getenv("T5G_GEMV_PAIR")) e->use_pair = atoi(s) != 0;
+  if (const char* s = getenv("T5G_ROW_ORDER")) e->use_row_order = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA")) e->attn_mma = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA_SMALL")) e->attn_mma_small = atoi(s) != 0;
   DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
@@ -337,6 +339,10 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   { const size_t V8 = ((size_t)e->V + 7) & ~(size_t)7; DM(e->d_samp_u64, (size_t)e->samp_scratch_rows * 2 * V8); DM(e->d_samp_f32, (size_t)e->samp_scratch_rows * 2 * V8); }
   DM(e->d_attn, (size_t)B * QD); DM(e->d_trace, 2 * T5G_TRACE_STRIDE);
   DM(e->d_barrier, 2); T5G_CUDA(cudaMemset(e->d_barrier, 0, 2 * sizeof(unsigned long long)));
+  DM(e->d_order_self, B); DM(e->d_order_cross, B);
+  { std::vector<int> id(B); for (int i = 0; i < B; ++i) id[i] = i;
+    T5G_CUDA(cudaMemcpy(e->d_order_self, id.data(), sizeof(int) * B, cudaMemcpyHostToDevice));
+    T5G_CUDA(cudaMemcpy(e->d_order_cross, id.data(), sizeof(int) * B, cudaMemcpyHostToDevice)); }
   DM(e->d_xn, (size_t)B * d); DM(e->d_attn_bf, (size_t)B * QD); DM(e->d_act_bf, (size_t)B * I); DM(e->d_t1_bf, (size_t)B * d);
   T5G_CUDA(cudaDeviceSynchronize());
   return T5G_OK;
@@ -838,6 +844,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
+      a.row_order = e->d_order_self;
       a.probe = (e->use_trace && l == 5) ? e->d_trace + 300 : nullptr;
       a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload; a.mma = e->attn_mma; a.trace = next_trace();
       if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
@@ -848,6 +855,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
       a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
+      a.row_order = e->d_order_cross;
       a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload; a.mma = e->attn_mma; a.trace = next_trace();
       if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
       nl++; }
@@ -868,6 +876,20 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
   T5G_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream_;
   CU(cudaEventRecord(e->ev[3], st));
+  if (e->c.max_slots > 4 && e->use_row_order) {
+    // rows by descending key count (host's last known lengths: prompt + tokens generated at the last poll)
+    const int B = e->c.max_slots;
+    std::vector<int> os(B), oc(B), ls(B), lc(B);
+    for (int s = 0; s < B; ++s) {
+      os[s] = oc[s] = s;
+      ls[s] = e->hslots[s].in_use ? e->hslots[s].n_dec + e->h_mirror[s * 4 + 2] : -1;
+      lc[s] = e->hslots[s].in_use ? e->hslots[s].n_text : -1;
+    }
+    std::stable_sort(os.begin(), os.end(), [&](int x, int y) { return ls[x] > ls[y]; });
+    std::stable_sort(oc.begin(), oc.end(), [&](int x, int y) { return lc[x] > lc[y]; });
+    CU(cudaMemcpyAsync(e->d_order_self, os.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(e->d_order_cross, oc.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  }
   // cross-attention fused into o_proj when the encoder keys of all rows in use fit its shared-memory staging
   bool fuse = false;
   if (e->c.max_slots <= 4 && e->use_xf && e->xf_max_keys > 0) {

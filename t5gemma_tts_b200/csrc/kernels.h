@@ -69,6 +69,7 @@ struct AttnDecodeArgs {
   PrefetchRange pf[2];
   unsigned long long* trace;
   unsigned long long* probe;               // optional [B][11] in-kernel checkpoints of the (kv head 0, split 0) CTAs (debug)
+  const int* row_order;                    // optional [B]: blockIdx.z -> row; longest rows first so they are scheduled first
 };
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
 bool attn_decode_mma_supported(const AttnDecodeArgs& a);

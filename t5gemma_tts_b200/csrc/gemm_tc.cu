@@ -135,6 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       }
       pdl_launch_dependents();
       pdl_wait();
+      trace_begin(p.trace);
       for (int i = 0; i < pre; ++i) tma_load_2d(S.x[i], &map_x, (kb0 + i) * TC_BK, t0, &S.full[i]);
       for (int i = NSTAGE; i < nkb; ++i) {
         const int s = i % NSTAGE;
@@ -229,6 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  trace_end(p.trace);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
@@ -510,7 +512,10 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
   TcParams p{a.M, a.N, a.K, a.epilogue, a.bias, a.out, a.ldo, kbps, split, atomic, a.trace, a.probe};
   dim3 grid((a.N + TC_BM - 1) / TC_BM, (a.M + tokt - 1) / tokt, split);
   static int use_stream = -1;
-  if (use_stream < 0) { const char* e = getenv("T5G_GEMM_STREAM"); use_stream = e ? atoi(e) : 1; }
+  // TMA front end by default.  The cp.async front end (T5G_GEMM_STREAM=1) looked faster while both kernels were bound by
+  // the old 4-warp epilogue; with the epilogue fixed the TMA ring wins on every decode GEMM at 64 rows (gate|up 17.9 ->
+  // 16.8 us, down 10.1 -> 8.9, vocabulary 71.8 -> 63.8; step 2.31 -> 2.22 ms; 16 rows 2.02 -> 1.84 ms)
+  if (use_stream < 0) { const char* e = getenv("T5G_GEMM_STREAM"); use_stream = e ? atoi(e) : 0; }
   if (use_stream && tokt <= 128) {
     switch (tokt) {
       case 16: return launch_stream<16, 8>(a, p, grid, st, pdl);

@@ -524,6 +524,16 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
       default: return launch_stream<128, 6>(a, p, grid, st, pdl);
     }
   }
+  static int small_ring = -1;       // experiment: rings of <= 100 KB so that two CTAs (of consecutive kernels) share an SM
+  if (small_ring < 0) { const char* e = getenv("T5G_TC_SMALL_RING"); small_ring = e ? atoi(e) : 0; }
+  if (small_ring) {
+    switch (tokt) {
+      case 16: return launch_tc<16, 5>(mw, mx, p, grid, st, pdl);
+      case 32: return launch_tc<32, 5>(mw, mx, p, grid, st, pdl);
+      case 64: return launch_tc<64, 4>(mw, mx, p, grid, st, pdl);
+      default: break;
+    }
+  }
   switch (tokt) {
     case 16: return launch_tc<16, 8>(mw, mx, p, grid, st, pdl);
     case 32: return launch_tc<32, 8>(mw, mx, p, grid, st, pdl);

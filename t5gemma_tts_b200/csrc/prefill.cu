@@ -25,8 +25,8 @@ __global__ void embed_slots_kernel(const bf16* __restrict__ table, const SlotDev
 // one CTA per token: h_out = h_in + rmsnorm(y)*g_post ; xn/xf = rmsnorm(h_out)*g_pre  (HF:66-74 in fp32).
 // Single reduction pass: with r = rsqrt(mean(y^2)+eps), sum(h + y r g)^2 = S2 + 2 r S3 + r^2 S4; all loads are
 // 128-bit and issued before the reduction; the gains are fetched before griddepcontrol.wait (PDL).
-constexpr int NK_THREADS = 128;
-constexpr int NK_MAXV = 8;                       // float4 per thread: d <= 128*4*8 = 4096
+constexpr int NK_THREADS = 512;
+constexpr int NK_MAXV = 2;                       // float4 per thread: d <= 512*4*2 = 4096
 // (activations are read with ld.global.cg: under PDL this kernel is launched while its producer is still running, so
 // they must not come from the non-coherent read-only path)
 __global__ void __launch_bounds__(NK_THREADS) norm_kernel(const float* h_in, const float* y,

@@ -99,6 +99,7 @@ struct T5GEngine {
   cudaGraphExec_t multi_graph = nullptr, multi_graph_fx = nullptr; int nodes_multi = 0, nodes_multi_fx = 0, graph_steps = 4;
   cudaGraphExec_t step_graph_fx = nullptr; int nodes_per_step_fx = 0;   // variant with cross-attention fused into its o_proj
   int last_nodes_per_step = 0;
+  bool prefill_pdl = true;
   int *d_order_self = nullptr, *d_order_cross = nullptr; bool use_row_order = true;   // batched attention: rows by descending length
   unsigned long long* d_barrier = nullptr; bool use_pair = true;         // o_proj + cross q_proj in one kernel (gemv_pair.cu)
   int xf_max_keys = 0; bool use_xf = false;                              // capacity (encoder keys over live rows) of that kernel; opt-in (T5G_FUSE_XATTN=1):
@@ -200,7 +201,9 @@ cudaError_t gemm(T5GEngine* e, const bf16* A, const bf16* W, int M, int N, int K
                  void* out, int ldo, cudaStream_t st) {
   GemmArgs g{A, W, M, N, K, epi, bias, out, ldo, 0};
   e->launches++;
-  if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms);
+  // programmatic dependent launch in the prefill chain as well: the GEMM streams its first weight tiles while the previous
+  // kernel drains (kernels that are not PDL-aware simply complete first)
+  if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms, e->use_pdl && e->prefill_pdl);
   return launch_gemm_simt(g, st);
 }
 
@@ -309,6 +312,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_FUSE_XATTN")) e->use_xf = atoi(s) != 0;
   if (const char* s = getenv("T5G_GEMV_PAIR")) e->use_pair = atoi(s) != 0;
   if (const char* s = getenv("T5G_ROW_ORDER")) e->use_row_order = atoi(s) != 0;
+  if (const char* s = getenv("T5G_PREFILL_PDL")) e->prefill_pdl = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA")) e->attn_mma = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA_SMALL")) e->attn_mma_small = atoi(s) != 0;
   DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
@@ -587,8 +591,8 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   for (int l = 0; l < c.n_enc_layers; ++l) {
     const EncLayer& L = e->enc[l];
     // h += post_ff(prev y) ; xn = pre_sa(h)
-    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Te, d, c.rms_eps, st));
-    else CU(launch_norm(e->p_h, e->p_y, e->enc[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st));
+    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl));
+    else CU(launch_norm(e->p_h, e->p_y, e->enc[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl));
     e->launches++;
     CU(gemm(e, e->p_xn, L.wqkv, Te, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st));
     RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Te;
@@ -599,12 +603,12 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
     CU(prefill_attention(e, aa, e->p_v, e->p_vt_off_e, Te, n_req, max_text, max_text, st));
     CU(gemm(e, e->p_att, L.wo, Te, d, QD, GE_F32, nullptr, e->p_y, d, st));
-    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st)); e->launches++;
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
     CU(gemm(e, e->p_xn, L.wgu, Te, 2 * I, d, GE_GEGLU_BF16, nullptr, e->p_act, I, st));
     CU(gemm(e, e->p_act, L.wd, Te, d, I, GE_F32, nullptr, e->p_y, d, st));
   }
   // memory = final_norm(h + post_ff(y))
-  CU(launch_norm(e->p_h, e->p_y, e->enc[c.n_enc_layers - 1].g_post_ff, e->g_enc_final, nullptr, e->p_mem_bf, e->p_memory, Te, d, c.rms_eps, st)); e->launches++;
+  CU(launch_norm(e->p_h, e->p_y, e->enc[c.n_enc_layers - 1].g_post_ff, e->g_enc_final, nullptr, e->p_mem_bf, e->p_memory, Te, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
   CU(cudaEventRecord(e->ev[1], st));
 
   // ================= decoder over BOS + prompt (HF:748-828; models/t5gemma.py:183-243) =================
@@ -624,8 +628,8 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   CU(launch_embed(e->audio_emb, e->p_ids, sqrtf((float)d), e->p_h, Td, d, st)); e->launches++;
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
-    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Td, d, c.rms_eps, st));
-    else CU(launch_norm(e->p_h, e->p_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st));
+    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl));
+    else CU(launch_norm(e->p_h, e->p_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl));
     e->launches++;
     CU(gemm(e, e->p_xn, L.wqkv, Td, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st));
     RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Td;
@@ -637,7 +641,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
     CU(prefill_attention(e, aa, e->p_v, e->p_vt_off_d, Td, n_req, max_dec, max_dec, st));
     CU(gemm(e, e->p_att, L.wo, Td, d, QD, GE_F32, nullptr, e->p_y, d, st));
-    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ca, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st)); e->launches++;
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ca, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
     // cross attention: q = RoPE(q_proj(x), decoder pos); K/V of this layer computed once from memory
     CU(gemm(e, e->p_xn, L.wq_c, Td, QD, d, GE_F32, nullptr, e->p_qkv, QD, st));
     RopeSplitArgs rq{}; rq.qkv = e->p_qkv; rq.ld = QD; rq.q_off = 0; rq.k_off = -1; rq.v_off = -1; rq.pos = e->p_pos; rq.M = Td;
@@ -652,12 +656,12 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     ac.Tq = Td; ac.Hq = e->Hq; ac.Hkv = e->Hkv; ac.D = D; ac.causal = 0; ac.window = 0; ac.scale = c.attn_scale; ac.softcap = c.attn_softcap; ac.out = e->p_att;
     CU(prefill_attention(e, ac, e->p_cv, e->p_vt_off_e, Te, n_req, max_dec, max_text, st));
     CU(gemm(e, e->p_att, L.wo_c, Td, d, QD, GE_F32, nullptr, e->p_y, d, st));
-    CU(launch_norm(e->p_h, e->p_y, L.g_post_ca, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st)); e->launches++;
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_ca, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
     CU(gemm(e, e->p_xn, L.wgu, Td, 2 * I, d, GE_GEGLU_BF16, nullptr, e->p_act, I, st));
     CU(gemm(e, e->p_act, L.wd, Td, d, I, GE_F32, nullptr, e->p_y, d, st));
   }
   // h = h + post_ff(y) (kept, pre-final-norm) ; p_qkv <- final_norm(h) fp32 for teacher-forced logits
-  CU(launch_norm(e->p_h, e->p_y, e->dec[c.n_dec_layers - 1].g_post_ff, e->g_dec_final, e->p_h, nullptr, e->p_final, Td, d, c.rms_eps, st)); e->launches++;
+  CU(launch_norm(e->p_h, e->p_y, e->dec[c.n_dec_layers - 1].g_post_ff, e->g_dec_final, e->p_h, nullptr, e->p_final, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
   // hand the last token of every request to the decode buffers: h_end buffer <- h, y <- 0
   {
     for (int r = 0; r < n_req; ++r) {

@@ -106,36 +106,59 @@ __global__ void rope_split_kernel(RopeSplitArgs a) {
     page = a.block_table[(size_t)slot * a.bt_stride + idx / a.pool.page_tokens];
     off = idx % a.pool.page_tokens;
   }
-  const int nq = a.q_off >= 0 ? a.Hq * half : 0, nk = a.k_off >= 0 ? a.Hkv * half : 0;
-  for (int i = threadIdx.x; i < nq + nk; i += blockDim.x) {
-    const bool isq = i < nq;
-    const int ii = isq ? i : i - nq;
-    const int hd = ii / half, j = ii - hd * half;
-    float s = 0.f, c = 1.f;
-    if (a.pos) sincosf(pos * a.inv_freq[j], &s, &c);
-    const float* src = row + (isq ? a.q_off : a.k_off) + hd * D;
-    const float x1 = src[j], x2 = src[j + half];
-    const float r1 = x1 * c - x2 * s, r2 = x2 * c + x1 * s;
-    if (isq) {
-      bf16* dst = a.q_out + (size_t)t * a.Hq * D + hd * D;
-      dst[j] = __float2bfloat16(r1); dst[j + half] = __float2bfloat16(r2);
-    } else {
-      if (a.k_out) {
-        bf16* dst = a.k_out + (size_t)t * a.Hkv * D + hd * D;
-        dst[j] = __float2bfloat16(r1); dst[j + half] = __float2bfloat16(r2);
+  // thread = (rotation pair j, head group): the angle is computed once per thread and the loads of a batch of heads
+  // are in flight together (the per-element version paid a sincosf and an L2 round trip per head)
+  const int nqh = a.q_off >= 0 ? a.Hq : 0, nkh = a.k_off >= 0 ? a.Hkv : 0, HT = nqh + nkh;
+  const int j = threadIdx.x % half, grp = threadIdx.x / half, ngrp = blockDim.x / half;
+  float s = 0.f, c = 1.f;
+  if (a.pos) sincosf(pos * a.inv_freq[j], &s, &c);
+  constexpr int HB = 4;
+  for (int h0 = grp; h0 < HT; h0 += ngrp * HB) {
+    float x1[HB], x2[HB];
+#pragma unroll
+    for (int u = 0; u < HB; ++u) {
+      const int h = h0 + u * ngrp;
+      if (h < HT) {
+        const float* src = row + (h < nqh ? a.q_off + h * D : a.k_off + (h - nqh) * D);
+        x1[u] = src[j]; x2[u] = src[j + half];
       }
-      if (a.block_table) {
-        bf16* dst = a.pool.ptr(a.layer, 0, page) + ((size_t)hd * a.pool.page_tokens + off) * D;
-        dst[j] = __float2bfloat16(r1); dst[j + half] = __float2bfloat16(r2);
+    }
+#pragma unroll
+    for (int u = 0; u < HB; ++u) {
+      const int h = h0 + u * ngrp;
+      if (h >= HT) continue;
+      const bf16 r1 = __float2bfloat16(x1[u] * c - x2[u] * s), r2 = __float2bfloat16(x2[u] * c + x1[u] * s);
+      if (h < nqh) {
+        bf16* dst = a.q_out + (size_t)t * a.Hq * D + h * D;
+        dst[j] = r1; dst[j + half] = r2;
+      } else {
+        const int hd = h - nqh;
+        if (a.k_out) {
+          bf16* dst = a.k_out + (size_t)t * a.Hkv * D + hd * D;
+          dst[j] = r1; dst[j + half] = r2;
+        }
+        if (a.block_table) {
+          bf16* dst = a.pool.ptr(a.layer, 0, page) + ((size_t)hd * a.pool.page_tokens + off) * D;
+          dst[j] = r1; dst[j + half] = r2;
+        }
       }
     }
   }
   if (a.v_off >= 0) {
-    for (int i = threadIdx.x; i < a.Hkv * D; i += blockDim.x) {
-      const int hd = i / D, j = i - hd * D;
-      const bf16 v = __float2bfloat16(row[a.v_off + i]);
-      if (a.v_out) a.v_out[(size_t)t * a.Hkv * D + i] = v;
-      if (a.block_table) a.pool.ptr(a.layer, 1, page)[((size_t)hd * a.pool.page_tokens + off) * D + j] = v;
+    const int nv = a.Hkv * D;
+    for (int i0 = threadIdx.x; i0 < nv; i0 += blockDim.x * HB) {
+      float v[HB];
+#pragma unroll
+      for (int u = 0; u < HB; ++u) { const int i = i0 + u * blockDim.x; v[u] = (i < nv) ? row[a.v_off + i] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < HB; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i >= nv) continue;
+        const int hd = i / D, jj = i - hd * D;
+        const bf16 vb = __float2bfloat16(v[u]);
+        if (a.v_out) a.v_out[(size_t)t * a.Hkv * D + i] = vb;
+        if (a.block_table) a.pool.ptr(a.layer, 1, page)[((size_t)hd * a.pool.page_tokens + off) * D + jj] = vb;
+      }
     }
   }
 }

@@ -67,7 +67,7 @@ struct T5GEngine {
   std::vector<HostSlot> hslots;
   // slot state
   SlotDev* d_slots = nullptr; std::vector<SlotDev> h_slots;   // host shadow used when (re)initialising
-  int* h_mirror = nullptr; int* d_mirror = nullptr;           // mapped pinned [max_slots][4]
+  int* h_mirror = nullptr; int* d_mirror = nullptr;           // mapped pinned [max_slots][8]: active, finished, n_generated, cur_len, error flags
   int* h_tokens = nullptr; int* d_tokens = nullptr;           // mapped pinned [max_slots][max_dec_len]
   int* h_picks = nullptr; int* d_picks = nullptr;             // mapped pinned [max_slots][max_dec_len]
   int* d_forced = nullptr;                                    // [max_slots][max_dec_len]
@@ -289,8 +289,8 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   memset(e->h_slots.data(), 0, sizeof(SlotDev) * B);
   DM(e->d_slots, B);
   T5G_CUDA(cudaMemset(e->d_slots, 0, sizeof(SlotDev) * B));
-  T5G_CUDA(cudaHostAlloc((void**)&e->h_mirror, sizeof(int) * 4 * B, cudaHostAllocMapped));
-  memset(e->h_mirror, 0, sizeof(int) * 4 * B);
+  T5G_CUDA(cudaHostAlloc((void**)&e->h_mirror, sizeof(int) * 8 * B, cudaHostAllocMapped));
+  memset(e->h_mirror, 0, sizeof(int) * 8 * B);
   T5G_CUDA(cudaHostGetDevicePointer((void**)&e->d_mirror, e->h_mirror, 0));
   T5G_CUDA(cudaHostAlloc((void**)&e->h_tokens, sizeof(int) * (size_t)B * cfg->max_dec_len, cudaHostAllocMapped));
   T5G_CUDA(cudaHostGetDevicePointer((void**)&e->d_tokens, e->h_tokens, 0));
@@ -545,7 +545,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     CU(cudaMemcpyAsync(e->d_slots + q.slot, &sd, sizeof(SlotDev), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(e->d_self_bt + (size_t)q.slot * e->max_self_pages, hsl.self_pages.data(), sizeof(int) * hsl.self_pages.size(), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(e->d_cross_bt + (size_t)q.slot * e->max_cross_pages, hsl.cross_pages.data(), sizeof(int) * hsl.cross_pages.size(), cudaMemcpyHostToDevice, st));
-    e->h_mirror[q.slot * 4 + 0] = 1; e->h_mirror[q.slot * 4 + 1] = 0; e->h_mirror[q.slot * 4 + 2] = 0; e->h_mirror[q.slot * 4 + 3] = q.n_dec;
+    e->h_mirror[q.slot * 8 + 0] = 1; e->h_mirror[q.slot * 8 + 1] = 0; e->h_mirror[q.slot * 8 + 2] = 0; e->h_mirror[q.slot * 8 + 3] = q.n_dec; e->h_mirror[q.slot * 8 + 4] = 0;
   }
   // the pageable host vectors above must outlive the async copies
   CU(cudaStreamSynchronize(st));
@@ -758,7 +758,7 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
     GemvPairArgs gp{};
     gp.W1 = L.wo; gp.N1 = d; gp.K1 = QD; gp.x = e->d_attn; gp.y = e->d_y; gp.W2 = L.wq_c; gp.N2 = QD; gp.K2 = d;
     gp.h_in = hbuf[t]; gp.g_post = L.g_post_sa; gp.g_pre = L.g_pre_ca; gp.h_out = hbuf[t ^ 1]; gp.eps = c.rms_eps;
-    gp.out = e->d_qc; gp.out_stride = QD; gp.B = B; gp.slots = e->d_slots; gp.barrier = e->d_barrier;
+    gp.out = e->d_qc; gp.out_stride = QD; gp.B = B; gp.slots = e->d_slots; gp.err_slots = e->d_slots; gp.barrier = e->d_barrier;
     if (e->use_pair && B <= 4 && gemv_pair_supported(gp)) {
       gp.trace = next_trace();
       CU(launch_gemv_pair(gp, e->num_sms, st, pdl)); nl++; t ^= 1;
@@ -886,7 +886,7 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
     std::vector<int> os(B), oc(B), ls(B), lc(B);
     for (int s = 0; s < B; ++s) {
       os[s] = oc[s] = s;
-      ls[s] = e->hslots[s].in_use ? e->hslots[s].n_dec + e->h_mirror[s * 4 + 2] : -1;
+      ls[s] = e->hslots[s].in_use ? e->hslots[s].n_dec + e->h_mirror[s * 8 + 2] : -1;
       lc[s] = e->hslots[s].in_use ? e->hslots[s].n_text : -1;
     }
     std::stable_sort(os.begin(), os.end(), [&](int x, int y) { return ls[x] > ls[y]; });
@@ -965,8 +965,11 @@ extern "C" int t5g_poll(T5GEngine* e, T5GSlotState* states, void* stream_) {
   if (cudaEventQuery(e->ev[4]) == cudaSuccess) cudaEventElapsedTime(&e->timings[3], e->ev[3], e->ev[4]);
   cudaGetLastError();
   for (int s = 0; s < e->c.max_slots; ++s) {
-    states[s].active = e->h_mirror[s * 4 + 0]; states[s].finished = e->h_mirror[s * 4 + 1];
-    states[s].n_generated = e->h_mirror[s * 4 + 2]; states[s].cur_len = e->h_mirror[s * 4 + 3];
+    states[s].active = e->h_mirror[s * 8 + 0]; states[s].finished = e->h_mirror[s * 8 + 1];
+    states[s].n_generated = e->h_mirror[s * 8 + 2]; states[s].cur_len = e->h_mirror[s * 8 + 3];
+    // device-side error flags (SlotDev.error): 2 = sampler scratch missing, 4 = grid barrier of gemv_pair timed out
+    const int err = e->h_mirror[s * 8 + 4];
+    T5G_CHECK((err & 6) == 0, T5G_ERR_STATE, "slot %d: device-side error flags 0x%x (2: sampler scratch missing, 4: grid barrier timeout)", s, err);
   }
   return T5G_OK;
 }
@@ -974,7 +977,7 @@ extern "C" int t5g_poll(T5GEngine* e, T5GSlotState* states, void* stream_) {
 extern "C" int t5g_read_tokens(T5GEngine* e, int slot, int32_t* out, int max_tokens, int* n_out, void* stream_) {
   T5G_CHECK(e && out && n_out && slot >= 0 && slot < e->c.max_slots, T5G_ERR_INVALID, "bad arguments");
   CU(cudaStreamSynchronize((cudaStream_t)stream_));
-  const int n = std::min(max_tokens, e->h_mirror[slot * 4 + 2]);
+  const int n = std::min(max_tokens, e->h_mirror[slot * 8 + 2]);
   memcpy(out, e->h_tokens + (size_t)slot * e->c.max_dec_len, sizeof(int) * n);
   *n_out = n;
   return T5G_OK;
@@ -983,7 +986,7 @@ extern "C" int t5g_read_tokens(T5GEngine* e, int slot, int32_t* out, int max_tok
 extern "C" int t5g_read_picks(T5GEngine* e, int slot, int32_t* out, int max_tokens, int* n_out, void* stream_) {
   T5G_CHECK(e && out && n_out && slot >= 0 && slot < e->c.max_slots, T5G_ERR_INVALID, "bad arguments");
   CU(cudaStreamSynchronize((cudaStream_t)stream_));
-  const int n = std::min(max_tokens, e->h_mirror[slot * 4 + 2]);
+  const int n = std::min(max_tokens, e->h_mirror[slot * 8 + 2]);
   memcpy(out, e->h_picks + (size_t)slot * e->c.max_dec_len, sizeof(int) * n);
   *n_out = n;
   return T5G_OK;
@@ -998,7 +1001,7 @@ extern "C" int t5g_release_slot(T5GEngine* e, int slot) {
   SlotDev sd; memset(&sd, 0, sizeof(sd));
   e->h_slots[slot] = sd;
   CU(cudaMemcpy(e->d_slots + slot, &sd, sizeof(sd), cudaMemcpyHostToDevice));
-  for (int i = 0; i < 4; ++i) e->h_mirror[slot * 4 + i] = 0;
+  for (int i = 0; i < 8; ++i) e->h_mirror[slot * 8 + i] = 0;
   return T5G_OK;
 }
 

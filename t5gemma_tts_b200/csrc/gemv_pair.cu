@@ -134,7 +134,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemv_pair_kernel(GemvPairArgs a
     __threadfence();                                       // ... and visible before the arrival
     const unsigned long long ticket = atomicAdd(a.barrier, 1ULL);
     const unsigned long long target = (ticket / gridDim.x + 1ULL) * gridDim.x;
-    while (*reinterpret_cast<volatile unsigned long long*>(a.barrier) < target) { }
+    // bounded spin: if the grid is ever not co-resident (foreign work hogging SMs) the step reports an error through the
+    // slot record instead of hanging the device
+    long long spins = 0;
+    while (*reinterpret_cast<volatile unsigned long long*>(a.barrier) < target) {
+      if (++spins > (1LL << 28)) { if (a.err_slots) a.err_slots[0].error |= 4; break; }
+    }
     __threadfence();
   }
   __syncthreads();

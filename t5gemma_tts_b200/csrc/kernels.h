@@ -33,7 +33,7 @@ struct GemvPairArgs {
   const float* h_in; const float* g_post; const float* g_pre; float* h_out;
   float eps;
   float* out; int out_stride;
-  int B; const SlotDev* slots;
+  int B; const SlotDev* slots; SlotDev* err_slots;
   unsigned long long* barrier;       // ticket counter of the grid-wide barrier (zeroed once at engine creation)
   unsigned long long* trace;
 };
@@ -156,7 +156,7 @@ struct SamplerArgs {
   float progress_scale;
   int* tokens_out; int tokens_stride; // [slot][tokens_stride], entry n_generated (flat_tokens: entry 0)
   int flat_tokens;
-  int* host_mirror;                   // optional mapped-host [rows][4]: active, finished, n_generated, cur_len
+  int* host_mirror;                   // optional mapped-host [rows][8]: active, finished, n_generated, cur_len, error flags
   float* rope_out; const float* inv_freq; int head_dim;   // optional: cos|sin table of the new position per row
   unsigned long long* trace;
   PrefetchRange pf[4];

@@ -660,8 +660,8 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
       sl.pos = (float)p;
     }
     if (a.host_mirror) {
-      volatile int* hm = a.host_mirror + row * 4;
-      hm[0] = sl.active; hm[1] = sl.finished; hm[2] = n_gen + 1; hm[3] = new_len;
+      volatile int* hm = a.host_mirror + row * 8;
+      hm[0] = sl.active; hm[1] = sl.finished; hm[2] = n_gen + 1; hm[3] = new_len; hm[4] = sl.error;
     }
     S.total = sl.pos;
   }

@@ -1,14 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- T5Gemma-TTS token-generation hot path on B200 (contract: see the task statement).
 
-A "step" is one utterance through the hot path (encoder prefill -> decoder prefill over the voice prompt ->
-autoregressive decode until the reference's stop rules fire).  Workload at every N = BASELINE.json configs[1]:
-T5Gemma-TTS-2b-2b random-init, bf16 weights, batch 1 per GPU, 64-token text, 150-token voice prompt + 10 s
-target (500 XCodec2 tokens; random-init never emits EOS, so the time-budget rule stops at 751 tokens exactly as
-the reference does), top_k=30 / top_p=0.9 / T=0.8.  N>1: one engine replica per GPU, requests sharded, no
-collective on the data path (NCCL only gathers token counts and timings) -> "scaling": "weak".
+Metric (BASELINE.json): XCodec2 audio tokens/s per GPU at bs=64 and aggregate over N GPUs; bs=1 ms/token; RTF.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-cpu-baseline]
+Headline workload at every N (weak scaling, request-sharded, no collective on the data path): every GPU runs one
+engine replica with 64 rows (configs[2]'s paged-KV CUDA-graph step) and serves its LPT shard of utterances drawn from
+configs[3]'s distribution (durations U[3,15] s, text length U[32,128], no prompt, top_k=30/top_p=0.9/T=0.8).  A "step" is
+one batch of 64 utterances per GPU; the timed region is ONE continuous-batching job over K*64 utterances per GPU (so
+at the default K the queue is >= 5x deeper than the rows and the ragged tail does not dominate); N=8, K=4 is exactly
+configs[3] (2048 utterances on 8 GPUs).  Random-init weights never emit eos, so every utterance ends at the reference's
+time-budget rule (target + 250 tokens).
+  value  = tokens of all ranks / max-over-ranks CUDA-event time of the job (request ids already staged on the host side of
+           the C ABI; the events bracket every prefill + decode call of the job on the launching stream)
+  e2e    = the same job through the public API (inference_tts_batch) from pinned host tensors to host result tensors,
+           host wall clock
+First-class blocks on the same line: `bs64_step` (all 64 rows busy, measured contexts, HBM roofline), `bs1`
+(configs[1]: ms/token, RTF, e2e), `roofline` (= the bs=1 decode step, north_star's 70 % target), `prefill`
+(configs[4] encoder prefill, tensor roofline), `parity_2b` (>= 64 teacher-forced decode steps at full size for both
+decode paths vs the fp32 oracle), `cpu_baseline`.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 """
 from __future__ import annotations
 
@@ -26,17 +37,33 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = ("configs[1]: T5Gemma-TTS-2b-2b random-init (seed 0), bs=1/GPU, 64-token text, 150-token voice prompt "
-            "(+y_sep) + 10 s target (500 tok), top_k=30 top_p=0.9 T=0.8")
+ROWS = 64
+WORKLOAD = ("request-sharded continuous batching, 64-row engine per GPU (configs[2] step), utterances from configs[3]: "
+            "T5Gemma-TTS-2b-2b random-init (seed 0) bf16, durations U[3,15] s, text U[32,128] tokens, no prompt, "
+            "top_k=30 top_p=0.9 T=0.8; one step = 64 utterances per GPU")
+WORKLOAD_BS1 = ("configs[1]: bs=1, 64-token text, 150-token voice prompt (+y_sep) + 10 s target (500 tok), "
+                "top_k=30 top_p=0.9 T=0.8")
 N_TEXT, N_PROMPT, TARGET_TOKENS = 64, 150, 500
+KW = dict(top_k=30, top_p=0.9, temperature=0.8)
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sus=float(d["bf16_tflops_sustained"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1600.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def profile_traffic(key: str):
+    """dram bytes per launch from a committed ncu --set full capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+        return d.get(key)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -86,7 +113,8 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(seed: int, cfg):
+# ----------------------------------------------------------------------------------------------- workloads
+def make_inputs_bs1(seed: int, cfg):
     g = torch.Generator().manual_seed(seed)
     x = torch.randint(2, min(255000, cfg.text_vocab), (1, N_TEXT), generator=g)
     prompt = torch.randint(0, cfg.audio_vocab, (1, N_PROMPT, 1), generator=g)
@@ -95,16 +123,46 @@ def make_inputs(seed: int, cfg):
     return x, torch.tensor([N_TEXT]), y, tgt
 
 
-def engine_config():
+def make_utterances(n: int, seed: int = 2048):
+    """configs[3]: (text ids int64 pinned tensor, target tokens) per utterance, fixed RNG seed."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        S = int(rng.integers(32, 129))
+        tgt = int(50 * rng.uniform(3, 15))
+        out.append((torch.from_numpy(rng.integers(2, 255000, S)), tgt))
+    return out
+
+
+def engine_config(rows: int, **kw):
     from t5gemma_tts_b200 import EngineConfig
-    return EngineConfig(max_slots=1, max_text_len=128, max_dec_len=1024, max_prefill_tokens=1024)
+    base = dict(max_slots=rows, max_text_len=128, max_dec_len=1024, max_prefill_tokens=8192 if rows > 1 else 1024)
+    base.update(kw)
+    return EngineConfig(**base)
 
 
-def oracle_from_engine_weights(cfg, device):
-    """fp32 CPU oracle holding exactly the (bf16-representable) weights the engine was given."""
-    from oracle.t5gemma_voice_oracle import Oracle, OracleConfig
+def new_engine(cfg, dev):
+    from t5gemma_tts_b200 import T5GemmaVoiceEngine
     from t5gemma_tts_b200.random_init import iter_random_state_dict
-    sd = {k: v.float().cpu() for k, v in iter_random_state_dict(cfg, seed=0, device=device)}
+    eng = T5GemmaVoiceEngine(cfg, device=dev)
+    eng.load_state_dict(iter_random_state_dict(cfg, seed=0, device=dev))
+    return eng
+
+
+def t5_config_dict_2b():
+    from transformers.models.t5gemma import T5GemmaConfig
+    return T5GemmaConfig().to_dict()
+
+
+def fp32_cpu_weights(cfg, device):
+    """The engine's (bf16-representable) random-init weights as fp32 CPU tensors, shared by the oracle and by the
+    reference model of the cpu_baseline / reference arm."""
+    from t5gemma_tts_b200.random_init import iter_random_state_dict
+    return {k: v.float().cpu() for k, v in iter_random_state_dict(cfg, seed=0, device=device)}
+
+
+def oracle_from(cfg, sd):
+    from oracle.t5gemma_voice_oracle import Oracle, OracleConfig
     ocfg = OracleConfig(hidden=cfg.hidden, inter=cfg.inter, n_enc_layers=cfg.n_enc_layers, n_dec_layers=cfg.n_dec_layers,
                         n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, head_dim=cfg.head_dim,
                         sliding_window=cfg.sliding_window, query_pre_attn_scalar=cfg.query_pre_attn_scalar,
@@ -113,125 +171,144 @@ def oracle_from_engine_weights(cfg, device):
     return Oracle(ocfg, sd)
 
 
-def cpu_port_run(orc, x, y, tgt, n_tokens: int, cores: int):
-    """Times the CPU port (oracle) on a bounded sample: prefill once (untimed), then n_tokens greedy decode
-    steps of the hot loop (head -> argmax -> embed -> 26 layers).  Returns tokens/s and first-step logits."""
-    torch.set_num_threads(cores)
-    c = orc.cfg
-    with torch.no_grad():
-        mem = orc.encoder(x[0])
-        cross = orc.cross_kv(mem)
-        cache = [None] * c.n_dec_layers
-        dec_ids = torch.cat([torch.tensor([c.empty_token]), y[0, :, 0]])
-        est_total = int(tgt[0]) + 1
-        hid = orc.decoder(orc.embed_audio(dec_ids), orc.decoder_prefill_positions(len(dec_ids), est_total), cache, cross)
-        last = hid[-1:]
-        cur = len(dec_ids)
-        first_logits = None
-        t0 = time.perf_counter()
-        for i in range(n_tokens):
-            logits = orc.head(last)[0]
-            if first_logits is None:
-                first_logits = logits.clone()
-            tok = int(torch.argmax(logits))
-            cur += 1
-            p = orc.decoder_step_position(cur, est_total)
-            last = orc.decoder(orc.embed_audio(torch.tensor([tok])), torch.tensor([p]), cache, cross)
-        dt = time.perf_counter() - t0
-    return n_tokens / dt, first_logits.numpy(), mem.numpy()
+# ----------------------------------------------------------------------------------------------- CPU arms
+REF_SAMPLE_GEN = 40      # generated tokens per reference step: target = prompt + 30, extra_cutoff 0.2 s -> 30 + 10 + 2
 
 
-def time_dominant_kernel(eng, cfg, dev):
-    """gate|up GEMV (the largest single kernel of the decode step) timed live with CUDA events on the launching
-    stream; weights rotate over 7 buffers (595 MB > L2) so every launch is HBM-sourced."""
-    import ctypes as C
-    from t5gemma_tts_b200 import lib as L
-    N, K = 2 * cfg.inter, cfg.hidden
-    ws = [(torch.randn(N, K, device=dev) * 0.02).to(torch.bfloat16) for _ in range(7)]
-    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-
-    def run(n):
-        for i in range(n):
-            L.check(eng.lib, eng.lib.t5g_debug_gemv_gateup(eng._h, C.c_void_p(ws[i % 7].data_ptr()), st))
-    run(14)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run(56)
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1000.0 / 56
-    del ws
-    return N * K * 2, us
+def reference_model(sd, device="cpu", dtype=None, extra_cutoff=0.2):
+    """The UNMODIFIED reference (hf_export/modeling_t5gemma_voice.py via oracle/ref_loader.py from baseline/_ref or
+    /root/reference) holding the engine's weights.  Returns None when the reference tree is not available."""
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        return None
+    return ref_loader.build_reference_model_from_tensors(t5_config_dict_2b(), sd.items(), audio_vocab=65536, device=device,
+                                                         dtype=dtype, extra_cutoff=extra_cutoff)
 
 
-def bench_bs64(cfg_mod, dev):
-    """BASELINE.json configs[2]: batched decode, 64 ragged requests (2-20 s targets) on one engine with 64 rows."""
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import bench_batched as bb
-    from t5gemma_tts_b200 import EngineConfig, T5GemmaVoiceEngine
-    from t5gemma_tts_b200.random_init import iter_random_state_dict
-    cfg = EngineConfig(max_slots=64, max_text_len=128, max_dec_len=1536, max_prefill_tokens=8192)
-    eng = T5GemmaVoiceEngine(cfg, device=dev)
-    eng.load_state_dict(iter_random_state_dict(cfg, seed=0, device=dev))
-    reqs = bb.make_requests(64, cfg, seed=0)
-    eng.generate(reqs[:4], chunk_steps=8)
-    torch.cuda.synchronize()
+def reference_step(model, cfg, seed, device="cpu"):
+    """One bounded sample of configs[1] through the reference's own inference_tts: same text, same 150-token prompt, same
+    sampler settings; the target is cut to prompt + 30 tokens and the model's extra_cutoff config field to 0.2 s so the
+    stock stop rule ends the run after ~42 tokens instead of 751.  Encoder + prompt prefill + sampling are all timed."""
+    x, xl, y, _ = make_inputs_bs1(seed, cfg)
+    tgt = torch.tensor([y.shape[1] + 30])
+    torch.manual_seed(seed)
+    x, y = x.to(device), y.to(device)
     t0 = time.perf_counter()
-    outs = eng.generate(reqs, chunk_steps=32)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    toks = sum(len(o) for o in outs)
-    eng.prefill(reqs, list(range(64)))
-    eng.decode(8)
-    eng.poll()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    eng.decode(32)
-    e1.record()
-    eng.poll()
-    step_ms = e0.elapsed_time(e1) / 32
-    eng.close()
-    return {"workload": "configs[2]: 64 ragged requests (S~U[32,96], 50% with 150-token prompt, 2-20 s targets), 64 engine rows",
-            "tokens": toks, "seconds": dt, "tokens_per_s_whole_job": toks / dt, "full_batch_step_ms": step_ms,
-            "tokens_per_s_full_batch": 64 / step_ms * 1000.0}
+    res, gen = model.inference_tts(x, xl.to(device), y, tgt.to(device), prompt_frames=y.shape[1], **KW)
+    if str(device) != "cpu":
+        torch.cuda.synchronize()
+    return int(gen.shape[-1]), time.perf_counter() - t0
+
+
+def oracle_port_step(orc, cfg, seed, n_tokens=8):
+    """Fallback when the reference tree is absent: the fp32 port, prefill timed as well."""
+    x, xl, y, _ = make_inputs_bs1(seed, cfg)
+    tgt = torch.tensor([y.shape[1] + 30])
+    t0 = time.perf_counter()
+    res, gen = orc.inference_tts(x, xl, y, tgt, prompt_frames=y.shape[1], max_new_tokens=n_tokens, **KW)
+    return int(gen.shape[-1]), time.perf_counter() - t0
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    cfg = engine_config()
+    torch.set_num_threads(cores)
+    cfg = engine_config(1)
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    orc = oracle_from_engine_weights(cfg, dev)
-    x, x_lens, y, tgt = make_inputs(1234, cfg)
-    n_tok = 8
-    vals = []
+    sd = fp32_cpu_weights(cfg, dev)
+    model = reference_model(sd)
+    kind = "reference" if model is not None else "port"
+    orc = None if model is not None else oracle_from(cfg, sd)
+    vals, toks, secs = [], 0, 0.0
+    t_begin = time.perf_counter()
+    budget_s = 420.0                      # keep the whole arm within a few minutes whatever K the driver passes
+    done = 0
     for i in range(args.warmup + args.steps):
-        tps, _, _ = cpu_port_run(orc, x, y, tgt, n_tok, cores)
+        n, dt = reference_step(model, cfg, 1234 + i) if model is not None else oracle_port_step(orc, cfg, 1234 + i)
         if i >= args.warmup:
-            vals.append(tps)
-    v = float(np.mean(vals))
+            vals.append(n / dt); toks += n; secs += dt; done += 1
+        if time.perf_counter() - t_begin > budget_s and done >= 1:
+            break
+    v = toks / secs
+    sample = (f"per step: one configs[1] utterance cut to ~{REF_SAMPLE_GEN} generated tokens (target = prompt + 30, "
+              "extra_cutoff 0.2 s), encoder + 152-token prompt prefill + sampling included; "
+              + ("UNMODIFIED reference inference_tts (hf_export/modeling_t5gemma_voice.py from baseline/_ref), fp32 torch CPU, "
+                 "eager attention" if kind == "reference" else "oracle/ fp32 torch port (reference tree absent)")
+              + f"; {done} of {args.steps} timed steps ran inside the {int(budget_s)} s budget")
     out = {"impl": "reference", "metric": "audio_tokens_per_sec", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * n_tok / v, "higher_is_better": True,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs / max(1, done), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD},
-           "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
-                            "sample": f"per step: {n_tok} greedy decode tokens after an untimed prefill "
-                                      "(oracle/ fp32 torch port of models/t5gemma.py; the Python reference cannot travel)"},
+           "config": {"workload": WORKLOAD, "sample_workload": WORKLOAD_BS1 + " (the CPU path has no batched mode: "
+                      "models/t5gemma.py:865 asserts batch_size == 1)"},
+           "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    # like-for-like GPU denominator (SURVEY 8d, optional): the same unmodified reference in bf16 eager ON the B200
+    if model is not None and torch.cuda.is_available() and not args.no_extra:
+        try:
+            del model
+            gm = reference_model(sd, device="cuda", dtype=torch.bfloat16, extra_cutoff=5.0)
+            x, xl, y, tgt = make_inputs_bs1(1234, cfg)
+            tgt = torch.tensor([y.shape[1] + 30])
+            torch.manual_seed(1)
+            for rep in range(2):          # first call warms cuBLAS / allocator
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                res, gen = gm.inference_tts(x.cuda(), xl.cuda(), y.cuda(), tgt.cuda(), prompt_frames=y.shape[1], **KW)
+                torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            out["reference_gpu_bf16_eager"] = {"tokens": int(gen.shape[-1]), "seconds": dt, "tokens_per_s": gen.shape[-1] / dt,
+                                               "what": "unmodified reference inference_tts, bf16, eager attention, on this B200 "
+                                                       "(bs=1, configs[1] text+prompt, 282 generated tokens incl. prefill)"}
+        except Exception as ex:
+            out["reference_gpu_bf16_eager"] = {"error": repr(ex)[:300]}
     print(json.dumps(out))
 
 
+# ----------------------------------------------------------------------------------------------- parity at full size
+def parity_rows(eng, slot, ref_gen, ref_logits, n_steps, eos):
+    """Steps an engine whose slot `slot` is teacher-forced along ref_gen; returns per-step rel-err stats vs ref_logits."""
+    errs, agree, margins = [], 0, []
+    for step in range(n_steps):
+        eng.decode(1)
+        eng.poll()
+        got = eng.read_logits(slot)
+        ref = ref_logits[step].copy()
+        got[eos] = ref[eos] = 0.0
+        errs.append(float(np.abs(got - ref).max() / np.abs(ref).max()))
+        a_g, a_r = int(np.argmax(got)), int(np.argmax(ref))
+        if a_g == a_r:
+            agree += 1
+        else:
+            top2 = np.partition(ref, -2)[-2:]
+            margins.append(float((top2[1] - top2[0]) / np.abs(ref).max()))
+    return {"steps": n_steps, "max_rel_err": max(errs), "mean_rel_err": float(np.mean(errs)), "argmax_agreement": agree / n_steps,
+            "oracle_top1_top2_margin_at_disagreements_rel": margins, "first_step_rel_err": errs[0], "last_step_rel_err": errs[-1]}
+
+
+def oracle_reference_run(orc, cfg, n_steps):
+    from t5gemma_tts_b200 import GenerationRequest
+    x, xl, y, tgt = make_inputs_bs1(1234, cfg)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        res, gen, logits = orc.inference_tts(x, xl, y, tgt, top_k=1, prompt_frames=y.shape[1], max_new_tokens=n_steps + 1,
+                                             return_logits=True)
+        mem = orc.encoder(x[0])
+    dt = time.perf_counter() - t0
+    gen = gen[0, 0].numpy()
+    req = GenerationRequest(text_ids=x[0].numpy(), prompt_ids=y[0, :, 0].numpy(), target_total=int(tgt[0]),
+                            prompt_frames=y.shape[1], top_k=1, forced_tokens=gen[:n_steps])
+    return req, gen, logits.numpy(), mem.numpy(), dt
+
+
+# ----------------------------------------------------------------------------------------------- engine arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-tokens", type=int, default=24)
-    ap.add_argument("--no-extra", action="store_true", help="skip the bs=64 (configs[2]) extra measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle / reference legs (parity_2b, cpu_baseline)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the bs=1, full-batch-step and prefill blocks")
+    ap.add_argument("--parity-steps", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -245,72 +322,208 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    from t5gemma_tts_b200 import GenerationRequest
+    from t5gemma_tts_b200.sharding import lpt_shard
+    peaks = load_peaks()
+    K, W = args.steps, args.warmup
+    out_extra = {}
 
-    from t5gemma_tts_b200 import T5GemmaVoiceEngine
-    from t5gemma_tts_b200.random_init import iter_random_state_dict
-    cfg = engine_config()
-    eng = T5GemmaVoiceEngine(cfg, device=dev)
-    eng.load_state_dict(iter_random_state_dict(cfg, seed=0, device=dev))
-    torch.manual_seed(1 + rank)                       # seed_everything(seed=1) semantics for the uniform draws
+    # ---- CPU oracle first (rank 0 of a single-GPU run): full-size reference logits for both decode paths ----
+    do_cpu = (not args.no_cpu_baseline) and world == 1
+    cfg1 = engine_config(1)
+    sd = orc = None
+    if do_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = fp32_cpu_weights(cfg1, dev)
+        orc = oracle_from(cfg1, sd)
+        p_req, p_gen, p_logits, p_mem, p_dt = oracle_reference_run(orc, cfg1, args.parity_steps)
 
-    # ---- inputs: pinned host tensors (e2e) ----
-    reqs = [make_inputs(1234 + rank * 1000 + i, cfg) for i in range(args.warmup + args.steps)]
-    reqs = [tuple(t.pin_memory() for t in r) for r in reqs]
-    kw = dict(top_k=30, top_p=0.9, temperature=0.8)
+    # ---- headline: request-sharded continuous batching on a 64-row engine per GPU ----
+    cfgB = engine_config(ROWS)
+    eng = new_engine(cfgB, dev)
+    torch.manual_seed(1 + rank)
+    utts = make_utterances(world * (W + K) * ROWS)
+    warm_ids, timed_ids = list(range(world * W * ROWS)), list(range(world * W * ROWS, world * (W + K) * ROWS))
+    cost = lambda i: utts[i][1] + 252
+    mine_w = [warm_ids[j] for j in lpt_shard([cost(i) for i in warm_ids], world)[rank]]
+    mine_t = [timed_ids[j] for j in lpt_shard([cost(i) for i in timed_ids], world)[rank]]
+    pinned = {i: utts[i][0].pin_memory() for i in mine_w + mine_t}
 
-    def run_one(r):
-        x, xl, y, tgt = r
-        xd, yd = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)      # H2D inside the timed region
-        res, gen = eng.inference_tts(xd, xl, yd, tgt, prompt_frames=y.shape[1], chunk_steps=64, **kw)
-        return int(gen.cpu().shape[-1])                                            # D2H of the result
+    def to_requests(idx):
+        return [GenerationRequest(text_ids=pinned[i].numpy(), prompt_ids=np.zeros(0, np.int64), target_total=utts[i][1],
+                                  prompt_frames=0, **KW) for i in idx]
 
-    for r in reqs[: args.warmup]:
-        run_one(r)
+    parity = {}
+    if do_cpu:      # 64-row tensor-core decode path at full size: the oracle's utterance in row 37, other rows busy
+        others = to_requests(mine_w[:ROWS - 1])
+        slots = [s for s in range(ROWS) if s != 37]
+        eng.prefill([p_req] + others, [37] + slots)
+        parity["batched_64row_tcgen05_step"] = parity_rows(eng, 37, p_gen, p_logits, args.parity_steps, cfgB.stop_token)
+        for s in range(ROWS):
+            eng.release(s)
+
+    # warm-up job (W steps of 64 utterances), then the timed job
+    eng.inference_tts_batch(to_requests(mine_w), chunk_steps=32)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    l0 = eng.launch_count()
+    c0 = eng.counters()
+    eng.stats = None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ev0.record()
-    n_tokens, dev_ms, decode_ms, prefill_ms, step_tokens = 0, 0.0, 0.0, 0.0, []
-    for r in reqs[args.warmup:]:
-        n = run_one(r)
-        n_tokens += n
-        step_tokens.append(n)
+    results = eng.inference_tts_batch(to_requests(mine_t), chunk_steps=32)      # host tensors in, host tensors out
     ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     if world > 1:
         dist.barrier()
-    dev_total_ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count() - l0
     clk = clocks.stop()
+    c1 = eng.counters()
+    st = eng.stats
+    n_tokens = int(sum(g.shape[-1] for _, g in results))
+    dev_s = ev0.elapsed_time(ev1) / 1000.0
+    busy_ms = (c1["prefill_ms"] - c0["prefill_ms"]) + (c1["decode_ms"] - c0["decode_ms"])
+    decode_ms = c1["decode_ms"] - c0["decode_ms"]
+    launches = c1["launches"] - c0["launches"]
+    h2d = int(sum(pinned[i].numel() * 8 for i in mine_t) / K)
+    d2h = int(n_tokens * 4 / K)
+    w_bytes, kv_tok = eng.weight_bytes_per_step(), eng.kv_bytes_per_token()
+    job_bytes = w_bytes * st["decode_steps"] + st["kv_token_reads"] * kv_tok
+    job_roof = {"bound": "hbm", "achieved": job_bytes / (decode_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                "what": "decode calls of the whole timed job (ragged tail included): (W_step * steps + sum over generated tokens "
+                        "of (ctx + S) * 106 496 B) / CUDA-event decode time", "decode_steps": st["decode_steps"],
+                "mean_live_rows": st["row_steps"] / max(1, st["decode_steps"]), "decode_ms": decode_ms,
+                "prefill_ms": c1["prefill_ms"] - c0["prefill_ms"], "kernels_per_step": c1["kernels_per_step"]}
+    job_roof["frac"] = job_roof["achieved"] / peaks["hbm"]
 
-    # ---- device-resident measurement ("value"): same utterances, ids already on the GPU, timed with the
-    # engine's own CUDA events (prefill + every decode call), host polling gaps excluded ----
-    tm = []
-    for r in reqs[args.warmup:]:
-        x, xl, y, tgt = r
-        xd, yd = x.to(dev), y.to(dev)
-        torch.cuda.synchronize()
+    # ---- all 64 rows busy: step time at measured contexts ----
+    if not args.no_extra:
+        reqs = to_requests(mine_t[:ROWS])
+        eng.prefill(reqs, list(range(ROWS)))
+        eng.decode(200)
+        s0 = eng.poll()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        res, gen = eng.inference_tts(xd, xl, yd, tgt, prompt_frames=y.shape[1], chunk_steps=1024, **kw)
-        e1.record()
-        torch.cuda.synchronize()
-        t = eng.timings()
-        tm.append((gen.shape[-1], e0.elapsed_time(e1), t[0] + t[2], t[3]))
-    toks_dev = sum(t[0] for t in tm)
-    ms_dev = sum(t[1] for t in tm)
-    prefill_ms = float(np.mean([t[2] for t in tm]))
-    # decode-only step time: last decode call covers all remaining steps at chunk 1024
-    ms_per_token = float(np.mean([t[3] / max(1, t[0]) for t in tm]))
+        NS = 64
+        e0.record(); eng.decode(NS); e1.record()
+        s1 = eng.poll()
+        step_ms = e0.elapsed_time(e1) / NS
+        live = [s for s in range(ROWS) if s1[s].active or s1[s].finished]
+        ctx_sum = sum((s0[s].cur_len + s1[s].cur_len) / 2.0 + len(reqs[s].text_ids) for s in range(ROWS))
+        bytes_step = w_bytes + ctx_sum * kv_tok
+        flops_step = 2.0 * (w_bytes / 2) * ROWS
+        out_extra["bs64_step"] = {
+            "workload": "configs[2] step: 64 rows all busy, contexts 200-264 generated tokens + text (measured)",
+            "ms_per_step": step_ms, "tokens_per_s": ROWS / step_ms * 1e3, "rows_live": len(live),
+            "mean_ctx_plus_text": ctx_sum / ROWS,
+            "roofline": {"bound": "hbm", "achieved": bytes_step / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": bytes_step / (step_ms * 1e-3) / 1e9 / peaks["hbm"], "algorithmic_bytes_per_step": bytes_step,
+                         "traffic": profile_traffic("bs64_step_dram_bytes")},
+            "tensor_pipe_frac_of_sustained": flops_step / (step_ms * 1e-3) / 1e12 / peaks["tf_sus"]}
+        for s in range(ROWS):
+            eng.release(s)
+    eng.close()
+    del eng
 
-    stats = torch.tensor([float(n_tokens), wall, float(toks_dev), ms_dev / 1000.0, float(launches)], device=dev, dtype=torch.float64)
+    # ---- bs=1 (configs[1]) ----
+    bs1 = None
+    eng1 = None
+    if not args.no_extra or do_cpu:
+        eng1 = new_engine(cfg1, dev)
+    if not args.no_extra:
+        torch.manual_seed(1 + rank)
+        n_utt = 3
+        ins = [tuple(t.pin_memory() for t in make_inputs_bs1(1234 + rank * 1000 + i, cfg1)) for i in range(n_utt + 1)]
+
+        def run_one(r, chunk):
+            x, xl, y, tgt = r
+            xd, yd = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+            res, gen = eng1.inference_tts(xd, xl, yd, tgt, prompt_frames=y.shape[1], chunk_steps=chunk, **KW)
+            return int(gen.cpu().shape[-1])
+        run_one(ins[0], 64)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tok1 = sum(run_one(r, 64) for r in ins[1:])
+        torch.cuda.synchronize()
+        wall1 = time.perf_counter() - t0
+        tm = []
+        for r in ins[1:]:
+            n = run_one(r, 1024)
+            t = eng1.timings()
+            tm.append((n, t[0] + t[2], t[3]))
+        ms_tok = float(np.mean([t[2] / max(1, t[0]) for t in tm]))
+        mean_ctx = (N_PROMPT + 2) + np.mean([t[0] for t in tm]) / 2.0
+        alg = eng1.weight_bytes_per_step() + (mean_ctx + N_TEXT) * eng1.kv_bytes_per_token()
+        ach = alg / (ms_tok * 1e-3) / 1e9
+        bs1 = {"workload": WORKLOAD_BS1, "ms_per_token": ms_tok, "tokens_per_s_device": 1000.0 / ms_tok,
+               "prefill_ms": float(np.mean([t[1] for t in tm])), "tokens_per_utterance": float(np.mean([t[0] for t in tm])),
+               "e2e_tokens_per_s": tok1 / wall1, "real_time_factor": (tok1 / 50.0) / wall1,
+               "kernels_per_step": eng1.counters()["kernels_per_step"]}
+        roofline = {"bound": "hbm", "achieved": float(ach), "peak": peaks["hbm"], "unit": "GB/s", "frac": float(ach / peaks["hbm"]),
+                    "traffic": profile_traffic("bs1_step_dram_bytes"), "peak_source": peaks["src"],
+                    "kernel": "bs=1 decode step (north_star: >= 0.70 of the HBM roofline), whole step",
+                    "algorithmic_bytes_per_launch": float(alg), "us_per_launch": ms_tok * 1e3,
+                    "timing": "CUDA events on the launching stream around the decode calls of 3 utterances (751 steps each, "
+                              "4.85 GB of weights streamed per step >> L2)"}
+    else:
+        roofline = dict(job_roof, kernel="bs=64 decode steps of the timed job", traffic=None, peak_source=peaks["src"])
+
+    # ---- full-size parity of the bs<=4 GEMV path + CPU baseline ----
+    cpu_baseline = None
+    if do_cpu:
+        eng1.prefill([p_req], [0])
+        m = eng1.read_memory(0, N_TEXT)
+        parity["encoder_states_rel_err"] = float(np.abs(m - p_mem).max() / np.abs(p_mem).max())
+        parity["single_row_gemv_step"] = parity_rows(eng1, 0, p_gen, p_logits, args.parity_steps, cfg1.stop_token)
+        parity["tolerance"] = 2e-2
+        parity["what"] = (f"{args.parity_steps} teacher-forced decode steps along the fp32 CPU oracle's greedy sequence (configs[1] "
+                          "utterance, 152-token prompt), logits of every step: max |engine - oracle| / max |oracle|")
+        eng1.release(0)
+        cores = os.cpu_count() or 1
+        model = reference_model(sd)
+        if model is not None:
+            n, dt = reference_step(model, cfg1, 1234)
+            cpu_baseline = {"value": n / dt, "unit": "tokens/s", "cores": cores, "kind": "reference",
+                            "sample": f"one configs[1] utterance cut to {n} generated tokens through the UNMODIFIED reference "
+                                      "inference_tts (fp32 torch CPU, eager; encoder + prompt prefill + sampling timed)"}
+            del model
+        else:
+            cpu_baseline = {"value": (args.parity_steps + 1) / p_dt, "unit": "tokens/s", "cores": cores, "kind": "port",
+                            "sample": f"{args.parity_steps + 1} greedy tokens incl. prefill through oracle/ (fp32 torch port)"}
+    if eng1 is not None:
+        eng1.close()
+        del eng1
+
+    # ---- configs[4] encoder prefill (tensor roofline) ----
+    if not args.no_extra and world == 1:
+        try:
+            B, S = 16, 512
+            cfgL = engine_config(B, max_text_len=S, max_dec_len=256, max_prefill_tokens=B * S)
+            engL = new_engine(cfgL, dev)
+            rng = np.random.default_rng(5)
+            reqs = [GenerationRequest(text_ids=rng.integers(2, 255000, S), prompt_ids=np.zeros(0, np.int64), target_total=100,
+                                      prompt_frames=0, **KW) for _ in range(B)]
+            enc_ms = []
+            for rep in range(4):
+                engL.prefill(reqs, list(range(B)))
+                enc_ms.append(engL.timings()[0])
+                for s in range(B):
+                    engL.release(s)
+            enc = float(np.min(enc_ms[1:]))
+            flops = 2 * 2024517888 * B * S + 4 * B * S * S * 2048 * 26
+            out_extra["prefill"] = {"workload": "configs[4] encoder prefill: 16 x 512 text tokens", "encoder_ms": enc,
+                                    "roofline": {"bound": "tensor", "achieved": flops / (enc * 1e-3) / 1e12, "peak": peaks["tf_sus"],
+                                                 "unit": "TFLOP/s", "frac": flops / (enc * 1e-3) / 1e12 / peaks["tf_sus"],
+                                                 "frac_of_burst": flops / (enc * 1e-3) / 1e12 / peaks["tf_burst"],
+                                                 "algorithmic_flops": float(flops)}}
+            engL.close()
+        except Exception as ex:
+            out_extra["prefill"] = {"error": repr(ex)[:300]}
+
+    stats = torch.tensor([float(n_tokens), wall, dev_s, float(launches), busy_ms / 1000.0], device=dev, dtype=torch.float64)
     if world > 1:
         allst = [torch.zeros_like(stats) for _ in range(world)]
         dist.all_gather(allst, stats)
@@ -321,74 +534,26 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    tot_tokens, max_wall = allst[:, 0].sum(), allst[:, 1].max()
-    tot_tokens_dev, max_dev = allst[:, 2].sum(), allst[:, 3].max()
-    peak, peak_src = load_peaks()
-    w_bytes = eng.weight_bytes_per_step()
-    kv_tok = eng.kv_bytes_per_token()
-    mean_ctx = (N_PROMPT + 2) + np.mean(step_tokens) / 2.0
-    alg_bytes = w_bytes + (mean_ctx + N_TEXT) * kv_tok
-    achieved = alg_bytes / (ms_per_token * 1e-3) / 1e9
+    tot_tokens, max_wall, max_dev = allst[:, 0].sum(), allst[:, 1].max(), allst[:, 2].max()
     out = {
-        "metric": "audio_tokens_per_sec", "value": float(tot_tokens_dev / max_dev), "unit": "tokens/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": float(1000.0 * max_wall / args.steps), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "l2": "inputs larger than L2 (4.85 GB of weights streamed per token)",
-                   "tokens_per_utterance": float(np.mean(step_tokens)), "parallelism": f"replicas x{world}"},
-        "ms_per_token_bs1": ms_per_token, "prefill_ms": prefill_ms,
+        "metric": "audio_tokens_per_sec", "value": float(tot_tokens / max_dev), "unit": "tokens/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": float(1000.0 * max_wall / K), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS, "utterances_per_gpu": K * ROWS, "utterances_total": world * K * ROWS,
+                   "l2": "inputs larger than L2 (4.85 GB of weights streamed per decode step)",
+                   "parallelism": f"one engine replica per GPU x{world}, LPT request sharding, no data-path collective"},
+        "tokens_per_s_per_gpu": float(tot_tokens / max_dev / world),
         "real_time_factor": float((tot_tokens / 50.0) / max_wall),
-        "e2e": {"value": float(tot_tokens / max_wall), "unit": "tokens/s",
-                "h2d_bytes_per_step": int((N_TEXT + N_PROMPT + 1) * 8),
-                "d2h_bytes_per_step": int(np.mean(step_tokens) * 4 + (N_PROMPT + 1 + np.mean(step_tokens)) * 8)},
-        "gpu_launches": int(allst[:, 4].sum()),
+        "e2e": {"value": float(tot_tokens / max_wall), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(allst[:, 3].sum()),
         "clocks": clk,
-        "roofline": None,
-        "step_roofline": {"bound": "hbm", "achieved": float(achieved), "peak": peak, "unit": "GB/s",
-                          "frac": float(achieved / peak), "peak_source": peak_src,
-                          "what": "whole decode step (186 kernel launches, 4 steps per CUDA-graph replay): (weights + KV bytes) / ms_per_token",
-                          "algorithmic_bytes_per_step": float(alg_bytes)},
+        "roofline": roofline,
+        "job_roofline_bs64": job_roof,
+        "bs1": bs1,
+        "cpu_baseline": cpu_baseline,
+        "parity_2b": parity or None,
     }
-    kbytes, kus = time_dominant_kernel(eng, cfg, dev)
-    out["roofline"] = {"bound": "hbm", "achieved": float(kbytes / kus / 1e3), "peak": peak, "unit": "GB/s",
-                       "frac": float(kbytes / kus / 1e3 / peak), "traffic": 85002240.0, "peak_source": peak_src,
-                       "kernel": "gemv_kernel<1,P_RES_NORM,E_GEGLU> (gate|up projection, 26 launches per decode step, "
-                                 "largest single kernel: 27 % of the step)",
-                       "algorithmic_bytes_per_launch": float(kbytes), "us_per_launch": float(kus),
-                       "traffic_source": "ncu --set full dram__bytes_read.sum+write.sum per launch (profiles/r1_decode_step_summary.md)",
-                       "timing": "CUDA events on the launching stream, 56 back-to-back launches over 7 rotating weight buffers (595 MB > L2)"}
-    if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
-        orc = oracle_from_engine_weights(cfg, dev)
-        x, xl, y, tgt = reqs[0]
-        tps, first_logits, mem = cpu_port_run(orc, x, y, tgt, args.cpu_tokens, cores)
-        out["cpu_baseline"] = {"value": float(tps), "unit": "tokens/s", "cores": cores, "kind": "port",
-                               "sample": f"{args.cpu_tokens} greedy decode tokens after an untimed prefill of the same "
-                                         "utterance (oracle/ fp32 torch port; weights identical to the engine's)"}
-        # full-size parity on the same weights: encoder states + first-step logits
-        from t5gemma_tts_b200 import GenerationRequest
-        rq = GenerationRequest(text_ids=x[0].numpy(), prompt_ids=y[0, :, 0].numpy(), target_total=int(tgt[0]),
-                               prompt_frames=y.shape[1], top_k=1)
-        eng.prefill([rq], [0])
-        m = eng.read_memory(0, N_TEXT)
-        eng.decode(1)
-        eng.poll()
-        lg = eng.read_logits(0)
-        eos = cfg.stop_token
-        lg[eos] = first_logits[eos] = 0.0
-        out["parity_2b"] = {"encoder_states_rel_err": float(np.abs(m - mem).max() / np.abs(mem).max()),
-                            "first_step_logits_rel_err": float(np.abs(lg - first_logits).max() / np.abs(first_logits).max()),
-                            "argmax_equal": bool(int(np.argmax(lg)) == int(np.argmax(first_logits))),
-                            "tolerance": 2e-2}
-        eng.release(0)
-    else:
-        out["cpu_baseline"] = None
-    if world == 1 and not args.no_extra:
-        try:
-            eng.close()
-            out["extra_bs64"] = bench_bs64(cfg, dev)
-        except Exception as ex:          # the extra must never take the headline line down
-            out["extra_bs64"] = {"error": repr(ex)}
+    out.update(out_extra)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -82,7 +82,8 @@ typedef struct T5GRequest {
   const int64_t* text_ids;      /* HOST pointer, n_text ids (x) */
   int32_t n_dec;                /* 1 + prompt length: BOS ++ y (models/t5gemma.py:902-908) */
   const int64_t* dec_ids;       /* HOST pointer, n_dec audio ids */
-  int32_t target_total;         /* tgt_y_lens */
+  int32_t target_total;         /* tgt_y_lens; < 0 = None: est_total from the 2 s lookahead, no time budget
+                                 * (models/t5gemma.py:896-933); eos is then forced when the slot's max_dec_len is reached */
   int32_t prompt_frames;        /* kwargs["prompt_frames"] */
   int32_t max_new_tokens;       /* 0 = reference behaviour (stop rules only) */
   T5GSampling sampling;
@@ -175,6 +176,11 @@ int64_t t5g_kv_bytes_per_token(const T5GEngine* eng);
 /* Per-phase device timings of the last calls, in milliseconds (CUDA events on the caller's stream):
  * [0]=encoder prefill [1]=cross-KV [2]=decoder prefill [3]=last t5g_decode call. */
 int t5g_get_timings(T5GEngine* eng, float* out_ms4);
+
+/* Running totals since t5g_create (CUDA-event time of every t5g_prefill call and of every t5g_decode call that was
+ * followed by t5g_poll): [0] prefill ms, [1] decode ms, [2] decode steps enqueued, [3] prefill calls, [4] kernel launches,
+ * [5] kernels per decode step of the last call, [6..7] reserved. */
+int t5g_get_counters(T5GEngine* eng, double* out8);
 
 const char* t5g_last_error(void);
 int t5g_abi_version(void);

@@ -27,6 +27,22 @@ from oracle import ref_loader  # noqa: E402
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
+def randomize_norm_gains(model, seed):
+    """HF init leaves every RMSNorm weight at 0 (gain 1+w = 1), which hides a swapped or dropped gain.  Real
+    checkpoints carry distinct non-zero gains, so each norm tensor gets its own seeded N(0, 0.3) draw (the six norms
+    of a PMDecoderLayer, models/t5gemma.py:205-243, the four of an encoder layer and the two final norms)."""
+    g = torch.Generator().manual_seed(seed)
+    n = 0
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if k.startswith(("encoder_module.", "decoder_module.")):
+                continue
+            if k.endswith("layernorm.weight") or k.endswith(".norm.weight"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+                n += 1
+    return n
+
+
 def save_model(name, model, t5d, attn_impl):
     sd = {k: v.detach().float().numpy() for k, v in model.state_dict().items()
           if not (k.startswith("encoder_module.") or k.startswith("decoder_module."))}
@@ -45,7 +61,7 @@ def run_case(model, x, y, tgt, prompt_frames, top_k=1):
     step_logits = []
     hook = model.predict_layer[0].register_forward_hook(
         lambda m, i, o: step_logits.append(o.detach().reshape(-1, o.shape[-1])[-1].clone()))
-    res, gen = model.inference_tts(x, x_lens, y, torch.tensor([tgt]), top_k=top_k, top_p=1.0,
+    res, gen = model.inference_tts(x, x_lens, y, None if tgt is None else torch.tensor([tgt]), top_k=top_k, top_p=1.0,
                                    temperature=1.0, prompt_frames=prompt_frames)
     hook.remove()
     step_logits = torch.stack(step_logits)
@@ -55,7 +71,10 @@ def run_case(model, x, y, tgt, prompt_frames, top_k=1):
         mem = model.encoder_module(input_ids=x, attention_mask=torch.ones_like(x),
                                    position_ids=enc_pos).last_hidden_state
         dec_ids = torch.cat([torch.tensor([cfg.empty_token]), y[0, :, 0], gen[0, 0, :-1]])
-        est_total = max(tgt + 1, y.shape[1] + 1)
+        if tgt is not None:
+            est_total = max(tgt + 1, y.shape[1] + 1)
+        else:                                   # models/t5gemma.py:925-933 (progress_lookahead_secs = 2.0)
+            est_total = max(int(y.shape[1] + 1 + int(cfg.encodec_sr) * 2.0), y.shape[1] + 1)
         T = dec_ids.shape[0]
         # positions exactly as the generate loop produced them: prefill formula for the prompt part,
         # python-float step formula afterwards (models/t5gemma.py:945-950,1086-1099)
@@ -71,7 +90,7 @@ def run_case(model, x, y, tgt, prompt_frames, top_k=1):
                                    use_cache=False, position_ids=pos, pm_decoder_position_ids=pos,
                                    pm_encoder_position_ids=enc_pos)
         tf_logits = model.predict_layer[0](out.last_hidden_state)[0]
-    return dict(x=x.numpy(), y=y.numpy(), tgt=np.int64(tgt), prompt_frames=np.int64(prompt_frames),
+    return dict(x=x.numpy(), y=y.numpy(), tgt=np.int64(-1 if tgt is None else tgt), prompt_frames=np.int64(prompt_frames),
                 memory=mem[0].numpy(), dec_ids=dec_ids.numpy(), dec_pos=pos[0].numpy(),
                 tf_logits=tf_logits.numpy(), gen=gen.numpy(), res=res.numpy(),
                 step_logits=step_logits.numpy(), est_total=np.int64(est_total))
@@ -156,6 +175,7 @@ def main():
     t5a = ref_loader.tiny_t5_config_dict(layers=3)
     for name, impl in (("tinyA_eager", "eager"), ("tinyA_sdpa", "sdpa")):
         model = ref_loader.build_reference_model(t5a, audio_vocab=100, attn_implementation=impl, seed=0)
+        print(name, "norm tensors randomised:", randomize_norm_gains(model, seed=100))
         save_model(name, model, t5a, impl)
         x = torch.randint(2, 500, (1, 12), generator=gen)
         y = torch.randint(0, 100, (1, 5, 1), generator=gen)
@@ -171,10 +191,23 @@ def main():
             sc = silence_case(model)
             np.savez_compressed(os.path.join(OUT, "case_tinyA_eager_silence.npz"), **sc)
             print("silence gen head", sc["gen"][0, 0, :24])
+    # tgt_y_lens=None (models/t5gemma.py:896-933): no time budget, est_total from the 2 s lookahead; the text guard
+    # (text_guard_frames_per_token=3) is what ends the utterance.  Same weights as tinyA_eager; a top_k LIST as well
+    # (models/t5gemma.py:991-994) -- greedy at every step but the list form goes through the schedule path.
+    model = ref_loader.build_reference_model(t5a, audio_vocab=100, attn_implementation="eager", seed=0,
+                                             text_guard_frames_per_token=3)
+    randomize_norm_gains(model, seed=100)
+    x = torch.randint(2, 500, (1, 14), generator=gen)
+    y = torch.randint(0, 100, (1, 4, 1), generator=gen)
+    c = run_case(model, x, y, tgt=None, prompt_frames=4, top_k=[1, 1, 1])
+    c["text_guard_frames_per_token"] = np.int64(3)
+    np.savez_compressed(os.path.join(OUT, "case_tinyA_eager_notarget.npz"), **c)
+    print("notarget gen len", c["gen"].shape)
     # tiny B: wider heads (head_dim 32, 4 layers, GQA 4/2), softcap strongly binding (cap 5)
     t5b = ref_loader.tiny_t5_config_dict(hidden=128, inter=256, layers=4, heads=4, kv_heads=2, head_dim=32,
                                          window=16, qpas=32, softcap=5.0)
     model = ref_loader.build_reference_model(t5b, audio_vocab=200, attn_implementation="eager", seed=1)
+    print("tinyB norm tensors randomised:", randomize_norm_gains(model, seed=101))
     save_model("tinyB_eager", model, t5b, "eager")
     x = torch.randint(2, 500, (1, 33), generator=gen)
     y = torch.randint(0, 200, (1, 21, 1), generator=gen)

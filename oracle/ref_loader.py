@@ -21,7 +21,37 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("T5G_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VENDORED_ROOT = os.path.join(_REPO, "baseline", "_ref")      # git-ignored copy that travels to the GPU box (vendor_reference)
+_VENDOR_ITEMS = ("models", "hf_export", "config.py", "inference_tts_utils.py", "LICENSE")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("T5G_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference"):
+        return "/root/reference"
+    return VENDORED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
+
+
+def vendor_reference(src: str = "/root/reference", dst: str = VENDORED_ROOT) -> bool:
+    """Copies the UNMODIFIED reference files of the hot path into the git-ignored baseline/_ref/ so that the GPU box
+    (which has no /root/reference) can run the real reference as the bench's reference arm.  Build container only."""
+    import shutil
+    if not os.path.isdir(src):
+        return False
+    os.makedirs(dst, exist_ok=True)
+    for item in _VENDOR_ITEMS:
+        s, d = os.path.join(src, item), os.path.join(dst, item)
+        if os.path.isdir(s):
+            shutil.copytree(s, d, dirs_exist_ok=True, ignore=shutil.ignore_patterns("__pycache__"))
+        elif os.path.isfile(s):
+            shutil.copy2(s, d)
+    return True
 
 
 def reference_available() -> bool:
@@ -98,6 +128,46 @@ def tiny_t5_config_dict(hidden=64, inter=128, layers=2, heads=4, kv_heads=2, hea
     cfg = T5GemmaConfig(encoder=dict(mod), decoder=dict(mod), vocab_size=text_vocab,
                         tie_word_embeddings=False)
     return cfg.to_dict()
+
+
+def build_reference_model_from_tensors(t5_config_dict, tensors, audio_vocab=65536, n_special=5,
+                                       attn_implementation="eager", dtype=None, device="cpu", **cfg_kw):
+    """Reference model holding GIVEN weights (an iterable of (state_dict key, tensor)), built without the minutes-long
+    random init of a 2b-2b model: the module tree is created on the meta device, parameters are assigned from
+    `tensors` (cast to `dtype`, moved to `device`), and the non-persistent rotary buffers are re-created by
+    instantiating each rotary module's own class on the target device.  No arithmetic of the reference is touched."""
+    import torch
+    cfg_mod, mdl_mod = load_reference()
+    V = audio_vocab
+    cfg = cfg_mod.T5GemmaVoiceConfig(
+        t5_config_dict=t5_config_dict, attn_implementation=attn_implementation,
+        precision="float32", prune_text_modules=2, audio_vocab_size=V, n_special=n_special,
+        empty_token=V, eog=V + 1, audio_pad_token=V + 2, eos=V + 3, y_sep_token=V + 4, x_sep_token=255999, **cfg_kw)
+    with torch.device("meta"):
+        model = mdl_mod.T5GemmaVoiceForConditionalGeneration(cfg)
+    want = set(model.state_dict().keys())
+    sd = {}
+    for k, t in tensors:
+        if k in want:
+            sd[k] = t.detach().to(device=device, dtype=dtype or torch.float32)
+    missing = [k for k in want if k not in sd and not k.startswith(("encoder_module.", "decoder_module."))]
+    if missing:
+        raise RuntimeError(f"{len(missing)} reference tensors missing, e.g. {missing[:3]}")
+    model.load_state_dict(sd, assign=True, strict=False)
+    for name, mod in list(model.named_modules()):
+        bufs = dict(mod.named_buffers(recurse=False))
+        if bufs and any(b.is_meta for b in bufs.values()):
+            fresh = type(mod)(config=mod.config, device=device) if "device" in type(mod).__init__.__code__.co_varnames \
+                else type(mod)(config=mod.config).to(device)
+            for bn, b in fresh.named_buffers(recurse=False):
+                mod.register_buffer(bn, b, persistent=False)
+            for an in ("attention_scaling", "rope_type", "max_seq_len_cached", "original_max_seq_len"):
+                if hasattr(fresh, an):
+                    setattr(mod, an, getattr(fresh, an))
+    left = [k for k, p in list(model.named_parameters()) + list(model.named_buffers()) if p.is_meta]
+    if left:
+        raise RuntimeError(f"tensors left on the meta device: {left[:4]}")
+    return model.eval()
 
 
 def build_reference_model(t5_config_dict, audio_vocab=100, n_special=5, x_sep_token=None,

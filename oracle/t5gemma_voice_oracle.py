@@ -298,11 +298,15 @@ class Oracle:
         yv = y.transpose(2, 1)[0, 0]                         # [Tp]
         y_len = yv.shape[0]
         prompt_frames = y_len if prompt_frames is None else prompt_frames
-        target_total = int(tgt_y_lens[0])
+        target_total = None if tgt_y_lens is None else int(tgt_y_lens[0])
         cated = torch.cat([torch.tensor([c.empty_token], dtype=torch.long), yv.long()])
         current_length = cated.shape[0]
         prompt_offset = prompt_frames + 1
-        est_total = max(target_total + 1, current_length)
+        if target_total is not None:
+            est_total = target_total + 1
+        else:       # models/t5gemma.py:925-933: no target -> progress_lookahead_secs (2.0 s) past the prompt
+            est_total = int(current_length + int(c.encodec_sr) * 2.0)
+        est_total = max(est_total, current_length)
         cache = [None] * c.n_dec_layers
         pos = self.decoder_prefill_positions(current_length, est_total)
         hid = self.decoder(self.embed_audio(cated), pos, cache, cross)

@@ -71,7 +71,7 @@ struct T5GEngine {
   int* h_tokens = nullptr; int* d_tokens = nullptr;           // mapped pinned [max_slots][max_dec_len]
   int* h_picks = nullptr; int* d_picks = nullptr;             // mapped pinned [max_slots][max_dec_len]
   int* d_forced = nullptr;                                    // [max_slots][max_dec_len]
-  int* d_topk_pool = nullptr; int topk_pool_cap = 0, topk_pool_used = 0;   // int pool: top-k schedules + silence token lists
+  int* d_topk_pool = nullptr; int topk_pool_cap = 0;   // int pool [max_slots][max_dec_len]: per-slot top-k schedule + silence token list
   unsigned long long* d_samp_u64 = nullptr; float* d_samp_f32 = nullptr; int samp_scratch_rows = 0;   // sampler general path
   int* d_sample_silence = nullptr; int n_sample_silence = 0, sample_stop_repetition = 0;   // t5g_sample settings
   // prefill workspaces (T = max_prefill_tokens)
@@ -107,6 +107,8 @@ struct T5GEngine {
   int64_t launches = 0;
   cudaEvent_t ev[6] = {};
   float timings[4] = {0, 0, 0, 0};
+  double tot_prefill_ms = 0, tot_decode_ms = 0; int64_t tot_decode_steps = 0, tot_prefill_calls = 0;   // t5g_get_counters
+  bool decode_pending = false; int pending_steps = 0;
 };
 
 namespace {
@@ -379,7 +381,8 @@ extern "C" int t5g_load_tensor(T5GEngine* e, const char* name, const void* data,
   const std::string n = name;
   // aliases / pruned text modules / buffers of the reference module are accepted and ignored
   if (n.rfind("encoder_module.", 0) == 0 || n.rfind("decoder_module.", 0) == 0 || n.rfind("backbone.lm_head", 0) == 0 ||
-      n.rfind("backbone.model.decoder.embed_tokens", 0) == 0 || n == "class_weight" || n.find("inv_freq") != std::string::npos)
+      n.rfind("backbone.model.decoder.embed_tokens", 0) == 0 || n == "class_weight" || n.find("inv_freq") != std::string::npos ||
+      n.rfind("accuracy_metrics.", 0) == 0)     // legacy keys the reference drops as well (models/t5gemma.py:1131-1141)
     return T5G_OK;
   Dest dst;
   T5G_CHECK(resolve(e, n, &dst), T5G_ERR_INVALID, "unknown tensor name '%s'", name);
@@ -496,20 +499,32 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   int* h_off_e = hs + 5 * Tm; int* h_off_d = h_off_e + (c.max_slots + 1); int* h_last = h_off_d + (c.max_slots + 1);
 
   e->prefill_counter++;
-  e->topk_pool_used = 0;   // schedules live until the next prefill call
   std::vector<int> est_totals(n_req);
   for (int r = 0; r < n_req; ++r) {
     const T5GRequest& q = reqs[r];
     HostSlot& hsl = e->hslots[q.slot];
     free_slot_pages(e, hsl);
     const int prompt_offset = q.prompt_frames + 1;
-    const int est_total = std::max(q.target_total + 1, q.n_dec);          // models/t5gemma.py:925-933
+    // models/t5gemma.py:925-933: est_total = target_total + 1 (BOS); without a target (tgt_y_lens=None, target_total < 0
+    // here) the reference falls back to current_length + encodec_sr * progress_lookahead_secs (2.0) and has no time budget
+    const bool has_target = q.target_total >= 0;
+    const int est_total = std::max(has_target ? q.target_total + 1 : (int)(q.n_dec + (int)(c.encodec_sr * 2.0)), q.n_dec);
     est_totals[r] = est_total;
-    const double lim = (double)q.target_total - (double)prompt_offset + (double)c.encodec_sr * (double)c.extra_cutoff;
-    int budget_limit = (int)std::floor(lim);
-    int max_new = budget_limit + 2;
-    if (max_new < 1) max_new = 1;
-    if (q.max_new_tokens > 0) max_new = std::min(max_new, q.max_new_tokens);
+    int budget_limit, max_new, slot_max_new = q.max_new_tokens;
+    if (has_target) {
+      const double lim = (double)q.target_total - (double)prompt_offset + (double)c.encodec_sr * (double)c.extra_cutoff;
+      budget_limit = (int)std::floor(lim);
+      max_new = budget_limit + 2;
+      if (max_new < 1) max_new = 1;
+      if (q.max_new_tokens > 0) max_new = std::min(max_new, q.max_new_tokens);
+    } else {
+      // unbounded in the reference; here the slot's KV capacity is the bound (eos is forced at max_dec_len)
+      budget_limit = 0x7fffffff;
+      max_new = c.max_dec_len - q.n_dec;
+      T5G_CHECK(max_new >= 1, T5G_ERR_INVALID, "request %d: no room to generate (n_dec %d, max_dec_len %d)", r, q.n_dec, c.max_dec_len);
+      if (q.max_new_tokens > 0) max_new = std::min(max_new, q.max_new_tokens);
+      slot_max_new = max_new;
+    }
     const int max_len = q.n_dec + max_new;
     T5G_CHECK(max_len <= c.max_dec_len, T5G_ERR_INVALID, "request %d: needs %d decoder tokens > max_dec_len %d", r, max_len, c.max_dec_len);
     int rc = alloc_pages(e, hsl.self_pages, cdiv(max_len, PT)); if (rc) return rc;
@@ -519,22 +534,26 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     memset(&sd, 0, sizeof(sd));
     sd.active = 1; sd.finished = 0; sd.n_generated = 0; sd.cur_len = q.n_dec; sd.prompt_offset = prompt_offset;
     sd.target_total = q.target_total; sd.est_total = est_total; sd.n_text = q.n_text; sd.budget_limit = budget_limit;
-    sd.max_new_tokens = q.max_new_tokens; sd.top_k = q.sampling.top_k; sd.top_p = q.sampling.top_p; sd.min_p = q.sampling.min_p;
+    sd.max_new_tokens = slot_max_new; sd.top_k = q.sampling.top_k; sd.top_p = q.sampling.top_p; sd.min_p = q.sampling.min_p;
     sd.temperature = q.sampling.temperature; sd.uniforms = q.uniforms; sd.n_uniforms = q.n_uniforms;
     sd.topk_sched_off = -1; sd.n_topk_sched = 0; sd.last_token = 0; sd.pos = 0.f;
     sd.prev_token = -1; sd.consec_silence = 0; sd.stop_repetition = q.stop_repetition; sd.silence_off = -1; sd.n_silence = 0;
+    // every slot owns a fixed region of the int pool ([slot*max_dec_len, (slot+1)*max_dec_len)): a prefill that admits new
+    // requests while other slots are still decoding never touches their schedules / silence lists
+    int pool_off = q.slot * c.max_dec_len;
+    const int pool_end = pool_off + c.max_dec_len;
     if (q.silence_tokens && q.n_silence > 0) {
-      T5G_CHECK(e->topk_pool_used + q.n_silence <= e->topk_pool_cap, T5G_ERR_OOM, "int pool exhausted (silence tokens)");
-      CU(cudaMemcpyAsync(e->d_topk_pool + e->topk_pool_used, q.silence_tokens, sizeof(int) * q.n_silence, cudaMemcpyHostToDevice, st));
-      sd.silence_off = e->topk_pool_used; sd.n_silence = q.n_silence;
-      e->topk_pool_used += q.n_silence;
+      T5G_CHECK(pool_off + q.n_silence <= pool_end, T5G_ERR_OOM, "request %d: %d silence tokens exceed the slot's int pool (%d)", r, q.n_silence, c.max_dec_len);
+      CU(cudaMemcpyAsync(e->d_topk_pool + pool_off, q.silence_tokens, sizeof(int) * q.n_silence, cudaMemcpyHostToDevice, st));
+      sd.silence_off = pool_off; sd.n_silence = q.n_silence;
+      pool_off += q.n_silence;
     }
     if (q.top_k_schedule && q.n_top_k_schedule > 0) {
-      T5G_CHECK(e->topk_pool_used + q.n_top_k_schedule <= e->topk_pool_cap, T5G_ERR_OOM, "top_k schedule pool exhausted");
-      for (int i = 0; i < q.n_top_k_schedule; ++i)
-      CU(cudaMemcpyAsync(e->d_topk_pool + e->topk_pool_used, q.top_k_schedule, sizeof(int) * q.n_top_k_schedule, cudaMemcpyHostToDevice, st));
-      sd.topk_sched_off = e->topk_pool_used; sd.n_topk_sched = q.n_top_k_schedule;
-      e->topk_pool_used += q.n_top_k_schedule;
+      // entries past the last step that can run are never read (models/t5gemma.py:991-994 clamps the index the other way)
+      const int n_sched = std::min(q.n_top_k_schedule, std::max(1, max_new));
+      T5G_CHECK(pool_off + n_sched <= pool_end, T5G_ERR_OOM, "request %d: top_k schedule + silence list exceed the slot's int pool (%d)", r, c.max_dec_len);
+      CU(cudaMemcpyAsync(e->d_topk_pool + pool_off, q.top_k_schedule, sizeof(int) * n_sched, cudaMemcpyHostToDevice, st));
+      sd.topk_sched_off = pool_off; sd.n_topk_sched = n_sched;
     }
     if (q.forced_tokens && q.n_forced > 0) {
       T5G_CHECK(q.n_forced <= c.max_dec_len, T5G_ERR_INVALID, "request %d: n_forced %d > max_dec_len", r, q.n_forced);
@@ -675,6 +694,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   cudaEventElapsedTime(&e->timings[0], e->ev[0], e->ev[1]);
   cudaEventElapsedTime(&e->timings[2], e->ev[1], e->ev[2]);
   e->timings[1] = 0.f;
+  e->tot_prefill_ms += (double)e->timings[0] + (double)e->timings[2]; e->tot_prefill_calls++;
   return T5G_OK;
 }
 
@@ -955,6 +975,7 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
     }
   }
   CU(cudaEventRecord(e->ev[4], st));
+  e->decode_pending = true; e->pending_steps = max_steps;
   return T5G_OK;
 }
 
@@ -962,7 +983,10 @@ extern "C" int t5g_poll(T5GEngine* e, T5GSlotState* states, void* stream_) {
   T5G_CHECK(e && states, T5G_ERR_INVALID, "bad arguments");
   T5G_CUDA(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize((cudaStream_t)stream_));
-  if (cudaEventQuery(e->ev[4]) == cudaSuccess) cudaEventElapsedTime(&e->timings[3], e->ev[3], e->ev[4]);
+  if (cudaEventQuery(e->ev[4]) == cudaSuccess) {
+    cudaEventElapsedTime(&e->timings[3], e->ev[3], e->ev[4]);
+    if (e->decode_pending) { e->tot_decode_ms += e->timings[3]; e->tot_decode_steps += e->pending_steps; e->decode_pending = false; }
+  }
   cudaGetLastError();
   for (int s = 0; s < e->c.max_slots; ++s) {
     states[s].active = e->h_mirror[s * 8 + 0]; states[s].finished = e->h_mirror[s * 8 + 1];
@@ -1126,6 +1150,13 @@ extern "C" int64_t t5g_kv_bytes_per_token(const T5GEngine* e) {
 extern "C" int t5g_get_timings(T5GEngine* e, float* out) {
   T5G_CHECK(e && out, T5G_ERR_INVALID, "bad arguments");
   for (int i = 0; i < 4; ++i) out[i] = e->timings[i];
+  return T5G_OK;
+}
+
+extern "C" int t5g_get_counters(T5GEngine* e, double* out) {
+  T5G_CHECK(e && out, T5G_ERR_INVALID, "bad arguments");
+  out[0] = e->tot_prefill_ms; out[1] = e->tot_decode_ms; out[2] = (double)e->tot_decode_steps; out[3] = (double)e->tot_prefill_calls;
+  out[4] = (double)e->launches; out[5] = (double)e->last_nodes_per_step; out[6] = 0; out[7] = 0;
   return T5G_OK;
 }
 

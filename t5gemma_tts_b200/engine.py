@@ -33,7 +33,7 @@ class GenerationRequest:
     """One utterance for inference_tts_batch (fields = the per-call arguments of inference_tts)."""
     text_ids: Sequence[int]                       # x[0, :x_lens[0]]
     prompt_ids: Sequence[int]                     # y[0, :, 0] (may be empty), before the special_first shift
-    target_total: int                             # tgt_y_lens[0]
+    target_total: Optional[int]                   # tgt_y_lens[0]; None = tgt_y_lens None (no time budget, models/t5gemma.py:896-933)
     prompt_frames: Optional[int] = None           # kwargs["prompt_frames"], default len(prompt_ids)
     top_k: Union[int, List[int]] = -100
     top_p: float = 1.0
@@ -188,8 +188,12 @@ class T5GemmaVoiceEngine:
     def max_new_tokens_of(self, req: GenerationRequest, n_dec: int) -> int:
         """Upper bound on generated tokens implied by the time-budget stop rule (models/t5gemma.py:1042-1046)."""
         pf = len(req.prompt_ids) if req.prompt_frames is None else req.prompt_frames
-        lim = math.floor(req.target_total - (pf + 1) + int(self.cfg.encodec_sr) * self.cfg.extra_cutoff)
-        n = max(1, lim + 2)
+        if req.target_total is None or req.target_total < 0:
+            # the reference has no bound without a target; the slot's KV capacity is the engine's
+            n = max(1, self.cfg.max_dec_len - n_dec)
+        else:
+            lim = math.floor(req.target_total - (pf + 1) + int(self.cfg.encodec_sr) * self.cfg.extra_cutoff)
+            n = max(1, lim + 2)
         if req.max_new_tokens > 0:
             n = min(n, req.max_new_tokens)
         return n
@@ -215,7 +219,8 @@ class T5GemmaVoiceEngine:
             q.slot, q.n_text, q.n_dec = slot, len(text), len(dec)
             q.text_ids = text.ctypes.data_as(C.POINTER(C.c_int64))
             q.dec_ids = dec.ctypes.data_as(C.POINTER(C.c_int64))
-            q.target_total, q.prompt_frames, q.max_new_tokens = int(r.target_total), pf, int(r.max_new_tokens)
+            q.target_total = -1 if r.target_total is None or r.target_total < 0 else int(r.target_total)
+            q.prompt_frames, q.max_new_tokens = pf, int(r.max_new_tokens)
             sched = None
             if isinstance(r.top_k, (list, tuple)):
                 sched = np.ascontiguousarray(np.asarray(r.top_k, dtype=np.int32))
@@ -337,15 +342,35 @@ class T5GemmaVoiceEngine:
         L.check(self.lib, self.lib.t5g_get_timings(self._h, out))
         return list(out)
 
+    def counters(self) -> Dict[str, float]:
+        """Running totals since creation: CUDA-event ms of all prefill / decode calls, decode steps, launches."""
+        out = (C.c_double * 8)()
+        L.check(self.lib, self.lib.t5g_get_counters(self._h, out))
+        return dict(prefill_ms=out[0], decode_ms=out[1], decode_steps=int(out[2]), prefill_calls=int(out[3]),
+                    launches=int(out[4]), kernels_per_step=int(out[5]))
+
     # ------------------------------------------------------------------ generation
     def generate(self, requests: Sequence[GenerationRequest], chunk_steps: int = 32) -> List[np.ndarray]:
         """Continuous batching over max_slots rows.  Returns the generated ids (incl. final eos) per request."""
+        results: List[Optional[np.ndarray]] = [None] * len(requests)
+        for idx, toks, done in self.generate_stream(requests, chunk_steps=chunk_steps, stream_partial=False):
+            if done:
+                results[idx] = toks
+        return results  # type: ignore
+
+    def generate_stream(self, requests: Sequence[GenerationRequest], chunk_steps: int = 32, stream_partial: bool = True):
+        """Generator form of `generate`: after every `chunk_steps` decode steps yields
+        (request index, new token ids since the last yield as int64, finished flag) for every running request, so a
+        consumer (XCodec2 decode, data/tokenizer.py:117-123) can overlap with generation.  The concatenation of a
+        request's chunks is exactly what `generate` returns for it.  Also accumulates self.stats (row-steps and the KV
+        tokens they read) for the roofline accounting of bench.py."""
         c = self.cfg
         pending = deque(range(len(requests)))
-        results: List[Optional[np.ndarray]] = [None] * len(requests)
         free = deque(range(c.max_slots))
         running: Dict[int, Tuple[int, int]] = {}        # slot -> (request index, max_new)
-        n_done = {}
+        n_done: Dict[int, int] = {}
+        n_sent: Dict[int, int] = {}
+        stats = self.stats = getattr(self, "stats", None) or dict(row_steps=0, kv_token_reads=0, decode_steps=0)
         while pending or running:
             admit, slots, tok_e, tok_d = [], [], 0, 0
             while pending and free:
@@ -362,17 +387,31 @@ class T5GemmaVoiceEngine:
                 for i, s in zip(admit, slots):
                     running[s] = (i, self.max_new_tokens_of(requests[i], len(requests[i].prompt_ids) + 1))
                     n_done[s] = 0
+                    n_sent[s] = 0
             remaining = max(mx - n_done[s] for s, (_, mx) in running.items())
-            self.decode(max(1, min(chunk_steps, remaining)))
+            steps = max(1, min(chunk_steps, remaining))
+            self.decode(steps)
             states = self.poll()
+            stats["decode_steps"] += steps
             for s in list(running.keys()):
+                i = running[s][0]
+                dn = states[s].n_generated - n_done[s]
+                # step j of this chunk attended to (BOS + prompt + tokens so far) self keys and n_text cross keys
+                ctx0 = len(requests[i].prompt_ids) + 1 + n_done[s] + len(requests[i].text_ids)
+                stats["row_steps"] += dn
+                stats["kv_token_reads"] += dn * ctx0 + dn * (dn - 1) // 2
                 n_done[s] = states[s].n_generated
-                if states[s].finished:
-                    results[running[s][0]] = self.read_tokens(s).astype(np.int64)
+                fin = bool(states[s].finished)
+                if fin or stream_partial:
+                    toks = self.read_tokens(s).astype(np.int64)
+                    new = toks[n_sent[s]:] if stream_partial else toks
+                    n_sent[s] = len(toks)
+                    if fin or len(new):
+                        yield i, new, fin
+                if fin:
                     self.release(s)
                     del running[s]
                     free.append(s)
-        return results  # type: ignore
 
     @torch.inference_mode()
     def inference_tts(self, x: torch.Tensor, x_lens: torch.Tensor, y: torch.Tensor, tgt_y_lens: torch.Tensor,
@@ -392,12 +431,21 @@ class T5GemmaVoiceEngine:
         yv = y.transpose(2, 1).contiguous()                 # [B,1,T]
         y_len = yv.shape[-1]
         prompt = yv[0, 0].detach().cpu().numpy()
-        req = GenerationRequest(text_ids=text, prompt_ids=prompt, target_total=int(tgt_y_lens[0].item()),
+        req = GenerationRequest(text_ids=text, prompt_ids=prompt,
+                                target_total=None if tgt_y_lens is None else int(tgt_y_lens[0].item()),
                                 prompt_frames=kwargs.get("prompt_frames", y_len), top_k=top_k, top_p=top_p, min_p=min_p,
                                 temperature=temperature, max_new_tokens=int(kwargs.get("max_new_tokens", 0) or 0),
                                 stop_repetition=int(stop_repetition), silence_tokens=list(silence_tokens or []),
                                 uniforms=kwargs.get("uniforms"))
-        gen = self.generate([req], chunk_steps=int(kwargs.get("chunk_steps", 32)))[0]
+        on_chunk = kwargs.get("on_chunk")            # optional streaming callback: on_chunk(new_ids int64 [n], finished)
+        if on_chunk is None:
+            gen = self.generate([req], chunk_steps=int(kwargs.get("chunk_steps", 32)))[0]
+        else:
+            parts = []
+            for _, new, fin in self.generate_stream([req], chunk_steps=int(kwargs.get("chunk_steps", 32))):
+                parts.append(new)
+                on_chunk(new - self.cfg.n_special if self.cfg.special_first else new, fin)
+            gen = np.concatenate(parts) if parts else np.zeros(0, np.int64)
         if self.cfg.special_first:
             gen = gen - self.cfg.n_special
         gen_t = torch.from_numpy(gen).to(device=x.device, dtype=torch.long)[None, :]       # [1,Tg]

@@ -81,6 +81,7 @@ SYMBOLS = {
     "t5g_weight_bytes_per_step": (C.c_int64, [_P]),
     "t5g_kv_bytes_per_token": (C.c_int64, [_P]),
     "t5g_get_timings": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "t5g_get_counters": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "t5g_last_error": (C.c_char_p, []),
     "t5g_abi_version": (C.c_int, []),
     "t5g_debug_trace": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int)]),

@@ -136,6 +136,131 @@ def test_batched_rows_equal_single_runs():
     assert all(s[-1] == eng1.cfg.stop_token for s in single)
 
 
+def test_continuous_batching_keeps_per_slot_schedules_and_silence_lists():
+    """More requests than rows, every request with its own top_k LIST (models/t5gemma.py:991-994) and silence-token
+    list: admissions happen while other rows are still decoding, and must not disturb their schedules / lists (each
+    slot owns a fixed region of the engine's int pool).  Every row must equal the bs=1 run of that request."""
+    eng1 = engine_for("tinyA_eager")
+    eng3 = engine_for("tinyA_eager", max_slots=3)
+    rng = np.random.default_rng(17)
+    reqs = []
+    for i in range(8):
+        S, Tp = int(rng.integers(4, 30)), int(rng.integers(0, 12))
+        u = torch.rand(400, generator=torch.Generator().manual_seed(300 + i)).cuda()
+        sched = [int(k) for k in rng.integers(1, 40, int(rng.integers(1, 30)))]
+        sil = [int(t) for t in rng.choice(100, int(rng.integers(1, 6)), replace=False)]
+        reqs.append(GenerationRequest(text_ids=rng.integers(2, 500, S), prompt_ids=rng.integers(0, 100, Tp),
+                                      target_total=Tp + int(rng.integers(5, 40)), top_k=sched, top_p=0.95, temperature=1.3,
+                                      uniforms=u, max_new_tokens=int(rng.integers(10, 70)), stop_repetition=1,
+                                      silence_tokens=sil))
+    single = [eng1.generate([r])[0] for r in reqs]
+    batched = eng3.generate(reqs, chunk_steps=5)
+    for a, b in zip(single, batched):
+        assert np.array_equal(a, b)
+    # the schedules matter: the same requests with a constant top_k give different tokens
+    import dataclasses
+    flat = [eng1.generate([dataclasses.replace(r, top_k=1)])[0] for r in reqs]
+    assert any(not np.array_equal(a, b) for a, b in zip(single, flat))
+
+
+def test_streaming_chunks_concatenate_to_the_full_result():
+    """generate_stream / inference_tts(on_chunk=...) hand out token chunks every chunk_steps decode steps (SURVEY 8f.4);
+    their concatenation is exactly the non-streaming result."""
+    eng = engine_for("tinyA_eager", max_slots=3)
+    rng = np.random.default_rng(23)
+    reqs = []
+    for i in range(5):
+        u = torch.rand(400, generator=torch.Generator().manual_seed(500 + i)).cuda()
+        reqs.append(GenerationRequest(text_ids=rng.integers(2, 500, 9 + i), prompt_ids=rng.integers(0, 100, 3 * i),
+                                      target_total=3 * i + 20, top_k=10, temperature=0.9, uniforms=u,
+                                      max_new_tokens=25 + 7 * i))
+    full = eng.generate(reqs, chunk_steps=16)
+    parts = {i: [] for i in range(len(reqs))}
+    n_chunks = {i: 0 for i in range(len(reqs))}
+    finished = set()
+    for i, new, fin in eng.generate_stream(reqs, chunk_steps=6):
+        assert i not in finished
+        parts[i].append(new)
+        n_chunks[i] += 1
+        if fin:
+            finished.add(i)
+    assert finished == set(range(len(reqs)))
+    for i, f in enumerate(full):
+        assert np.array_equal(np.concatenate(parts[i]), f)
+        assert n_chunks[i] >= 4 and max(len(p) for p in parts[i]) <= 6
+    # drop-in call with a streaming callback
+    c = fixtures.load_case("tinyA_eager_prompt")
+    x, y = torch.from_numpy(c["x"]).cuda(), torch.from_numpy(c["y"]).cuda()
+    got = []
+    eng1 = engine_for("tinyA_eager")
+    res, gen = eng1.inference_tts(x, torch.tensor([x.shape[1]]), y, torch.tensor([int(c["tgt"])]), top_k=1,
+                                  prompt_frames=int(c["prompt_frames"]), chunk_steps=50, on_chunk=lambda t, fin: got.append((t, fin)))
+    assert len(got) >= 5 and got[-1][1] and not got[0][1]
+    assert np.array_equal(np.concatenate([t for t, _ in got]), gen[0, 0].cpu().numpy())
+
+
+def test_top_k_list_is_applied_per_step():
+    """top_k as a per-step list: at every step the engine's pick equals the numpy sampler oracle run on the engine's
+    own logits with kk = top_k[min(len-1, cur_num_gen)] and the same uniform draw (bit-exact sampler contract)."""
+    from oracle import sampler_oracle
+    eng = engine_for("tinyA_eager")
+    c = fixtures.load_case("tinyA_eager_prompt")
+    gen = c["gen"][0, 0][:40]
+    sched = [1, 50, 3, 100, 2, 7, 30]
+    u = torch.rand(64, generator=torch.Generator().manual_seed(9))
+    req = _request(c, top_k=sched, top_p=0.9, temperature=0.7, uniforms=u.cuda(), forced_tokens=gen, max_new_tokens=40)
+    eng.prefill([req], [0])
+    npre = c["y"].shape[1] + 1
+    want = []
+    for step in range(39):
+        eng.decode(1)
+        eng.poll()
+        lg = eng.read_logits(0)        # logits as the sampler left them (eos edits applied in place, idempotent)
+        want.append(sampler_oracle.sample_step(lg.copy(), eos=eng.cfg.stop_token, cur_num_gen=step, current_length=npre + step,
+                                               prompt_offset=int(c["prompt_frames"]) + 1, target_total=int(c["tgt"]),
+                                               top_k=sched[min(len(sched) - 1, step)], top_p=0.9, temperature=0.7,
+                                               u=float(u[step]), x_len=c["x"].shape[1]))
+    picks = eng.read_picks(0)[:39]
+    assert np.array_equal(picks, np.asarray(want)), (picks, want)
+    assert len(set(picks.tolist())) > 5                 # not a degenerate greedy run
+    eng.release(0)
+
+
+def test_no_target_fallback_matches_reference():
+    """tgt_y_lens=None (models/t5gemma.py:896-933): est_total = current_length + 2 s lookahead, no time budget; the
+    text guard (3 frames per text token) stops the run exactly where the reference stops.  Teacher-forced logits along
+    the reference sequence, then the drop-in call with tgt_y_lens=None."""
+    from types import SimpleNamespace
+    from t5gemma_tts_b200 import T5GemmaVoiceEngine
+    _, sd, meta = fixtures.load_model_fixture("tinyA_eager")
+    c = fixtures.load_case("tinyA_eager_notarget")
+    meta = dict(meta, text_guard_frames_per_token=int(c["text_guard_frames_per_token"]))
+    eng = T5GemmaVoiceEngine.from_state_dict(SimpleNamespace(**meta), sd, max_slots=1, max_text_len=64, max_dec_len=512,
+                                             max_prefill_tokens=512)
+    gen = c["gen"][0, 0]
+    req = GenerationRequest(text_ids=c["x"][0], prompt_ids=c["y"][0, :, 0], target_total=None,
+                            prompt_frames=int(c["prompt_frames"]), top_k=[1, 1, 1], forced_tokens=gen)
+    eng.prefill([req], [0])
+    eos = eng.cfg.stop_token
+    worst = 0.0
+    for step in range(len(gen)):
+        eng.decode(1)
+        eng.poll()
+        got, ref = eng.read_logits(0), c["step_logits"][step].copy()
+        got[eos] = ref[eos] = 0.0
+        worst = max(worst, rel_err(got, ref))
+    assert worst <= TOL_REF, worst
+    st = eng.poll()[0]
+    assert st.finished == 1 and st.n_generated == len(gen)
+    assert np.array_equal(eng.read_tokens(0), gen)
+    eng.release(0)
+    x, y = torch.from_numpy(c["x"]).cuda(), torch.from_numpy(c["y"]).cuda()
+    res, g = eng.inference_tts(x, torch.tensor([x.shape[1]]).cuda(), y, None, top_k=[1, 1, 1], prompt_frames=int(c["prompt_frames"]))
+    assert g.shape[2] == len(gen) and int(g[0, 0, -1]) == eos
+    assert float((g[0, 0].cpu().numpy() == gen).mean()) >= 0.9
+    eng.close()
+
+
 def test_sliding_window_binds():
     """tiny configs use window 8 / 16 so the window mask is exercised by every decode test; check the
     decode attention really limits the context by comparing against a wide-window engine."""

@@ -137,3 +137,37 @@ def test_silence_repetition_penalty_matches_reference():
                                  logits_hook=lambda lg, step: base.copy())
     assert np.array_equal(gen.numpy(), c["gen"])
     assert gen[0, 0, :10].tolist() == [7, 7, 7, 7, 9, 7, 7, 7, 7, 9]
+
+
+def test_no_target_fallback_and_top_k_list_match_reference():
+    """tgt_y_lens=None (models/t5gemma.py:896-933): est_total from the 2 s lookahead, no time budget, the text guard
+    (3 frames per text token) ends the utterance; top_k given as a list (models/t5gemma.py:991-994)."""
+    cfg, sd, meta = fixtures.load_model_fixture("tinyA_eager")
+    c = fixtures.load_case("tinyA_eager_notarget")
+    cfg.text_guard_frames_per_token = int(c["text_guard_frames_per_token"])
+    from oracle.t5gemma_voice_oracle import Oracle
+    orc = Oracle(cfg, sd)
+    x, y = torch.from_numpy(c["x"]), torch.from_numpy(c["y"])
+    assert int(c["tgt"]) == -1 and int(c["est_total"]) == y.shape[1] + 1 + 100
+    res, gen, logits = orc.inference_tts(x, torch.tensor([x.shape[1]]), y, None, top_k=[1, 1, 1], top_p=1.0,
+                                         temperature=1.0, prompt_frames=int(c["prompt_frames"]), return_logits=True)
+    assert np.array_equal(gen.numpy(), c["gen"])
+    assert gen.shape[-1] == 3 * x.shape[1] + 2          # effective_length > 3 * n_text fires at the 44th token
+    ref, got = c["step_logits"].copy(), logits.numpy()
+    ref[:, orc.cfg.eos] = 0
+    got[:, orc.cfg.eos] = 0
+    assert np.abs(got - ref).max() <= 5e-5
+
+
+@pytest.mark.parametrize("model", ["tinyA_eager", "tinyA_sdpa", "tinyB_eager"])
+def test_fixture_norm_gains_are_distinct_and_nonzero(model):
+    """A swapped / dropped RMSNorm gain must be visible: every norm tensor of every fixture is a different non-zero draw."""
+    _, sd, _ = fixtures.load_model_fixture(model)
+    norms = {k: v.numpy() for k, v in sd.items() if k.endswith("layernorm.weight") or k.endswith(".norm.weight")}
+    assert len(norms) >= 32
+    keys = sorted(norms)
+    for k in keys:
+        assert np.abs(norms[k]).mean() > 0.1, k
+    for i in range(len(keys)):
+        for j in range(i + 1, len(keys)):
+            assert np.abs(norms[keys[i]] - norms[keys[j]]).max() > 0.1, (keys[i], keys[j])

@@ -101,6 +101,8 @@ struct T5GEngine {
   int last_nodes_per_step = 0;
   bool prefill_pdl = true;
   int *d_order_self = nullptr, *d_order_cross = nullptr; bool use_row_order = true;   // batched attention: rows by descending length
+  PersistLayer* d_persist_layers = nullptr; float *d_part_o = nullptr, *d_part_ml = nullptr;   // decode_persist.cu
+  bool use_persist = false; int persist_keys_per_split = 64;
   unsigned long long* d_barrier = nullptr; bool use_pair = true;         // o_proj + cross q_proj in one kernel (gemv_pair.cu)
   int xf_max_keys = 0; bool use_xf = false;                              // capacity (encoder keys over live rows) of that kernel; opt-in (T5G_FUSE_XATTN=1):
                                                                          // measured 11.9 us vs 9.4 us for the two separate kernels (profiles/r1_gemv_design_experiments.md)
@@ -345,6 +347,13 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   { const size_t V8 = ((size_t)e->V + 7) & ~(size_t)7; DM(e->d_samp_u64, (size_t)e->samp_scratch_rows * 2 * V8); DM(e->d_samp_f32, (size_t)e->samp_scratch_rows * 2 * V8); }
   DM(e->d_attn, (size_t)B * QD); DM(e->d_trace, 2 * T5G_TRACE_STRIDE);
   DM(e->d_barrier, 2); T5G_CUDA(cudaMemset(e->d_barrier, 0, 2 * sizeof(unsigned long long)));
+  // single-row engines run all decoder layers of a step in one persistent cooperative kernel (decode_persist.cu)
+  e->use_persist = (B == 1) && cfg->n_dec_layers <= T5G_PERSIST_MAX_LAYERS &&
+                   decode_persist_supported(d, I, e->Hq, e->Hkv, D, cfg->n_dec_layers, e->num_sms);
+  if (const char* s = getenv("T5G_PERSIST")) e->use_persist = e->use_persist && atoi(s) != 0;
+  if (const char* s = getenv("T5G_PERSIST_KEYS")) e->persist_keys_per_split = std::max(1, atoi(s));
+  DM(e->d_persist_layers, cfg->n_dec_layers);
+  DM(e->d_part_o, (size_t)e->Hq * 8 * D); DM(e->d_part_ml, (size_t)e->Hq * 8 * 2);
   DM(e->d_order_self, B); DM(e->d_order_cross, B);
   { std::vector<int> id(B); for (int i = 0; i < B; ++i) id[i] = i;
     T5G_CUDA(cudaMemcpy(e->d_order_self, id.data(), sizeof(int) * B, cudaMemcpyHostToDevice));
@@ -416,6 +425,16 @@ extern "C" int t5g_finalize_weights(T5GEngine* e) {
   T5G_CHECK(e, T5G_ERR_INVALID, "null engine");
   for (const auto& r : e->required)
     T5G_CHECK(e->loaded.count(r), T5G_ERR_STATE, "missing tensor '%s' (%zu of %zu loaded)", r.c_str(), e->loaded.size(), e->required.size());
+  {   // device table of the decoder layers for the persistent kernel
+    std::vector<PersistLayer> tab(e->c.n_dec_layers);
+    for (int l = 0; l < e->c.n_dec_layers; ++l) {
+      const DecLayer& L = e->dec[l];
+      tab[l] = PersistLayer{L.wqkv, L.wo, L.wq_c, L.wo_c, L.wgu, L.wd, L.g_pre_sa, L.g_post_sa, L.g_pre_ca, L.g_post_ca,
+                            L.g_pre_ff, L.g_post_ff, e->c.dec_layer_sliding[l] ? 1 : 0, 0};
+    }
+    T5G_CUDA(cudaSetDevice(e->device));
+    T5G_CUDA(cudaMemcpy(e->d_persist_layers, tab.data(), sizeof(PersistLayer) * tab.size(), cudaMemcpyHostToDevice));
+  }
   e->finalized = true;
   return T5G_OK;
 }
@@ -818,6 +837,51 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
 }
 
 
+// Single-row decode step with the persistent layers kernel: head fc1 -> vocabulary projection -> sampler -> all layers.
+int enqueue_step_persist(T5GEngine* e, cudaStream_t st, int* n_launch) {
+  const T5GConfig& c = e->c;
+  const int d = e->d, D = e->D;
+  const bool pdl = e->use_pdl;
+  int nl = 0, kidx = 0;
+  auto next_trace = [&]() -> unsigned long long* {
+    if (!e->use_trace || kidx >= T5G_TRACE_STRIDE) return nullptr;
+    return e->d_trace + (kidx++);
+  };
+  if (e->use_trace) {
+    CU(cudaMemsetAsync(e->d_trace, 0xFF, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
+    CU(cudaMemsetAsync(e->d_trace + T5G_TRACE_STRIDE, 0, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
+  }
+  float* hfin = e->h_end == 0 ? e->d_hA : e->d_hB;
+  const DecLayer& Llast = e->dec[c.n_dec_layers - 1];
+  GemvArgs z{}; z.eps = c.rms_eps; z.slots = e->d_slots; z.B = 1; z.slot0 = 0;
+  { GemvArgs a = z; a.W = e->head_w1; a.N = d; a.K = d; a.h_in = hfin; a.y = e->d_y; a.g_post = Llast.g_post_ff; a.g_pre = e->g_dec_final;
+    a.h_out = nullptr; a.bias = e->head_b1; a.out = e->d_t1; a.out_stride = d; a.trace = next_trace();
+    CU(launch_gemv(a, P_RES_NORM, E_BIAS_GELU, e->num_sms, st, pdl)); nl++; }
+  { GemvArgs a = z; a.W = e->head_w2; a.N = e->Vpad; a.K = d; a.x = e->d_t1; a.bias = e->head_b2; a.out = e->d_logits; a.out_stride = e->Vpad;
+    a.trace = next_trace();
+    CU(launch_gemv(a, P_PLAIN, E_BIAS, e->num_sms, st, pdl)); nl++; }
+  { SamplerArgs s{}; s.logits = e->d_logits; s.ld = e->Vpad; s.V = e->V; s.slots = e->d_slots; s.topk_sched_pool = e->d_topk_pool;
+    s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
+    s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = 1; s.host_mirror = e->d_mirror;
+    s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
+    s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32;
+    s.trace = next_trace(); s.probe = e->use_trace ? e->d_trace + 1000 : nullptr;
+    CU(launch_sampler(s, st, pdl)); nl++; }
+  { PersistArgs a{}; a.layers = e->d_persist_layers; a.n_layers = c.n_dec_layers;
+    a.d = d; a.I = e->I; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.QD = e->QD; a.KD = e->KD; a.QKV = e->QKV;
+    a.emb = e->audio_emb; a.emb_scale = sqrtf((float)d); a.eps = c.rms_eps; a.pool = e->pool;
+    a.self_bt = e->d_self_bt; a.self_bt_stride = e->max_self_pages; a.cross_bt = e->d_cross_bt; a.cross_bt_stride = e->max_cross_pages;
+    a.slots = e->d_slots; a.rope_cs = e->d_rope; a.window = c.sliding_window; a.scale = c.attn_scale; a.softcap = c.attn_softcap;
+    a.ns_max = std::max(1, std::min(8, e->num_sms / e->Hkv)); a.keys_per_split = e->persist_keys_per_split;
+    a.xbuf_floats = decode_persist_xbuf_floats(d, e->I, e->QD, e->Hq / e->Hkv, D);
+    a.qkv = e->d_qkv; a.qc = e->d_qc; a.act = e->d_act; a.y = e->d_y; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml;
+    a.h_out = hfin; a.barrier = e->d_barrier; a.err = &e->d_slots[0].error;
+    a.probe = e->use_trace ? e->d_trace + 900 : nullptr; a.probe_layer = std::min(5, c.n_dec_layers - 1); a.trace = next_trace();
+    CU(launch_decode_persist(a, e->num_sms, st, pdl)); nl++; }
+  *n_launch = nl;
+  return T5G_OK;
+}
+
 // Batched decode step (B > 4 rows): the projections become skinny tensor-core GEMMs with M = B (weights are
 // streamed once for the whole batch); attention and sampling are the same kernels as the bs=1 path.
 int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
@@ -922,6 +986,7 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
     fuse = keys > 0 && keys <= e->xf_max_keys;
   }
   auto enqueue = [&](cudaStream_t s_, int* nl) -> int {
+    if (e->use_persist) return enqueue_step_persist(e, s_, nl);
     return (e->c.max_slots > 4) ? enqueue_step_batched(e, s_, nl) : enqueue_step(e, s_, nl, fuse);
   };
   if (e->use_graph) {

@@ -75,6 +75,37 @@ cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pd
 bool attn_decode_mma_supported(const AttnDecodeArgs& a);
 cudaError_t launch_attn_decode_mma(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);   // attention_mma.cu
 
+// ---------------- all decoder layers of the single-row decode step in one persistent cooperative kernel (decode_persist.cu) ----------------
+#define T5G_PERSIST_MAX_LAYERS 64
+#define T5G_PERSIST_MAX_HEADS 32
+struct PersistLayer {
+  const bf16 *wqkv, *wo, *wq_c, *wo_c, *wgu, *wd;
+  const float *g_pre_sa, *g_post_sa, *g_pre_ca, *g_post_ca, *g_pre_ff, *g_post_ff;
+  int sliding, pad_;
+};
+struct PersistArgs {
+  const PersistLayer* layers; int n_layers;          // device table
+  int d, I, Hq, Hkv, D, QD, KD, QKV;
+  const bf16* emb; float emb_scale, eps;
+  KVPool pool;
+  const int* self_bt; int self_bt_stride; const int* cross_bt; int cross_bt_stride;   // block tables of row 0
+  const SlotDev* slots;                              // row 0
+  const float* rope_cs;                              // [D]: cos | sin of the row's position (written by the sampler)
+  int window; float scale, softcap;
+  int ns_max, keys_per_split;                        // split-KV: ns = clamp(ceil(keys / keys_per_split), 1, ns_max) CTAs per kv head
+  int xbuf_floats;                                   // shared-memory activation buffer (decode_persist_xbuf_floats)
+  float *qkv, *qc, *act, *y;                         // [QKV], [QD], [I], [d] fp32 exchange buffers (global, L2-resident)
+  float *part_o, *part_ml;                           // attention partials [Hq][8][D], [Hq][8][2]
+  float* h_out;                                      // residual stream after the last layer's cross/MLP adds (pre post_ff)
+  unsigned long long* barrier;                       // ticket counter, zeroed once at engine creation
+  int* err;                                          // device error flags (4 = barrier timeout)
+  unsigned long long* probe; int probe_layer;        // optional [32] phase timestamps of CTA 0 for one layer (T5G_TRACE)
+  unsigned long long* trace;                         // optional kernel begin/end record like the other step kernels
+};
+int decode_persist_xbuf_floats(int d, int I, int QD, int G, int D);
+bool decode_persist_supported(int d, int I, int Hq, int Hkv, int D, int n_layers, int num_sms);
+cudaError_t launch_decode_persist(const PersistArgs& a, int num_sms, cudaStream_t st, bool pdl);
+
 // ---------------- cross-attention fused into its output projection, bs<=4 decode (xattn_fused.cu) ----------------
 struct XAttnOprojArgs {
   KVPool pool; int layer;

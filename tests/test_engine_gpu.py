@@ -187,7 +187,8 @@ def test_streaming_chunks_concatenate_to_the_full_result():
     assert finished == set(range(len(reqs)))
     for i, f in enumerate(full):
         assert np.array_equal(np.concatenate(parts[i]), f)
-        assert n_chunks[i] >= 4 and max(len(p) for p in parts[i]) <= 6
+        assert max(len(p) for p in parts[i]) <= 6 and n_chunks[i] >= -(-len(f) // 6)
+    assert max(n_chunks.values()) >= 4
     # drop-in call with a streaming callback
     c = fixtures.load_case("tinyA_eager_prompt")
     x, y = torch.from_numpy(c["x"]).cuda(), torch.from_numpy(c["y"]).cuda()

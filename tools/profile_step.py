@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import engine_config, make_inputs  # noqa: E402
+from bench import engine_config, make_inputs_bs1 as make_inputs  # noqa: E402
 from t5gemma_tts_b200 import T5GemmaVoiceEngine, GenerationRequest  # noqa: E402
 from t5gemma_tts_b200.random_init import iter_random_state_dict  # noqa: E402
 
@@ -14,7 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--ctx", type=int, default=150)
 a = ap.parse_args()
-cfg = engine_config()
+cfg = engine_config(1)
 eng = T5GemmaVoiceEngine(cfg)
 eng.load_state_dict(iter_random_state_dict(cfg, seed=0, device="cuda"))
 x, xl, y, tgt = make_inputs(1234, cfg)
@@ -46,6 +46,8 @@ if os.environ.get("T5G_TRACE") == "1":
         else:
             per_layer = ["qkv", "sattn", "o+qc", "cattn", "oc", "gu", "down"]     # o_proj + cross q_proj in one kernel
     names = ["head1", "head2", "sampler"] + per_layer * 26
+    if n == 4:
+        names = ["head1", "head2", "sampler", "layers(persistent)"]
     print("step span us", (e_.max() - t0) / 1000.0)
     agg = {}
     for i in range(n):
@@ -57,6 +59,12 @@ if os.environ.get("T5G_TRACE") == "1":
         print(f"{nm:8s} n={c:3d} body avg {d/c:7.2f} us   gap avg {g/c:6.2f} us   total {(d+g):8.1f} us")
     sp = np.zeros(1024, dtype=np.uint64); se = np.zeros(1024, dtype=np.uint64); nn = C.c_int(0)
     L.check(eng.lib, eng.lib.t5g_debug_trace(eng._h, sp.ctypes.data_as(C.POINTER(C.c_uint64)), se.ctypes.data_as(C.POINTER(C.c_uint64)), 1024, C.byref(nn)))
+    if n == 4:   # phase timestamps of CTA 0 for layer 5 of the persistent kernel
+        pp = sp[900:918].astype(np.int64)
+        lab = ["start", "sandwich", "qkv", "bar", "sattn", "bar", "merge+o", "bar", "norm+qc", "bar", "cattn", "bar", "merge+oc", "bar",
+               "norm+gu", "bar", "act+down", "bar"]
+        print("persistent kernel, layer 5, CTA 0 (us):", ", ".join(f"{lab[i]} +{(pp[i] - pp[i - 1]) / 1000.0:.2f}" for i in range(1, 18)),
+              f"| layer {(pp[17] - pp[0]) / 1000.0:.2f}")
     pr = sp[1000:1012].astype(np.int64)
     lab = ["post-wait", "slot staged", "eos edits", "logits pass", "argmax", "lower bound", "candidates", "top-k done", "drawn", "state updated", "exit"]
     print("sampler probes (us after post-wait):", ", ".join(f"{l} {(pr[i] - pr[0]) / 1000.0:.2f}" for i, l in enumerate(lab) if 0 < pr[i] < 2**62), f"| candidates {int(pr[11])}")

@@ -6,11 +6,16 @@
 // 6.47 TB/s) through 8 dependent phases; as separate kernels every phase boundary drained the machine (a streaming
 // kernel fills the register file, so the next kernel's CTAs -- and their weight prefetch -- could only start when it
 // exited) and the step ran at 0.47 of the HBM roofline.  Here
-//   * every warp walks a STATIC stream of weight units (one unit = a 2304-element K-segment of one weight row,
-//     4.6 KB) that covers all six projections of all layers, and keeps a private ring of RING units in shared
-//     memory filled with 16-byte cp.async copies (L2 evict-first).  The ring runs ahead of the math across phase
-//     boundaries: while the CTA waits on a grid barrier or computes attention, the weights of the following phases
-//     keep streaming (147 KB per SM, 21.8 MB chip-wide, in flight or landed);
+//   * every CTA walks a STATIC stream of weight units (one unit = a 2304-element K-segment of one weight row,
+//     4.6 KB) that covers all six projections of all layers.  A dedicated producer warp copies the stream into a
+//     ~36-slot shared-memory ring with 16-byte cp.async (L2 evict-first, completion on per-slot mbarriers) and runs
+//     ahead of the math across phase boundaries: while the consumers wait on a grid barrier or compute attention,
+//     the weights of the following phases keep arriving (~165 KB per SM, 24 MB chip-wide).  The number of units IN
+//     FLIGHT is capped separately (Little: bytes in flight beyond bandwidth x latency only queue in the memory
+//     system and inflate the latency of the phase-critical loads and of the barrier word);
+//   * the 16 consumer warps keep their slice of the activation vector in registers for a whole phase, so a unit
+//     costs one shared-memory read of the weights and nothing else (x re-reads from shared memory capped the first
+//     version at the shared-memory bandwidth);
 //   * phases are separated by a ticket-counter grid barrier (release/acquire on one L2 word, ~1.2 us); the launch is
 //     cooperative, so co-residency of the grid is guaranteed by the driver, not assumed;
 //   * the residual stream h lives in registers, replicated in every CTA; the RMSNorm sandwich (HF:66-74; post-norm of
@@ -26,24 +31,56 @@
 
 namespace {
 
-constexpr int DP_THREADS = 512;
-constexpr int DP_WARPS = DP_THREADS / 32;
-constexpr int DP_RING = 2;                       // units per warp kept in flight / landed
+constexpr int DP_CONS_WARPS = 12;                // consumer warps: prologues, dot products, attention, barriers (512 threads
+                                                 // in all, so every thread may use 128 registers: 72 of them hold x)
+constexpr int DP_PROD_WARPS = 4;                 // producer warps: only issue cp.async weight copies (one warp alone issues
+                                                 // ~15 GB/s: 2.2 TB/s chip-wide, measured)
+constexpr int DP_CONS = DP_CONS_WARPS * 32;
+constexpr int DP_THREADS = DP_CONS + 32 * DP_PROD_WARPS;
 constexpr int DP_UNIT_CHUNKS = 288;              // 16-byte chunks per unit (9 per lane) = 2304 bf16
+constexpr int DP_UPL = DP_UNIT_CHUNKS / 32;
 constexpr int DP_UNIT_BYTES = DP_UNIT_CHUNKS * 16;
-constexpr int DP_NP = 8;                         // residual elements per thread: hidden <= 4096
+constexpr int DP_MAX_SLOTS = 64;
+constexpr int DP_NP = 6;                         // residual elements per thread: hidden <= 2304 (wider models use the multi-kernel step)
 constexpr int DP_BT = 256;                       // block-table entries cached per table
 constexpr int DP_MAX_NS = 8;
+constexpr int DP_PART = 1024;                    // split-K partials per CTA
 constexpr int N_PHASE = 6;                       // weight phases per layer: qkv, o, q_cross, o_cross, gate|up, down
 
-struct PhaseGeo { int n_tasks, rows_per_task, kseg, K; };
+// per-phase constants of this CTA, computed once (integer divisions are ~40 dependent instructions each: none may sit on
+// the per-unit path of a warp that has nothing else to hide latency with)
+struct PhaseGeo {
+  int n_tasks, rows_per_task, kseg, K;
+  int nt_cta;            // tasks of this CTA
+  int ng;                // warp groups (DP_CONS_WARPS / kseg)
+  int units;             // units of this CTA in the phase = nt_cta * rows_per_task * kseg
+  int umod, upar;        // units % n_slots, (units / n_slots) & 1
+};
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint64_t pol) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {     // arrives once this thread's earlier copies have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "DP_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DP_DONE;\n\t"
+      "bra DP_WAIT;\n\t"
+      "DP_DONE:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(DP_CONS) : "memory"); }
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -54,14 +91,15 @@ __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsig
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Grid-wide barrier on a monotonically increasing ticket counter (never reset: every launch adds a multiple of the grid
-// size).  `target` lives in thread 0.  A bounded wait (4 s of %globaltimer) turns a lost CTA into an error flag instead of
-// a hung device.
+// Grid-wide barrier of the consumer threads on a monotonically increasing ticket counter (never reset: every launch adds
+// a multiple of the grid size).  Release/acquire at gpu scope on one word; the data exchanged between phases is read
+// with ld.global.cg, so no L1 invalidation is needed.  `target` lives in thread 0.  A bounded wait (4 s of %globaltimer)
+// turns a lost CTA into an error flag instead of a hung device.
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long& target, int* err) {
-  __syncthreads();
+  cons_sync();
   if (threadIdx.x == 0) {
-    __threadfence();
     if (target == 0) {
+      __threadfence();
       const unsigned long long ticket = atomicAdd(counter, 1ULL);
       target = (ticket / gridDim.x + 1ULL) * gridDim.x;
     } else {
@@ -77,104 +115,142 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
         else if (now - t0 > 4000000000ULL) { if (err) atomicOr(err, 4); break; }
       }
     }
-    __threadfence();
   }
-  __syncthreads();
+  cons_sync();
 }
 
-// x vector in shared memory, split into lo/hi 16-byte halves of every 8-element chunk (conflict-free LDS.128)
-struct XBuf {
-  float4* lo; float4* hi;
-  __device__ __forceinline__ XBuf(float* base, int K) { lo = reinterpret_cast<float4*>(base); hi = lo + (K >> 3); }
-  __device__ __forceinline__ void store(int k, float v) {
-    const int c = k >> 3, j = k & 7;
-    reinterpret_cast<float*>((j < 4 ? lo : hi) + c)[j & 3] = v;
-  }
-};
-
-// position of a warp in its static unit stream
-struct Cursor {
-  int l, p, j, u;
-};
+// sum of four values over the consumer threads
+__device__ __forceinline__ void cons_sum4(float& a, float& b, float& c, float& d, float* red /* >= 128 floats */) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  cons_sync();
+  if (lane == 0) { red[w] = a; red[32 + w] = b; red[64 + w] = c; red[96 + w] = d; }
+  cons_sync();
+  a = warp_sum(lane < DP_CONS_WARPS ? red[lane] : 0.f); b = warp_sum(lane < DP_CONS_WARPS ? red[32 + lane] : 0.f);
+  c = warp_sum(lane < DP_CONS_WARPS ? red[64 + lane] : 0.f); d = warp_sum(lane < DP_CONS_WARPS ? red[96 + lane] : 0.f);
+}
 
 template <int G, int D>
 __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArgs a) {
   constexpr int LPT = Geo<D>::LPT, DPL = Geo<D>::DPL, TPW = Geo<D>::TPW, NV = Geo<D>::NV;
   extern __shared__ __align__(16) unsigned char dp_smem[];
-  unsigned char* ring = dp_smem;                                                   // [DP_WARPS][DP_RING][DP_UNIT_BYTES]
-  float* xbase = reinterpret_cast<float*>(dp_smem + (size_t)DP_WARPS * DP_RING * DP_UNIT_BYTES);   // a.xbuf_floats floats
+  unsigned char* ring = dp_smem;                                                   // [n_slots][DP_UNIT_BYTES]
+  float* xbuf = reinterpret_cast<float*>(dp_smem + (size_t)a.n_slots * DP_UNIT_BYTES);   // a.xbuf_floats floats
   __shared__ PersistLayer lay[T5G_PERSIST_MAX_LAYERS];
   __shared__ PhaseGeo geo[N_PHASE];
-  __shared__ float red[128];
+  __shared__ __align__(8) uint64_t full_bar[DP_MAX_SLOTS], empty_bar[DP_MAX_SLOTS];
+  __shared__ __align__(16) float red[128], part[DP_PART];
   __shared__ int bt_self[DP_BT], bt_cross[DP_BT];
-  __shared__ float cs[D / 2], sn[D / 2];
-  __shared__ float qs[G][D], knew[D], vnew[D];
-  __shared__ float w_ml[DP_WARPS][G][2], w_wt[DP_WARPS][G], c_ml[G][2];
+  __shared__ __align__(16) float cs[D / 2], sn[D / 2];
+  __shared__ __align__(16) float qs[G][D], knew[D], vnew[D];      // read with 16-byte loads
+  __shared__ float w_ml[DP_CONS_WARPS][G][2], w_wt[DP_CONS_WARPS][G], c_ml[G][2];
   __shared__ float m_wt[T5G_PERSIST_MAX_HEADS][DP_MAX_NS];
+  __shared__ float h_park[DP_NP * DP_CONS];            // the residual registers are parked here while a CTA runs attention
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x, n_cta = gridDim.x;
-  const int d = a.d, I = a.I, QD = a.QD, KD = a.KD, QKV = a.QKV;
-  const uint64_t pol = l2_evict_first_policy();
+  const int d = a.d, I = a.I, QD = a.QD, QKV = a.QKV;
+  const int NS = a.n_slots;
 
   // ---- static tables (host-written before the launch: safe to read before the dependency resolves) ----
   for (int i = tid; i < a.n_layers * (int)(sizeof(PersistLayer) / 4); i += DP_THREADS)
     reinterpret_cast<int*>(lay)[i] = reinterpret_cast<const int*>(a.layers)[i];
   if (tid == 0) {
     auto ks = [](int K) { return ((K >> 3) + DP_UNIT_CHUNKS - 1) / DP_UNIT_CHUNKS; };
-    geo[0] = PhaseGeo{QKV, 1, ks(d), d};
-    geo[1] = PhaseGeo{d, 1, ks(QD), QD};
-    geo[2] = PhaseGeo{QD, 1, ks(d), d};
-    geo[3] = PhaseGeo{d, 1, ks(QD), QD};
-    geo[4] = PhaseGeo{I, 2, ks(d), d};
-    geo[5] = PhaseGeo{d, 1, ks(I), I};
+    geo[0] = PhaseGeo{QKV, 1, ks(d), d, 0, 0, 0, 0, 0};
+    geo[1] = PhaseGeo{d, 1, ks(QD), QD, 0, 0, 0, 0, 0};
+    geo[2] = PhaseGeo{QD, 1, ks(d), d, 0, 0, 0, 0, 0};
+    geo[3] = PhaseGeo{d, 1, ks(QD), QD, 0, 0, 0, 0, 0};
+    geo[4] = PhaseGeo{I, 2, ks(d), d, 0, 0, 0, 0, 0};
+    geo[5] = PhaseGeo{d, 1, ks(I), I, 0, 0, 0, 0, 0};
+    for (int p = 0; p < N_PHASE; ++p) {
+      PhaseGeo& g = geo[p];
+      g.nt_cta = g.n_tasks > cta ? (g.n_tasks - cta + n_cta - 1) / n_cta : 0;
+      g.ng = DP_CONS_WARPS / g.kseg;
+      g.units = g.nt_cta * g.rows_per_task * g.kseg;
+      g.umod = g.units % NS; g.upar = (g.units / NS) & 1;
+    }
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 32); mbar_init(&empty_bar[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < DP_BT; i += DP_THREADS) {
     bt_self[i] = i < a.self_bt_stride ? a.self_bt[i] : 0;
     bt_cross[i] = i < a.cross_bt_stride ? a.cross_bt[i] : 0;
   }
   __syncthreads();
-
-  // ---- the warp's unit stream ----
-  auto task_of = [&](int j) { return cta + n_cta * (warp + DP_WARPS * j); };
-  auto normalize = [&](Cursor& c) {          // move to the next existing (layer, phase, task) at or after c
-    while (c.l < a.n_layers) {
-      if (c.p < N_PHASE && task_of(c.j) < geo[c.p].n_tasks) return;
-      c.j = 0; c.u = 0;
-      if (++c.p >= N_PHASE) { c.p = 0; ++c.l; }
-    }
-  };
-  auto advance = [&](Cursor& c) {
-    const PhaseGeo g = geo[c.p];
-    if (++c.u >= g.rows_per_task * g.kseg) { c.u = 0; ++c.j; }
-    normalize(c);
-  };
   auto weight_of = [&](int l, int p) -> const bf16* {
     const PersistLayer& L = lay[l];
     return p == 0 ? L.wqkv : p == 1 ? L.wo : p == 2 ? L.wq_c : p == 3 ? L.wo_c : p == 4 ? L.wgu : L.wd;
   };
-  unsigned char* my_ring = ring + (size_t)warp * DP_RING * DP_UNIT_BYTES;
-  auto issue = [&](const Cursor& c, int slot) {       // one commit group per unit (empty past the end of the stream)
-    if (c.l < a.n_layers) {
-      const PhaseGeo g = geo[c.p];
-      const int row = task_of(c.j) * g.rows_per_task + c.u / g.kseg, seg = c.u % g.kseg;
-      const int nvalid = min(DP_UNIT_CHUNKS, (g.K >> 3) - seg * DP_UNIT_CHUNKS);
-      const bf16* src = weight_of(c.l, c.p) + (size_t)row * g.K + (size_t)seg * DP_UNIT_CHUNKS * 8;
-      unsigned char* dst = my_ring + (size_t)slot * DP_UNIT_BYTES;
-#pragma unroll
-      for (int i = 0; i < DP_UNIT_CHUNKS / 32; ++i) {
-        const int ch = lane + 32 * i;
-        if (ch < nvalid) cp_async16(dst + ch * 16, src + ch * 8, pol);
-      }
-    }
-    cp_async_commit();
-  };
-  Cursor pre{0, 0, 0, 0};
-  normalize(pre);
-  int n_issued = 0, n_consumed = 0;
-#pragma unroll
-  for (int r = 0; r < DP_RING; ++r) { issue(pre, n_issued % DP_RING); ++n_issued; if (pre.l < a.n_layers) advance(pre); }
 
+  // =====================================================================================================================
+  // producer warp: walks the CTA's static unit stream (layer, phase, task, row of the task, K-segment) and copies every
+  // unit into the next ring slot; at most a.max_inflight units are in flight (more would only queue in the memory system
+  // and inflate the latency of the phase-critical loads and barrier words), the rest of the ring holds landed units
+  // =====================================================================================================================
+  const bool dbg_nomath = a.dbg & 1, dbg_nostream = a.dbg & 2;
+  if (warp >= DP_CONS_WARPS) {
+    const int pw = warp - DP_CONS_WARPS;               // units n = pw (mod DP_PROD_WARPS) are this warp's
+    if (dbg_nostream) return;
+    const uint64_t pol = l2_evict_first_policy();
+    const uint32_t ring_u32 = smem_u32(ring);
+    // this warp's units are n = pw, pw + 4, ...; slot / parity of the unit and of the in-flight reference advance without
+    // divisions (n_slots is a multiple of 4, so both stay congruent to pw)
+    int n = 0;
+    bool waited = false;
+    const int F = max(1, a.max_inflight / DP_PROD_WARPS) * DP_PROD_WARPS;   // units between this warp's issue and its own earlier unit
+    int slot = pw, par = 0;                    // of unit n_mine (next unit of this warp)
+    int fslot = pw, fpar = 0, n_mine = pw;     // of unit n_mine - F once n_mine >= F
+#pragma unroll 1
+    for (int l = 0; l < a.n_layers; ++l)
+#pragma unroll 1
+      for (int p = 0; p < N_PHASE; ++p) {
+        const PhaseGeo g = geo[p];
+        const bf16* W = weight_of(l, p);
+        const int nch = g.K >> 3, upt = g.rows_per_task * g.kseg;
+        // unit index inside the phase: q = i * upt + r * kseg + seg ; walk q = first unit of this warp, += 4
+        int q = (pw - n % DP_PROD_WARPS + DP_PROD_WARPS) % DP_PROD_WARPS;
+        int i = q / upt, rem = q - i * upt;
+#pragma unroll 1
+        for (; q < g.units; q += DP_PROD_WARPS) {
+          if (!waited && n_mine >= NS) {
+            // the first ring-full of weights needs nothing from this step; everything later needs a free slot, i.e. a
+            // running consumer, so the slot state (written by this step's sampler) is checked first
+            pdl_wait();
+            waited = true;
+            if (!a.slots[0].active) { cp_async_wait_all(); return; }
+          }
+          const int r = rem / g.kseg, seg = rem - r * g.kseg;      // kseg, upt are tiny: these stay cheap only because
+                                                                   // the producer warps are off the critical path
+          mbar_wait(&empty_bar[slot], par ^ 1);
+          if (n_mine >= F) {
+            mbar_wait(&full_bar[fslot], fpar);
+            fslot += DP_PROD_WARPS; if (fslot >= NS) { fslot -= NS; fpar ^= 1; }
+          }
+          const bf16* src = W + ((size_t)(cta + n_cta * i) * g.rows_per_task + r) * g.K + (size_t)seg * DP_UNIT_CHUNKS * 8;
+          const int nvalid = min(DP_UNIT_CHUNKS, nch - seg * DP_UNIT_CHUNKS);
+          const uint32_t dst = ring_u32 + (uint32_t)slot * DP_UNIT_BYTES;
+#pragma unroll
+          for (int u = 0; u < DP_UPL; ++u) {
+            const int ch = lane + 32 * u;
+            if (ch < nvalid) cp_async16(dst + ch * 16, src + ch * 8, pol);
+          }
+          cp_async_arrive(&full_bar[slot]);
+          slot += DP_PROD_WARPS; if (slot >= NS) { slot -= NS; par ^= 1; }
+          n_mine += DP_PROD_WARPS;
+          rem += DP_PROD_WARPS;
+          while (rem >= upt) { rem -= upt; ++i; }
+        }
+        n += g.units;
+      }
+    if (!waited) pdl_wait();
+    cp_async_wait_all();
+    return;
+  }
+
+  // =====================================================================================================================
+  // consumer warps
+  // =====================================================================================================================
   pdl_wait();
   // dependents (the head of the next step) may only become resident once the sampler of THIS step has completed: they
   // read the slot state before their own griddepcontrol.wait
@@ -182,53 +258,113 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
   trace_begin(a.trace);
   // ---- state written by this step's sampler ----
   const SlotDev& sl = a.slots[0];
-  const int active = sl.active;
-  if (!active) { cp_async_wait<0>(); return; }     // uniform over the grid: no barrier has been touched
-  const int L_self = sl.cur_len, L_cross = sl.n_text, last_token = sl.last_token;
-  for (int i = tid; i < D / 2; i += DP_THREADS) { cs[i] = a.rope_cs[i]; sn[i] = a.rope_cs[D / 2 + i]; }
-  unsigned long long bar_target = 0;
-  unsigned long long* probe = (a.probe && cta == 0 && tid == 0) ? a.probe : nullptr;
-  int probe_i = 0;
-#define DP_PROBE(l_) do { if (probe && (l_) == a.probe_layer && probe_i < 32) probe[probe_i++] = globaltimer_ns(); } while (0)
+  if (!sl.active) return;                              // uniform over the grid: no barrier has been touched
+  // step-invariant scalars are parked in shared memory rather than in (spilled) registers
+  __shared__ int s_Lself, s_Lcross, s_ns_cross;
+  const int last_token = sl.last_token;
+  if (tid == 0) { s_Lself = sl.cur_len; s_Lcross = sl.n_text; }
+  for (int i = tid; i < D / 2; i += DP_CONS) { cs[i] = a.rope_cs[i]; sn[i] = a.rope_cs[D / 2 + i]; }
+  // thread-0-only bookkeeping lives in shared memory: every register counts (a spill is an L2 round trip here)
+  __shared__ unsigned long long bar_target;
+  __shared__ int probe_i, fine_i, cur_layer;
+  if (tid == 0) { bar_target = 0; probe_i = 0; fine_i = 32; cur_layer = 0; }
+  const bool probing = a.probe && cta == 0 && tid == 0;
+#define DP_PROBE(l_) do { if (probing && (l_) == a.probe_layer && probe_i < 32) a.probe[probe_i++] = globaltimer_ns(); } while (0)
+  // finer checkpoints of the same layer: entries [32, 96)
+#define DP_FINE() do { if (probing && cur_layer == a.probe_layer && fine_i < 96) a.probe[fine_i++] = globaltimer_ns(); } while (0)
 
-  // consume all tasks of phase p of layer l that belong to this warp; EPI: 0 store, 1 GeGLU
-  auto run_phase = [&](int l, int p, float* out) {
+  int base_slot = 0, base_par = 0;                     // ring slot / parity of the first unit of the current phase
+  // all tasks of phase p that belong to this warp; the x vector of the phase is in xbuf[0, K)
+  auto run_phase = [&](int p, float* out) {
     const PhaseGeo g = geo[p];
-    const XBuf xs(xbase, g.K);
-    const int upt = g.rows_per_task * g.kseg;
-    for (int j = 0; task_of(j) < g.n_tasks; ++j) {
-      const int task = task_of(j);
-      float acc0 = 0.f, acc1 = 0.f;
-      for (int u = 0; u < upt; ++u) {
-        cp_async_wait<DP_RING - 1>();
-        __syncwarp();
-        const uint4* slot = reinterpret_cast<const uint4*>(my_ring + (size_t)(n_consumed % DP_RING) * DP_UNIT_BYTES);
-        const int seg = u % g.kseg, cbase = seg * DP_UNIT_CHUNKS;
-        const int nvalid = min(DP_UNIT_CHUNKS, (g.K >> 3) - cbase);
-        float acc = 0.f;
+    const int KS = g.kseg, rpt = g.rows_per_task, ng = g.ng;
+    int seg = warp, gi = 0;
+    while (seg >= KS) { seg -= KS; ++gi; }             // warp = gi * KS + seg (KS is 1, 2 or 4 in practice)
+    const int nt = (gi < ng) ? g.nt_cta : 0;           // DP_CONS_WARPS % KS warps sit the phase out
+    const int cbase = seg * DP_UNIT_CHUNKS, nvalid = min(DP_UNIT_CHUNKS, (g.K >> 3) - cbase);
+    // this warp's slice of x stays in registers for the whole phase
+    float xr[DP_UPL][8];
 #pragma unroll
-        for (int i = 0; i < DP_UNIT_CHUNKS / 32; ++i) {
-          const int ch = lane + 32 * i;
-          if (ch < nvalid) {
-            float wf[8];
-            bf16x8_to_f32(slot[ch], wf);
-            const float4 x0 = xs.lo[cbase + ch], x1 = xs.hi[cbase + ch];
-            acc = fmaf(wf[0], x0.x, acc); acc = fmaf(wf[1], x0.y, acc); acc = fmaf(wf[2], x0.z, acc); acc = fmaf(wf[3], x0.w, acc);
-            acc = fmaf(wf[4], x1.x, acc); acc = fmaf(wf[5], x1.y, acc); acc = fmaf(wf[6], x1.z, acc); acc = fmaf(wf[7], x1.w, acc);
+    for (int u = 0; u < DP_UPL; ++u) {
+      const int ch = lane + 32 * u;
+      if (ch < nvalid) {
+        const float4 x0 = *reinterpret_cast<const float4*>(xbuf + (size_t)(cbase + ch) * 8);
+        const float4 x1 = *reinterpret_cast<const float4*>(xbuf + (size_t)(cbase + ch) * 8 + 4);
+        xr[u][0] = x0.x; xr[u][1] = x0.y; xr[u][2] = x0.z; xr[u][3] = x0.w;
+        xr[u][4] = x1.x; xr[u][5] = x1.y; xr[u][6] = x1.z; xr[u][7] = x1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xr[u][j] = 0.f;
+      }
+    }
+    // first unit of this warp: n = base + gi * rpt * KS + seg ; next row of the task: + KS ; next task: + ng * rpt * KS
+    int slot = base_slot + gi * rpt * KS + seg, par = base_par;
+    while (slot >= NS) { slot -= NS; par ^= 1; }
+    const int task_stride = ng * rpt * KS;
+    const bool full_unit = (nvalid == DP_UNIT_CHUNKS);
+    DP_FINE();
+#pragma unroll 1
+    for (int i = gi; i < nt; i += ng) {
+      float acc0 = 0.f, acc1 = 0.f;       // (no indexed local array: with ~200 KB of shared memory carved out, L1 is too
+                                          //  small for local memory and every spill / stack access costs an L2 round trip)
+      int s2 = slot, p2 = par;
+#pragma unroll 1
+      for (int r = 0; r < rpt; ++r) {
+        if (!dbg_nostream) mbar_wait(&full_bar[s2], p2);
+        const uint4* w = reinterpret_cast<const uint4*>(ring + (size_t)s2 * DP_UNIT_BYTES) + lane;
+        float ae = 0.f, ao = 0.f, be = 0.f, bo = 0.f;   // four independent FMA chains
+        if (!dbg_nomath && !dbg_nostream) {
+          if (full_unit) {
+#pragma unroll
+            for (int u = 0; u < DP_UPL; u += 3) {
+              const uint4 w0 = w[32 * u], w1 = w[32 * (u + 1)], w2 = w[32 * (u + 2)];
+              float f0[8], f1[8], f2[8];
+              bf16x8_to_f32(w0, f0); bf16x8_to_f32(w1, f1); bf16x8_to_f32(w2, f2);
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                ae = fmaf(f0[j], xr[u][j], ae); ao = fmaf(f0[j + 1], xr[u][j + 1], ao);
+                be = fmaf(f1[j], xr[u + 1][j], be); bo = fmaf(f1[j + 1], xr[u + 1][j + 1], bo);
+                ae = fmaf(f2[j], xr[u + 2][j], ae); ao = fmaf(f2[j + 1], xr[u + 2][j + 1], ao);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < DP_UPL; ++u) {
+              if (lane + 32 * u < nvalid) {
+                float f0[8];
+                bf16x8_to_f32(w[32 * u], f0);
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) { ae = fmaf(f0[j], xr[u][j], ae); ao = fmaf(f0[j + 1], xr[u][j + 1], ao); }
+              }
+            }
           }
         }
-        if (u < g.kseg) acc0 += acc; else acc1 += acc;
-        __syncwarp();                                  // every lane is done with the slot before it is refilled
-        issue(pre, n_consumed % DP_RING);
-        ++n_issued; ++n_consumed;
-        if (pre.l < a.n_layers) advance(pre);
+        const float acc = (ae + ao) + (be + bo);
+        if (r == 0) acc0 = acc; else acc1 = acc;
+        __syncwarp();
+        if (lane == 0 && !dbg_nostream) mbar_arrive(&empty_bar[s2]);
+        s2 += KS; if (s2 >= NS) { s2 -= NS; p2 ^= 1; }
       }
-      acc0 = warp_sum(acc0);
-      if (g.rows_per_task == 2) {
-        acc1 = warp_sum(acc1);
-        if (lane == 0) out[task] = gelu_tanh_f(acc0) * acc1;
-      } else if (lane == 0) {
-        out[task] = acc0;
+      const float v0 = warp_sum(acc0);
+      float v1 = 0.f;
+      if (rpt == 2) v1 = warp_sum(acc1);
+      if (lane == 0) {
+        const float o = (rpt == 2) ? gelu_tanh_f(v0) * v1 : v0;
+        if (KS == 1) out[cta + n_cta * i] = o;
+        else part[i * KS + seg] = o;
+      }
+      slot += task_stride;
+      while (slot >= NS) { slot -= NS; par ^= 1; }
+    }
+    DP_FINE();
+    base_slot += g.umod; if (base_slot >= NS) { base_slot -= NS; base_par ^= 1; }
+    base_par ^= g.upar;
+    if (KS > 1) {                                      // split-K inside the CTA: combine the K-segments of every row
+      cons_sync();
+      for (int i = tid; i < g.nt_cta; i += DP_CONS) {
+        float v = 0.f;
+        for (int k2 = 0; k2 < KS; ++k2) v += part[i * KS + k2];
+        out[cta + n_cta * i] = v;
       }
     }
   };
@@ -237,16 +373,17 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
   float hreg[DP_NP];
   // h += rmsnorm(y) * g_post (when y) ; xbuf = rmsnorm(h) * g_pre
   auto sandwich = [&](const float* y, const float* g_post, const float* g_pre) {
-    XBuf xs(xbase, d);
     float gp[DP_NP], gq[DP_NP], yv[DP_NP];
 #pragma unroll
     for (int i = 0; i < DP_NP; ++i) {
-      const int k = tid + i * DP_THREADS;
+      const int k = tid + i * DP_CONS;
       gp[i] = (k < d) ? g_pre[k] : 0.f;
       gq[i] = (y && k < d) ? g_post[k] : 0.f;
       yv[i] = (y && k < d) ? __ldcg(y + k) : 0.f;
     }
     float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+    if (yv[0] == 12345.678f) s1 = 1.f;                 // (keeps the probe below after the loads have returned)
+    DP_FINE();
 #pragma unroll
     for (int i = 0; i < DP_NP; ++i) {
       const float yg = yv[i] * gq[i];
@@ -254,7 +391,8 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
       s3 = fmaf(hreg[i], yg, s3); s4 = fmaf(yg, yg, s4);
       yv[i] = yg;
     }
-    block_sum4(s1, s2, s3, s4, red);
+    cons_sum4(s1, s2, s3, s4, red);
+    DP_FINE();
     float ss = s2;
     if (y) {
       const float ry = rsqrtf(s1 / (float)d + a.eps);
@@ -265,10 +403,10 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
     const float rinv = rsqrtf(ss / (float)d + a.eps);
 #pragma unroll
     for (int i = 0; i < DP_NP; ++i) {
-      const int k = tid + i * DP_THREADS;
-      if (k < d) xs.store(k, hreg[i] * rinv * gp[i]);
+      const int k = tid + i * DP_CONS;
+      if (k < d) xbuf[k] = hreg[i] * rinv * gp[i];
     }
-    __syncthreads();
+    cons_sync();
   };
 
   // split-KV attention partial of (kv head hk, split) on this CTA; result to part_o / part_ml
@@ -277,7 +415,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
     const int* bt = is_cross ? bt_cross : bt_self;
     const int* bt_g = is_cross ? a.cross_bt : a.self_bt;
     const int PT = a.pool.page_tokens;
-    const int Lk = is_cross ? L_cross : L_self;
+    const int Lk = is_cross ? s_Lcross : s_Lself;
     const int window = (!is_cross && lay[l].sliding) ? a.window : 0;
     const int lo = window > 0 ? max(0, Lk - window) : 0;
     int chunk = (Lk - lo + ns - 1) / ns;
@@ -286,74 +424,117 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
     const bool has_new = (!is_cross) && (t_end == Lk) && (t_end > t_begin);
     const int grp = lane / LPT, l8 = lane % LPT;
     auto page_of = [&](int t) -> int { const int pi = t / PT; return pi < DP_BT ? bt[pi] : bt_g[pi]; };
+    // K/V rows of earlier tokens are immutable: this warp's first tile is requested before anything that depends on
+    // the producer phase, and every later tile one iteration ahead of its use
+    uint4 ku[NV], vu[NV];
+    auto load_tile = [&](int t0, uint4* kd, uint4* vd) {
+      const int t = t0 + grp;
+      if (t < t_end && !(has_new && t == Lk - 1)) {
+        const int page = page_of(t), off = t % PT;
+        const bf16* kp = a.pool.ptr(l, 0, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
+        const bf16* vp = a.pool.ptr(l, 1, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { kd[i] = *reinterpret_cast<const uint4*>(kp + i * 8); vd[i] = *reinterpret_cast<const uint4*>(vp + i * 8); }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { kd[i] = make_uint4(0, 0, 0, 0); vd[i] = make_uint4(0, 0, 0, 0); }
+      }
+    };
+    load_tile(t_begin + warp * TPW, ku, vu);
     // producer outputs: raw q of the group's heads and the new k/v
-    for (int i = tid; i < G * D; i += DP_THREADS) qs[i / D][i % D] = __ldcg(q + (size_t)(hk * G) * D + i);
+    for (int i = tid; i < G * D; i += DP_CONS) qs[i / D][i % D] = __ldcg(q + (size_t)(hk * G) * D + i);
     if (has_new)
-      for (int j = tid; j < D; j += DP_THREADS) {
+      for (int j = tid; j < D; j += DP_CONS) {
         knew[j] = __ldcg(kv_new + (size_t)hk * D + j);
         vnew[j] = __bfloat162float(__float2bfloat16(__ldcg(kv_new + (size_t)(a.Hkv + hk) * D + j)));
       }
-    __syncthreads();
-    for (int i = tid; i < G * D / 2; i += DP_THREADS) {           // PM-RoPE, half-split pairs (j, j + D/2)
+    cons_sync();
+    for (int i = tid; i < G * D / 2; i += DP_CONS) {             // PM-RoPE, half-split pairs (j, j + D/2)
       const int g = i / (D / 2), j = i - g * (D / 2);
       const float x1 = qs[g][j], x2 = qs[g][j + D / 2];
       qs[g][j] = x1 * cs[j] - x2 * sn[j];
       qs[g][j + D / 2] = x2 * cs[j] + x1 * sn[j];
     }
     if (has_new)
-      for (int j = tid; j < D / 2; j += DP_THREADS) {
+      for (int j = tid; j < D / 2; j += DP_CONS) {
         const float x1 = knew[j], x2 = knew[j + D / 2];
         knew[j] = __bfloat162float(__float2bfloat16(x1 * cs[j] - x2 * sn[j]));
         knew[j + D / 2] = __bfloat162float(__float2bfloat16(x2 * cs[j] + x1 * sn[j]));
       }
-    __syncthreads();
+    cons_sync();
     if (has_new) {                                                  // append (K post-RoPE), visible to later steps
       const int t = Lk - 1, page = page_of(t), off = t % PT;
       bf16* kd = a.pool.ptr(l, 0, page) + ((size_t)hk * PT + off) * D;
       bf16* vd = a.pool.ptr(l, 1, page) + ((size_t)hk * PT + off) * D;
-      for (int j = tid; j < D; j += DP_THREADS) { kd[j] = __float2bfloat16(knew[j]); vd[j] = __float2bfloat16(vnew[j]); }
+      for (int j = tid; j < D; j += DP_CONS) { kd[j] = __float2bfloat16(knew[j]); vd[j] = __float2bfloat16(vnew[j]); }
     }
-    float qreg[G][DPL];
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-      for (int i = 0; i < DPL; ++i) qreg[g][i] = qs[g][l8 * DPL + i];
     GroupState<G, DPL> st;
     st.init();
-    for (int t0 = t_begin + warp * TPW; t0 < t_end; t0 += 2 * DP_WARPS * TPW) {
-      uint4 ku[2][NV], vu[2][NV];
+    const float inv_softcap = a.softcap > 0.f ? 1.f / a.softcap : 0.f;
+#pragma unroll 1
+    for (int t0 = t_begin + warp * TPW; t0 < t_end; t0 += DP_CONS_WARPS * TPW) {
+      const int t = t0 + grp;
+      const bool valid = t < t_end, fresh = valid && has_new && t == Lk - 1;
+      uint4 kn[NV], vn[NV];
+      load_tile(t0 + DP_CONS_WARPS * TPW, kn, vn);       // next tile in flight while this one is consumed
+      // scores of the group's G query heads (q stays in shared memory: registers are the scarce resource here)
+      float dot[G];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int t = t0 + u * DP_WARPS * TPW + grp;
-        if (t < t_end && !(has_new && t == Lk - 1)) {
-          const int page = page_of(t), off = t % PT;
-          const bf16* kp = a.pool.ptr(l, 0, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
-          const bf16* vp = a.pool.ptr(l, 1, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
+      for (int g = 0; g < G; ++g) dot[g] = 0.f;
 #pragma unroll
-          for (int i = 0; i < NV; ++i) { ku[u][i] = *reinterpret_cast<const uint4*>(kp + i * 8); vu[u][i] = *reinterpret_cast<const uint4*>(vp + i * 8); }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (t0 + u * DP_WARPS * TPW >= t_end) break;               // warp-uniform
-        const int t = t0 + u * DP_WARPS * TPW + grp;
-        const bool valid = t < t_end, fresh = valid && has_new && t == Lk - 1;
-        float kf[DPL], vf[DPL];
+      for (int i = 0; i < NV; ++i) {
+        float kf[8];
         if (fresh) {
 #pragma unroll
-          for (int i = 0; i < DPL; ++i) { kf[i] = knew[l8 * DPL + i]; vf[i] = vnew[l8 * DPL + i]; }
-        } else if (valid) {
-#pragma unroll
-          for (int i = 0; i < NV; ++i) { bf16x8_to_f32(ku[u][i], kf + i * 8); bf16x8_to_f32(vu[u][i], vf + i * 8); }
+          for (int j = 0; j < 8; ++j) kf[j] = knew[l8 * DPL + i * 8 + j];
         } else {
-#pragma unroll
-          for (int i = 0; i < DPL; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
+          bf16x8_to_f32(ku[i], kf);
         }
-        group_update<G, D>(st, qreg, kf, vf, a.scale, a.softcap, valid);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float4 q0 = *reinterpret_cast<const float4*>(&qs[g][l8 * DPL + i * 8]);
+          const float4 q1 = *reinterpret_cast<const float4*>(&qs[g][l8 * DPL + i * 8 + 4]);
+          dot[g] = fmaf(q0.x, kf[0], dot[g]); dot[g] = fmaf(q0.y, kf[1], dot[g]); dot[g] = fmaf(q0.z, kf[2], dot[g]); dot[g] = fmaf(q0.w, kf[3], dot[g]);
+          dot[g] = fmaf(q1.x, kf[4], dot[g]); dot[g] = fmaf(q1.y, kf[5], dot[g]); dot[g] = fmaf(q1.z, kf[6], dot[g]); dot[g] = fmaf(q1.w, kf[7], dot[g]);
+        }
       }
+      float pw[G], corr[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float dd = dot[g];
+#pragma unroll
+        for (int o = LPT >> 1; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+        float sc = dd * a.scale;
+        if (a.softcap > 0.f) {                   // softcap*tanh(s/softcap), tanh(x) = 1 - 2/(exp(2x)+1)
+          const float e2 = __expf(2.f * sc * inv_softcap);
+          sc = a.softcap * (1.f - __fdividef(2.f, e2 + 1.f));
+        }
+        if (!valid) sc = -INFINITY;
+        const float mn = fmaxf(st.m[g], sc);
+        corr[g] = (st.m[g] == -INFINITY) ? 0.f : __expf(st.m[g] - mn);
+        pw[g] = valid ? __expf(sc - mn) : 0.f;
+        st.l[g] = st.l[g] * corr[g] + pw[g];
+        st.m[g] = mn;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float vf[8];
+        if (fresh) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vf[j] = vnew[l8 * DPL + i * 8 + j];
+        } else {
+          bf16x8_to_f32(vu[i], vf);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) st.acc[g][i * 8 + j] = fmaf(pw[g], vf[j], st.acc[g][i * 8 + j] * corr[g]);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { ku[i] = kn[i]; vu[i] = vn[i]; }
     }
     warp_merge<G, D>(st);
-    float* w_o = xbase;                                             // [DP_WARPS][G][D] (the x buffer is dead here)
+    float* w_o = xbuf;                                              // [DP_CONS_WARPS][G][D] (the x buffer is dead here)
     if (grp == 0) {
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -362,14 +543,14 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
         for (int i = 0; i < DPL; ++i) w_o[((size_t)warp * G + g) * D + l8 * DPL + i] = st.acc[g][i];
       }
     }
-    __syncthreads();
+    cons_sync();
     if (tid < G) {
       float M = -INFINITY;
 #pragma unroll
-      for (int w = 0; w < DP_WARPS; ++w) M = fmaxf(M, w_ml[w][tid][0]);
+      for (int w = 0; w < DP_CONS_WARPS; ++w) M = fmaxf(M, w_ml[w][tid][0]);
       float den = 0.f;
 #pragma unroll
-      for (int w = 0; w < DP_WARPS; ++w) {
+      for (int w = 0; w < DP_CONS_WARPS; ++w) {
         const float m = w_ml[w][tid][0];
         const float wt = (m == -INFINITY) ? 0.f : __expf(m - M);
         den = fmaf(wt, w_ml[w][tid][1], den);
@@ -377,12 +558,12 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
       }
       c_ml[tid][0] = M; c_ml[tid][1] = den;
     }
-    __syncthreads();
-    for (int i = tid; i < G * D; i += DP_THREADS) {
+    cons_sync();
+    for (int i = tid; i < G * D; i += DP_CONS) {
       const int g = i / D, dd = i - g * D;
       float num = 0.f;
 #pragma unroll
-      for (int w = 0; w < DP_WARPS; ++w) num = fmaf(w_wt[w][g], w_o[((size_t)w * G + g) * D + dd], num);
+      for (int w = 0; w < DP_CONS_WARPS; ++w) num = fmaf(w_wt[w][g], w_o[((size_t)w * G + g) * D + dd], num);
       a.part_o[((size_t)(hk * G + g) * DP_MAX_NS + split) * D + dd] = num;
     }
     if (tid < G) {
@@ -393,112 +574,118 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
 
   // xbuf[0..QD) = merged attention output (every CTA, redundantly)
   auto merge_partials = [&](int ns) {
-    XBuf xs(xbase, QD);
-    if (tid < a.Hq) {
-      float M = -INFINITY, m[DP_MAX_NS], lv[DP_MAX_NS];
+    // one round trip: the partial outputs are requested first, then Hq * 8 threads each derive ONE normalised merge
+    // weight (own loads of the head's (m, l) pairs, one exp) while those are in flight
+    constexpr int MP = (2048 + DP_CONS - 1) / DP_CONS;
+    float v[MP][DP_MAX_NS];
+#pragma unroll
+    for (int e = 0; e < MP; ++e) {
+      const int i = tid + e * DP_CONS;
+      const int h = i / D, dd = i - h * D;
+#pragma unroll
+      for (int s = 0; s < DP_MAX_NS; ++s) v[e][s] = (i < QD && s < ns) ? __ldcg(a.part_o + ((size_t)h * DP_MAX_NS + s) * D + dd) : 0.f;
+    }
+    if (tid < a.Hq * DP_MAX_NS) {
+      const int h = tid / DP_MAX_NS, s0 = tid % DP_MAX_NS;
+      float m[DP_MAX_NS], lv[DP_MAX_NS], M = -INFINITY;
 #pragma unroll
       for (int s = 0; s < DP_MAX_NS; ++s) {
-        m[s] = s < ns ? __ldcg(a.part_ml + (tid * DP_MAX_NS + s) * 2) : -INFINITY;
-        lv[s] = s < ns ? __ldcg(a.part_ml + (tid * DP_MAX_NS + s) * 2 + 1) : 0.f;
+        m[s] = s < ns ? __ldcg(a.part_ml + (h * DP_MAX_NS + s) * 2) : -INFINITY;
+        lv[s] = s < ns ? __ldcg(a.part_ml + (h * DP_MAX_NS + s) * 2 + 1) : 0.f;
         M = fmaxf(M, m[s]);
       }
-      float den = 0.f, wt[DP_MAX_NS];
+      float den = 0.f, mine = 0.f;
 #pragma unroll
-      for (int s = 0; s < DP_MAX_NS; ++s) { wt[s] = (m[s] == -INFINITY) ? 0.f : __expf(m[s] - M); den = fmaf(wt[s], lv[s], den); }
-      const float inv = den > 0.f ? 1.f / den : 0.f;
-#pragma unroll
-      for (int s = 0; s < DP_MAX_NS; ++s) m_wt[tid][s] = wt[s] * inv;
+      for (int s = 0; s < DP_MAX_NS; ++s) {
+        const float wt = (m[s] == -INFINITY) ? 0.f : __expf(m[s] - M);
+        den = fmaf(wt, lv[s], den);
+        if (s == s0) mine = wt;
+      }
+      m_wt[h][s0] = den > 0.f ? mine / den : 0.f;
     }
-    __syncthreads();
-    for (int i = tid; i < QD; i += DP_THREADS) {
+    cons_sync();
+#pragma unroll
+    for (int e = 0; e < MP; ++e) {
+      const int i = tid + e * DP_CONS;
+      if (i < QD) {
+        const int h = i / D;
+        float o = 0.f;
+#pragma unroll
+        for (int s = 0; s < DP_MAX_NS; ++s) o = fmaf(m_wt[h][s], v[e][s], o);
+        xbuf[i] = o;
+      }
+    }
+    for (int i = tid + MP * DP_CONS; i < QD; i += DP_CONS) {      // wider models than MP elements per thread
       const int h = i / D, dd = i - h * D;
-      float v[DP_MAX_NS];
-#pragma unroll
-      for (int s = 0; s < DP_MAX_NS; ++s) v[s] = s < ns ? __ldcg(a.part_o + ((size_t)h * DP_MAX_NS + s) * D + dd) : 0.f;
       float o = 0.f;
-#pragma unroll
-      for (int s = 0; s < DP_MAX_NS; ++s) o = fmaf(m_wt[h][s], v[s], o);
-      xs.store(i, o);
+      for (int s = 0; s < ns; ++s) o = fmaf(m_wt[h][s], __ldcg(a.part_o + ((size_t)h * DP_MAX_NS + s) * D + dd), o);
+      xbuf[i] = o;
     }
-    __syncthreads();
+    cons_sync();
   };
 
   auto n_splits = [&](int keys, int ns_max) { return max(1, min(ns_max, (keys + a.keys_per_split - 1) / a.keys_per_split)); };
-  const int ns_cross = n_splits(L_cross, a.ns_max);
+  cons_sync();
+  if (tid == 0) s_ns_cross = n_splits(s_Lcross, a.ns_max);
 
   // ---- layer 0 input: audio embedding * sqrt(d) (models/t5gemma.py:1083; HF:769) ----
 #pragma unroll
   for (int i = 0; i < DP_NP; ++i) {
-    const int k = tid + i * DP_THREADS;
+    const int k = tid + i * DP_CONS;
     hreg[i] = (k < d) ? __bfloat162float(a.emb[(size_t)last_token * d + k]) * a.emb_scale : 0.f;
   }
 
+  // One layer = 8 stages separated by grid barriers.  The stage loop has ONE call site per building block (prologue kinds,
+  // attention, projection): the first version inlined them per stage and grew to 270 KB of SASS, which made the whole
+  // kernel instruction-fetch bound (69 us per layer with the weight stream switched off).
+#pragma unroll 1
   for (int l = 0; l < a.n_layers; ++l) {
-    const PersistLayer& Ly = lay[l];
-    DP_PROBE(l);
-    // P0: qkv = Wqkv . pre_sa(h + post_ff(y of the previous layer))
-    if (l == 0) sandwich(nullptr, nullptr, Ly.g_pre_sa);
-    else sandwich(a.y, lay[l - 1].g_post_ff, Ly.g_pre_sa);
-    DP_PROBE(l);
-    run_phase(l, 0, a.qkv);
-    DP_PROBE(l);
-    grid_barrier(a.barrier, bar_target, a.err);
-    DP_PROBE(l);
-    // P1: self-attention partials
-    const int win = Ly.sliding ? a.window : 0;
-    const int keys_self = win > 0 ? min(L_self, win) : L_self;
-    const int ns_self = n_splits(keys_self, a.ns_max);
-    if (cta < a.Hkv * ns_self) attention(l, false, a.qkv, a.qkv + QD, ns_self);
-    DP_PROBE(l);
-    grid_barrier(a.barrier, bar_target, a.err);
-    DP_PROBE(l);
-    // P2: y = Wo . attn
-    merge_partials(ns_self);
-    run_phase(l, 1, a.y);
-    DP_PROBE(l);
-    grid_barrier(a.barrier, bar_target, a.err);
-    DP_PROBE(l);
-    // P3: qc = Wq_c . pre_ca(h + post_sa(y))
-    sandwich(a.y, Ly.g_post_sa, Ly.g_pre_ca);
-    run_phase(l, 2, a.qc);
-    DP_PROBE(l);
-    grid_barrier(a.barrier, bar_target, a.err);
-    DP_PROBE(l);
-    // P4: cross-attention partials over the encoder pages
-    if (cta < a.Hkv * ns_cross) attention(l, true, a.qc, nullptr, ns_cross);
-    DP_PROBE(l);
-    grid_barrier(a.barrier, bar_target, a.err);
-    DP_PROBE(l);
-    // P5: y = Wo_c . attn
-    merge_partials(ns_cross);
-    run_phase(l, 3, a.y);
-    DP_PROBE(l);
-    grid_barrier(a.barrier, bar_target, a.err);
-    DP_PROBE(l);
-    // P6: act = GeGLU(Wgu . pre_ff(h + post_ca(y)))
-    sandwich(a.y, Ly.g_post_ca, Ly.g_pre_ff);
-    run_phase(l, 4, a.act);
-    DP_PROBE(l);
-    grid_barrier(a.barrier, bar_target, a.err);
-    DP_PROBE(l);
-    // P7: y = Wd . act
-    {
-      XBuf xs(xbase, I);
-      const float4* av = reinterpret_cast<const float4*>(a.act);
-      for (int i = tid; i < (I >> 2); i += DP_THREADS) ((i & 1) ? xs.hi : xs.lo)[i >> 1] = __ldcg(av + i);
-      __syncthreads();
+    if (tid == 0) cur_layer = l;
+    const int win = lay[l].sliding ? a.window : 0;
+    const int ns_self = n_splits(win > 0 ? min(s_Lself, win) : s_Lself, a.ns_max);
+#pragma unroll 1
+    for (int stage = 0; stage < 8; ++stage) {
+      DP_PROBE(l);
+      const PersistLayer& Ly = lay[l];
+      const bool is_attn = (stage == 1 || stage == 4);
+      if (stage == 0 || stage == 3 || stage == 6) {
+        // qkv / cross q / gate|up consume pre_norm(h + post_norm(previous sub-layer output))
+        const float* y = (stage == 0 && l == 0) ? nullptr : a.y;
+        const float* g_post = stage == 0 ? (l > 0 ? lay[l - 1].g_post_ff : nullptr) : stage == 3 ? Ly.g_post_sa : Ly.g_post_ca;
+        const float* g_pre = stage == 0 ? Ly.g_pre_sa : stage == 3 ? Ly.g_pre_ca : Ly.g_pre_ff;
+        sandwich(y, g_post, g_pre);
+      } else if (stage == 2 || stage == 5) {
+        merge_partials(stage == 2 ? ns_self : s_ns_cross);            // o projections consume the merged attention output
+      } else if (stage == 7) {
+        const float4* av = reinterpret_cast<const float4*>(a.act);   // down projection consumes the GeGLU activations
+        float4* xv = reinterpret_cast<float4*>(xbuf);
+        for (int i = tid; i < (I >> 2); i += DP_CONS) xv[i] = __ldcg(av + i);
+        cons_sync();
+      }
+      if (is_attn) {
+        const bool cross = stage == 4;
+        const int ns = cross ? s_ns_cross : ns_self;
+        if (cta < a.Hkv * ns) {
+#pragma unroll
+          for (int i = 0; i < DP_NP; ++i) h_park[i * DP_CONS + tid] = hreg[i];
+          attention(l, cross, cross ? a.qc : a.qkv, cross ? nullptr : a.qkv + QD, ns);
+#pragma unroll
+          for (int i = 0; i < DP_NP; ++i) hreg[i] = h_park[i * DP_CONS + tid];
+        }
+      } else {
+        const int p = stage == 0 ? 0 : stage == 2 ? 1 : stage == 3 ? 2 : stage == 5 ? 3 : stage == 6 ? 4 : 5;
+        float* out = stage == 0 ? a.qkv : stage == 3 ? a.qc : stage == 6 ? a.act : a.y;
+        run_phase(p, out);
+      }
+      DP_PROBE(l);
+      if (!(stage == 7 && l + 1 == a.n_layers)) grid_barrier(a.barrier, bar_target, a.err);
     }
-    run_phase(l, 5, a.y);
-    DP_PROBE(l);
-    if (l + 1 < a.n_layers) grid_barrier(a.barrier, bar_target, a.err);
-    DP_PROBE(l);
   }
-  cp_async_wait<0>();
   // the head kernel applies post_ff of the last layer: hand it h (CTA 0) and y (already in a.y)
   if (cta == 0) {
 #pragma unroll
     for (int i = 0; i < DP_NP; ++i) {
-      const int k = tid + i * DP_THREADS;
+      const int k = tid + i * DP_CONS;
       if (k < d) a.h_out[k] = hreg[i];
     }
   }
@@ -526,33 +713,45 @@ cudaError_t launch_gd(const PersistArgs& a, int num_sms, cudaStream_t st, bool p
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-size_t smem_bytes(const PersistArgs& a) {
-  return (size_t)DP_WARPS * DP_RING * DP_UNIT_BYTES + (size_t)a.xbuf_floats * sizeof(float);
-}
-
 }  // namespace
 
 int decode_persist_xbuf_floats(int d, int I, int QD, int G, int D) {
   int m = d > I ? d : I;
   if (QD > m) m = QD;
-  const int attn = DP_WARPS * G * D;          // per-warp attention partials alias the x buffer
+  const int attn = DP_CONS_WARPS * G * D;     // per-warp attention partials alias the x buffer
   if (attn > m) m = attn;
   return (m + 7) & ~7;
+}
+
+// ring slots that fit next to the x buffer and ~30 KB of static shared memory
+int decode_persist_slots(int xbuf_floats) {
+  const long budget = 227L * 1024 - 32L * 1024 - (long)xbuf_floats * 4;
+  long n = budget / DP_UNIT_BYTES;
+  if (n > DP_MAX_SLOTS) n = DP_MAX_SLOTS;
+  return (int)(n / DP_PROD_WARPS * DP_PROD_WARPS);
 }
 
 bool decode_persist_supported(int d, int I, int Hq, int Hkv, int D, int n_layers, int num_sms) {
   if (Hkv <= 0 || Hq % Hkv) return false;
   const int G = Hq / Hkv;
   if (G != 2 || !(D == 16 || D == 32 || D == 64 || D == 128 || D == 256)) return false;
-  if (d % 8 || I % 8 || d > DP_THREADS * DP_NP) return false;
+  if (d % 8 || I % 8 || d > DP_CONS * DP_NP) return false;
   if (n_layers > T5G_PERSIST_MAX_LAYERS || Hq > T5G_PERSIST_MAX_HEADS || Hkv > num_sms) return false;
-  const size_t smem = (size_t)DP_WARPS * DP_RING * DP_UNIT_BYTES + (size_t)decode_persist_xbuf_floats(d, I, Hq * D, G, D) * 4;
-  return smem + 16 * 1024 <= 227 * 1024;
+  auto ks = [](int K) { return ((K >> 3) + DP_UNIT_CHUNKS - 1) / DP_UNIT_CHUNKS; };
+  const int Ks[3] = {d, Hq * D, I}, Ns[3] = {I > Hq * D + 2 * Hkv * D ? I : Hq * D + 2 * Hkv * D, d, d};
+  for (int i = 0; i < 3; ++i) {
+    const int k = ks(Ks[i]);
+    if (k > DP_CONS_WARPS) return false;                                         // K-segments are dealt to warp groups
+    if (k > 1 && ((Ns[i] + num_sms - 1) / num_sms) * k > DP_PART) return false;
+  }
+  return decode_persist_slots(decode_persist_xbuf_floats(d, I, Hq * D, G, D)) >= 8;
 }
 
 cudaError_t launch_decode_persist(const PersistArgs& a, int num_sms, cudaStream_t st, bool pdl) {
   const int G = a.Hq / a.Hkv;
-  const size_t smem = smem_bytes(a);
+  if (a.n_slots < 2 * DP_PROD_WARPS || a.n_slots > DP_MAX_SLOTS || a.n_slots % DP_PROD_WARPS || a.max_inflight < 1)
+    return cudaErrorInvalidValue;
+  const size_t smem = (size_t)a.n_slots * DP_UNIT_BYTES + (size_t)a.xbuf_floats * sizeof(float);
   if (G == 2) {
     switch (a.D) {
       case 16: return launch_gd<2, 16>(a, num_sms, st, pdl, smem);

@@ -102,7 +102,7 @@ struct T5GEngine {
   bool prefill_pdl = true;
   int *d_order_self = nullptr, *d_order_cross = nullptr; bool use_row_order = true;   // batched attention: rows by descending length
   PersistLayer* d_persist_layers = nullptr; float *d_part_o = nullptr, *d_part_ml = nullptr;   // decode_persist.cu
-  bool use_persist = false; int persist_keys_per_split = 64;
+  bool use_persist = false; int persist_keys_per_split = 24, persist_slots = 0, persist_inflight = 12;
   unsigned long long* d_barrier = nullptr; bool use_pair = true;         // o_proj + cross q_proj in one kernel (gemv_pair.cu)
   int xf_max_keys = 0; bool use_xf = false;                              // capacity (encoder keys over live rows) of that kernel; opt-in (T5G_FUSE_XATTN=1):
                                                                          // measured 11.9 us vs 9.4 us for the two separate kernels (profiles/r1_gemv_design_experiments.md)
@@ -352,6 +352,8 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
                    decode_persist_supported(d, I, e->Hq, e->Hkv, D, cfg->n_dec_layers, e->num_sms);
   if (const char* s = getenv("T5G_PERSIST")) e->use_persist = e->use_persist && atoi(s) != 0;
   if (const char* s = getenv("T5G_PERSIST_KEYS")) e->persist_keys_per_split = std::max(1, atoi(s));
+  if (const char* s = getenv("T5G_PERSIST_SLOTS")) e->persist_slots = atoi(s);
+  if (const char* s = getenv("T5G_PERSIST_INFLIGHT")) e->persist_inflight = atoi(s);
   DM(e->d_persist_layers, cfg->n_dec_layers);
   DM(e->d_part_o, (size_t)e->Hq * 8 * D); DM(e->d_part_ml, (size_t)e->Hq * 8 * 2);
   DM(e->d_order_self, B); DM(e->d_order_cross, B);
@@ -874,9 +876,13 @@ int enqueue_step_persist(T5GEngine* e, cudaStream_t st, int* n_launch) {
     a.slots = e->d_slots; a.rope_cs = e->d_rope; a.window = c.sliding_window; a.scale = c.attn_scale; a.softcap = c.attn_softcap;
     a.ns_max = std::max(1, std::min(8, e->num_sms / e->Hkv)); a.keys_per_split = e->persist_keys_per_split;
     a.xbuf_floats = decode_persist_xbuf_floats(d, e->I, e->QD, e->Hq / e->Hkv, D);
+    a.n_slots = decode_persist_slots(a.xbuf_floats);
+    if (e->persist_slots > 0) a.n_slots = std::max(8, std::min(a.n_slots, e->persist_slots / 4 * 4));
+    a.max_inflight = std::max(1, std::min(a.n_slots - 4, e->persist_inflight));
     a.qkv = e->d_qkv; a.qc = e->d_qc; a.act = e->d_act; a.y = e->d_y; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml;
     a.h_out = hfin; a.barrier = e->d_barrier; a.err = &e->d_slots[0].error;
     a.probe = e->use_trace ? e->d_trace + 900 : nullptr; a.probe_layer = std::min(5, c.n_dec_layers - 1); a.trace = next_trace();
+    if (const char* s = getenv("T5G_PERSIST_DBG")) a.dbg = atoi(s);
     CU(launch_decode_persist(a, e->num_sms, st, pdl)); nl++; }
   *n_launch = nl;
   return T5G_OK;

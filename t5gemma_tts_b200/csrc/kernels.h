@@ -94,15 +94,18 @@ struct PersistArgs {
   int window; float scale, softcap;
   int ns_max, keys_per_split;                        // split-KV: ns = clamp(ceil(keys / keys_per_split), 1, ns_max) CTAs per kv head
   int xbuf_floats;                                   // shared-memory activation buffer (decode_persist_xbuf_floats)
+  int n_slots, max_inflight;                         // weight ring: slots of 4608 B (decode_persist_slots), units in flight
   float *qkv, *qc, *act, *y;                         // [QKV], [QD], [I], [d] fp32 exchange buffers (global, L2-resident)
   float *part_o, *part_ml;                           // attention partials [Hq][8][D], [Hq][8][2]
   float* h_out;                                      // residual stream after the last layer's cross/MLP adds (pre post_ff)
   unsigned long long* barrier;                       // ticket counter, zeroed once at engine creation
   int* err;                                          // device error flags (4 = barrier timeout)
-  unsigned long long* probe; int probe_layer;        // optional [32] phase timestamps of CTA 0 for one layer (T5G_TRACE)
+  unsigned long long* probe; int probe_layer;        // optional [96] phase timestamps of CTA 0 for one layer (T5G_TRACE)
+  int dbg;                                           // measurement switches (T5G_PERSIST_DBG): 1 = skip the FMAs, 2 = no weight streaming
   unsigned long long* trace;                         // optional kernel begin/end record like the other step kernels
 };
 int decode_persist_xbuf_floats(int d, int I, int QD, int G, int D);
+int decode_persist_slots(int xbuf_floats);
 bool decode_persist_supported(int d, int I, int Hq, int Hkv, int D, int n_layers, int num_sms);
 cudaError_t launch_decode_persist(const PersistArgs& a, int num_sms, cudaStream_t st, bool pdl);
 

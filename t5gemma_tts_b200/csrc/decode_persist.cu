@@ -80,6 +80,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
       "bra DP_WAIT;\n\t"
       "DP_DONE:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
+// bounded wait: a lost arrival turns into an error code (site) instead of a hung device
+__device__ __forceinline__ void mbar_wait_checked(uint64_t* b, uint32_t parity, int* err, int site) {
+  for (unsigned spins = 0;; ++spins) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    if (done) return;
+    if (spins > (1u << 20)) { if (err) atomicCAS(err, 0, 4 | (site << 20)); return; }
+  }
+}
 __device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(DP_CONS) : "memory"); }
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -89,6 +101,60 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 }
 __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- flag-in-data exchange between CTAs -------------------------------------------------------------------------------
+// Every value a phase hands to the next one travels as an 8-byte (value, tag) pair written with ONE 64-bit store (single-
+// copy atomic); the tag encodes (launch epoch, layer, stage).  A reader polls the pair itself until the tag matches, so an
+// exchange costs one L2 round trip after the producer's store -- no fence, no atomic, no grid barrier (a ticket-counter
+// barrier cost 1.2-2.4 us per phase here: membar + atomic + poll round trip + two CTA barriers, 8 times per layer).
+// Buffer reuse is safe without barriers because every stage's output depends on the previous stage's outputs of ALL CTAs.
+__device__ __forceinline__ void st_tag(uint2* p, float v, unsigned tag) {
+  asm volatile("st.global.cg.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_tag(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
+// B tagged elements per thread (element k = k0 + i * stride, valid while k < n): all loads of a round are in flight together.
+// Waiting must not flood L2: 57 K spinning threads saturate its request bandwidth and starve the weight stream and the
+// very stores they wait for (measured: phases slowed down from microseconds to tens of milliseconds).  So only lane 0 of a
+// warp polls (its own first element, with a short sleep between polls) until that shows up; then every lane reads its
+// elements and re-reads, again with a sleep, only if some tag is still missing.
+template <int B>
+__device__ __forceinline__ void ld_tag_vec(const uint2* src, int k0, int stride, int n, unsigned tag, float* out, int* err, int site = 0) {
+  if ((threadIdx.x & 31) == 0 && k0 < n) {
+    // every CTA polls a different element: 148 CTAs spinning on the same dozen addresses load single L2 slices enough to
+    // slow the weight stream that is striped over all of them
+    const int kp = (stride == DP_CONS) ? (int)((blockIdx.x * 41u + (threadIdx.x >> 5) * 32u) % (unsigned)n) : k0;   // (dense vectors only)
+    unsigned spins = 0;
+    while (ld_tag(src + kp).y != tag) {
+      if (++spins > (1u << 22)) { if (err) atomicCAS(err, 0, 4 | ((tag & 0x3ff) << 8) | (site << 20)); break; }
+    }
+  }
+  __syncwarp();
+  uint2 r[B];
+  unsigned miss = 0;
+#pragma unroll
+  for (int i = 0; i < B; ++i) {
+    const int k = k0 + i * stride;
+    r[i] = (k < n) ? ld_tag(src + k) : make_uint2(0u, tag);
+  }
+#pragma unroll
+  for (int i = 0; i < B; ++i) miss |= (r[i].y != tag) ? (1u << i) : 0u;
+  unsigned spins = 0;
+  while (miss) {                                   // only the elements whose producer is late are read again
+#pragma unroll
+    for (int i = 0; i < B; ++i)
+      if (miss & (1u << i)) {
+        r[i] = ld_tag(src + k0 + i * stride);
+        if (r[i].y == tag) miss &= ~(1u << i);
+      }
+    if (++spins > (1u << 22)) { if (err) atomicCAS(err, 0, 4 | ((tag & 0x3ff) << 8) | (site << 20) | (1 << 24)); break; }
+  }
+#pragma unroll
+  for (int i = 0; i < B; ++i) out[i] = __uint_as_float(r[i].x);
 }
 
 // Grid-wide barrier of the consumer threads on a monotonically increasing ticket counter (never reset: every launch adds
@@ -144,7 +210,6 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
   __shared__ __align__(16) float cs[D / 2], sn[D / 2];
   __shared__ __align__(16) float qs[G][D], knew[D], vnew[D];      // read with 16-byte loads
   __shared__ float w_ml[DP_CONS_WARPS][G][2], w_wt[DP_CONS_WARPS][G], c_ml[G][2];
-  __shared__ float m_wt[T5G_PERSIST_MAX_HEADS][DP_MAX_NS];
   __shared__ float h_park[DP_NP * DP_CONS];            // the residual registers are parked here while a CTA runs attention
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -222,9 +287,9 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
           }
           const int r = rem / g.kseg, seg = rem - r * g.kseg;      // kseg, upt are tiny: these stay cheap only because
                                                                    // the producer warps are off the critical path
-          mbar_wait(&empty_bar[slot], par ^ 1);
+          mbar_wait_checked(&empty_bar[slot], par ^ 1, a.err, 10);
           if (n_mine >= F) {
-            mbar_wait(&full_bar[fslot], fpar);
+            mbar_wait_checked(&full_bar[fslot], fpar, a.err, 11);
             fslot += DP_PROD_WARPS; if (fslot >= NS) { fslot -= NS; fpar ^= 1; }
           }
           const bf16* src = W + ((size_t)(cta + n_cta * i) * g.rows_per_task + r) * g.K + (size_t)seg * DP_UNIT_CHUNKS * 8;
@@ -273,9 +338,14 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
   // finer checkpoints of the same layer: entries [32, 96)
 #define DP_FINE() do { if (probing && cur_layer == a.probe_layer && fine_i < 96) a.probe[fine_i++] = globaltimer_ns(); } while (0)
 
-  int base_slot = 0, base_par = 0;                     // ring slot / parity of the first unit of the current phase
+  // ring slot / parity of the first unit of the current phase: uniform values kept in shared memory, double-buffered by
+  // phase parity (phases alternate 0,1,0,1,...; a warp cannot enter phase k+1 before every warp has left the CTA barrier
+  // that follows their read in phase k)
+  __shared__ int s_base[2][2];
+  if (tid == 0) { s_base[0][0] = 0; s_base[0][1] = 0; }
+  int rb_slot = 0, rb_par = 0;                         // (dbg & 4: per-thread copies instead, for bisecting)
   // all tasks of phase p that belong to this warp; the x vector of the phase is in xbuf[0, K)
-  auto run_phase = [&](int p, float* out) {
+  auto run_phase = [&](int p, uint2* out, unsigned tag, float* plain) {
     const PhaseGeo g = geo[p];
     const int KS = g.kseg, rpt = g.rows_per_task, ng = g.ng;
     int seg = warp, gi = 0;
@@ -298,6 +368,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
       }
     }
     // first unit of this warp: n = base + gi * rpt * KS + seg ; next row of the task: + KS ; next task: + ng * rpt * KS
+    int base_slot = (a.dbg & 4) ? rb_slot : s_base[p & 1][0], base_par = (a.dbg & 4) ? rb_par : s_base[p & 1][1];
     int slot = base_slot + gi * rpt * KS + seg, par = base_par;
     while (slot >= NS) { slot -= NS; par ^= 1; }
     const int task_stride = ng * rpt * KS;
@@ -310,7 +381,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
       int s2 = slot, p2 = par;
 #pragma unroll 1
       for (int r = 0; r < rpt; ++r) {
-        if (!dbg_nostream) mbar_wait(&full_bar[s2], p2);
+        if (!dbg_nostream) mbar_wait_checked(&full_bar[s2], p2, a.err, 9);
         const uint4* w = reinterpret_cast<const uint4*>(ring + (size_t)s2 * DP_UNIT_BYTES) + lane;
         float ae = 0.f, ao = 0.f, be = 0.f, bo = 0.f;   // four independent FMA chains
         if (!dbg_nomath && !dbg_nostream) {
@@ -350,7 +421,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
       if (rpt == 2) v1 = warp_sum(acc1);
       if (lane == 0) {
         const float o = (rpt == 2) ? gelu_tanh_f(v0) * v1 : v0;
-        if (KS == 1) out[cta + n_cta * i] = o;
+        if (KS == 1) { st_tag(out + cta + n_cta * i, o, tag); if (plain) plain[cta + n_cta * i] = o; }
         else part[i * KS + seg] = o;
       }
       slot += task_stride;
@@ -359,12 +430,15 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
     DP_FINE();
     base_slot += g.umod; if (base_slot >= NS) { base_slot -= NS; base_par ^= 1; }
     base_par ^= g.upar;
+    rb_slot = base_slot; rb_par = base_par;
+    if (tid == 0) { s_base[(p & 1) ^ 1][0] = base_slot; s_base[(p & 1) ^ 1][1] = base_par; }
     if (KS > 1) {                                      // split-K inside the CTA: combine the K-segments of every row
       cons_sync();
       for (int i = tid; i < g.nt_cta; i += DP_CONS) {
         float v = 0.f;
         for (int k2 = 0; k2 < KS; ++k2) v += part[i * KS + k2];
-        out[cta + n_cta * i] = v;
+        st_tag(out + cta + n_cta * i, v, tag);
+        if (plain) plain[cta + n_cta * i] = v;
       }
     }
   };
@@ -372,15 +446,16 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
   // residual stream, replicated per CTA: thread t holds h[t + 512 i]
   float hreg[DP_NP];
   // h += rmsnorm(y) * g_post (when y) ; xbuf = rmsnorm(h) * g_pre
-  auto sandwich = [&](const float* y, const float* g_post, const float* g_pre) {
+  auto sandwich = [&](const uint2* y, unsigned tag, const float* g_post, const float* g_pre) {
     float gp[DP_NP], gq[DP_NP], yv[DP_NP];
 #pragma unroll
     for (int i = 0; i < DP_NP; ++i) {
       const int k = tid + i * DP_CONS;
       gp[i] = (k < d) ? g_pre[k] : 0.f;
       gq[i] = (y && k < d) ? g_post[k] : 0.f;
-      yv[i] = (y && k < d) ? __ldcg(y + k) : 0.f;
+      yv[i] = 0.f;
     }
+    if (y) ld_tag_vec<DP_NP>(y, tid, DP_CONS, d, tag, yv, a.err, 1);
     float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
     if (yv[0] == 12345.678f) s1 = 1.f;                 // (keeps the probe below after the loads have returned)
     DP_FINE();
@@ -409,8 +484,10 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
     cons_sync();
   };
 
-  // split-KV attention partial of (kv head hk, split) on this CTA; result to part_o / part_ml
-  auto attention = [&](int l, bool is_cross, const float* q, const float* kv_new, int ns) {
+  // split-KV attention of (kv head hk, split) on this CTA: partial -> exchange among the ns CTAs of the head group -> every
+  // CTA finalises a D/ns slice of the group's heads and publishes it in attn_out
+  auto attention = [&](int l, bool is_cross, const uint2* q, const uint2* kv_new, unsigned tag_in, int ns,
+                       uint2* part_o, uint2* part_ml, unsigned tag_part, uint2* attn_out, unsigned tag_out) {
     const int hk = cta % a.Hkv, split = cta / a.Hkv;
     const int* bt = is_cross ? bt_cross : bt_self;
     const int* bt_g = is_cross ? a.cross_bt : a.self_bt;
@@ -442,12 +519,23 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
     };
     load_tile(t_begin + warp * TPW, ku, vu);
     // producer outputs: raw q of the group's heads and the new k/v
-    for (int i = tid; i < G * D; i += DP_CONS) qs[i / D][i % D] = __ldcg(q + (size_t)(hk * G) * D + i);
-    if (has_new)
-      for (int j = tid; j < D; j += DP_CONS) {
-        knew[j] = __ldcg(kv_new + (size_t)hk * D + j);
-        vnew[j] = __bfloat162float(__float2bfloat16(__ldcg(kv_new + (size_t)(a.Hkv + hk) * D + j)));
+    {
+      constexpr int QB = (G * D + DP_CONS - 1) / DP_CONS, KB = (D + DP_CONS - 1) / DP_CONS;
+      float qv[QB];
+      ld_tag_vec<QB>(q + (size_t)(hk * G) * D, tid, DP_CONS, G * D, tag_in, qv, a.err, 2);
+#pragma unroll
+      for (int i = 0; i < QB; ++i) { const int k = tid + i * DP_CONS; if (k < G * D) qs[k / D][k % D] = qv[i]; }
+      if (has_new) {
+        float kv[KB], vv[KB];
+        ld_tag_vec<KB>(kv_new + (size_t)hk * D, tid, DP_CONS, D, tag_in, kv, a.err, 3);
+        ld_tag_vec<KB>(kv_new + (size_t)(a.Hkv + hk) * D, tid, DP_CONS, D, tag_in, vv, a.err, 4);
+#pragma unroll
+        for (int i = 0; i < KB; ++i) {
+          const int k = tid + i * DP_CONS;
+          if (k < D) { knew[k] = kv[i]; vnew[k] = __bfloat162float(__float2bfloat16(vv[i])); }
+        }
       }
+    }
     cons_sync();
     for (int i = tid; i < G * D / 2; i += DP_CONS) {             // PM-RoPE, half-split pairs (j, j + D/2)
       const int g = i / (D / 2), j = i - g * (D / 2);
@@ -564,67 +652,57 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
       float num = 0.f;
 #pragma unroll
       for (int w = 0; w < DP_CONS_WARPS; ++w) num = fmaf(w_wt[w][g], w_o[((size_t)w * G + g) * D + dd], num);
-      a.part_o[((size_t)(hk * G + g) * DP_MAX_NS + split) * D + dd] = num;
+      st_tag(part_o + ((size_t)(hk * G + g) * DP_MAX_NS + split) * D + dd, num, tag_part);
     }
     if (tid < G) {
-      a.part_ml[((hk * G + tid) * DP_MAX_NS + split) * 2] = c_ml[tid][0];
-      a.part_ml[((hk * G + tid) * DP_MAX_NS + split) * 2 + 1] = c_ml[tid][1];
+      st_tag(part_ml + ((hk * G + tid) * DP_MAX_NS + split) * 2, c_ml[tid][0], tag_part);
+      st_tag(part_ml + ((hk * G + tid) * DP_MAX_NS + split) * 2 + 1, c_ml[tid][1], tag_part);
+    }
+    cons_sync();      // w_o aliases the x buffer, which the next stage's prologue overwrites: every warp is done reading it
+    // second hop, among the ns CTAs of this head group only: dims [split * D/ns, (split+1) * D/ns) of the G heads
+    const int dsl = D / ns;
+    for (int ob = warp * 32; ob < G * dsl; ob += DP_CONS) {        // warp-uniform trip count (ld_tag_vec syncs the warp)
+      const int o = ob + lane;
+      const bool live = o < G * dsl;
+      const int g = live ? o / dsl : 0, dd = split * dsl + (live ? o - g * dsl : 0), h = hk * G + g;
+      float v[DP_MAX_NS], ml[2 * DP_MAX_NS];
+      ld_tag_vec<DP_MAX_NS>(part_o + (size_t)h * DP_MAX_NS * D + dd, 0, D, live ? ns * D : 0, tag_part, v, a.err, 5);
+      ld_tag_vec<2 * DP_MAX_NS>(part_ml + h * DP_MAX_NS * 2, 0, 1, live ? 2 * ns : 0, tag_part, ml, a.err, 6);
+      float M = -INFINITY;
+#pragma unroll
+      for (int s2 = 0; s2 < DP_MAX_NS; ++s2) if (s2 < ns) M = fmaxf(M, ml[2 * s2]);
+      float den = 0.f, num = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < DP_MAX_NS; ++s2) {
+        if (s2 < ns) {
+          const float wt = (ml[2 * s2] == -INFINITY) ? 0.f : __expf(ml[2 * s2] - M);
+          den = fmaf(wt, ml[2 * s2 + 1], den);
+          num = fmaf(wt, v[s2], num);
+        }
+      }
+      if (live) st_tag(attn_out + (size_t)h * D + dd, den > 0.f ? num / den : 0.f, tag_out);
     }
   };
 
-  // xbuf[0..QD) = merged attention output (every CTA, redundantly)
-  auto merge_partials = [&](int ns) {
-    // one round trip: the partial outputs are requested first, then Hq * 8 threads each derive ONE normalised merge
-    // weight (own loads of the head's (m, l) pairs, one exp) while those are in flight
-    constexpr int MP = (2048 + DP_CONS - 1) / DP_CONS;
-    float v[MP][DP_MAX_NS];
+  // xbuf[0, n) = a tagged vector published by the previous stage (attention output, GeGLU activations)
+  auto load_x = [&](const uint2* src, int n, unsigned tag) {
+    constexpr int XB = 24;
+#pragma unroll 1
+    for (int base = 0; base < n; base += XB * DP_CONS) {
+      float v[XB];
+      ld_tag_vec<XB>(src + base, tid, DP_CONS, n - base, tag, v, a.err, 7);
 #pragma unroll
-    for (int e = 0; e < MP; ++e) {
-      const int i = tid + e * DP_CONS;
-      const int h = i / D, dd = i - h * D;
-#pragma unroll
-      for (int s = 0; s < DP_MAX_NS; ++s) v[e][s] = (i < QD && s < ns) ? __ldcg(a.part_o + ((size_t)h * DP_MAX_NS + s) * D + dd) : 0.f;
-    }
-    if (tid < a.Hq * DP_MAX_NS) {
-      const int h = tid / DP_MAX_NS, s0 = tid % DP_MAX_NS;
-      float m[DP_MAX_NS], lv[DP_MAX_NS], M = -INFINITY;
-#pragma unroll
-      for (int s = 0; s < DP_MAX_NS; ++s) {
-        m[s] = s < ns ? __ldcg(a.part_ml + (h * DP_MAX_NS + s) * 2) : -INFINITY;
-        lv[s] = s < ns ? __ldcg(a.part_ml + (h * DP_MAX_NS + s) * 2 + 1) : 0.f;
-        M = fmaxf(M, m[s]);
-      }
-      float den = 0.f, mine = 0.f;
-#pragma unroll
-      for (int s = 0; s < DP_MAX_NS; ++s) {
-        const float wt = (m[s] == -INFINITY) ? 0.f : __expf(m[s] - M);
-        den = fmaf(wt, lv[s], den);
-        if (s == s0) mine = wt;
-      }
-      m_wt[h][s0] = den > 0.f ? mine / den : 0.f;
-    }
-    cons_sync();
-#pragma unroll
-    for (int e = 0; e < MP; ++e) {
-      const int i = tid + e * DP_CONS;
-      if (i < QD) {
-        const int h = i / D;
-        float o = 0.f;
-#pragma unroll
-        for (int s = 0; s < DP_MAX_NS; ++s) o = fmaf(m_wt[h][s], v[e][s], o);
-        xbuf[i] = o;
-      }
-    }
-    for (int i = tid + MP * DP_CONS; i < QD; i += DP_CONS) {      // wider models than MP elements per thread
-      const int h = i / D, dd = i - h * D;
-      float o = 0.f;
-      for (int s = 0; s < ns; ++s) o = fmaf(m_wt[h][s], __ldcg(a.part_o + ((size_t)h * DP_MAX_NS + s) * D + dd), o);
-      xbuf[i] = o;
+      for (int i = 0; i < XB; ++i) { const int k = tid + i * DP_CONS; if (k < n - base) xbuf[base + k] = v[i]; }
     }
     cons_sync();
   };
 
-  auto n_splits = [&](int keys, int ns_max) { return max(1, min(ns_max, (keys + a.keys_per_split - 1) / a.keys_per_split)); };
+  auto n_splits = [&](int keys, int ns_max) {          // power of two (the second hop deals D/ns dims to every split CTA)
+    const int want = max(1, min(ns_max, (keys + a.keys_per_split - 1) / a.keys_per_split));
+    int ns = 1;
+    while (ns * 2 <= want && D % (ns * 2) == 0) ns *= 2;
+    return ns;
+  };
   cons_sync();
   if (tid == 0) s_ns_cross = n_splits(s_Lcross, a.ns_max);
 
@@ -635,9 +713,23 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
     hreg[i] = (k < d) ? __bfloat162float(a.emb[(size_t)last_token * d + k]) * a.emb_scale : 0.f;
   }
 
-  // One layer = 8 stages separated by grid barriers.  The stage loop has ONE call site per building block (prologue kinds,
-  // attention, projection): the first version inlined them per stage and grew to 270 KB of SASS, which made the whole
-  // kernel instruction-fetch bound (69 us per layer with the weight stream switched off).
+  // exchange buffers (tagged pairs): offsets live in shared memory (a dozen live 64-bit pointers would spill)
+  enum { X_QKV = 0, X_PS_O, X_PS_ML, X_AS, X_YO, X_QC, X_PC_O, X_PC_ML, X_AC, X_YOC, X_ACT, X_YDN, X_N };
+  __shared__ int xoff[X_N];
+  if (tid == 0) {
+    const int sizes[X_N] = {QKV, a.Hq * DP_MAX_NS * D, a.Hq * DP_MAX_NS * 2, QD, d, QD, a.Hq * DP_MAX_NS * D, a.Hq * DP_MAX_NS * 2, QD, d, I, d};
+    int o = 0;
+    for (int i = 0; i < X_N; ++i) { xoff[i] = o; o += sizes[i]; }
+  }
+  cons_sync();
+#define XB(k) (a.xchg + xoff[k])
+  const unsigned ep_tag = (*reinterpret_cast<const volatile unsigned*>(a.epoch)) << 10;
+  auto TAG = [&](int l, int sid) -> unsigned { return ep_tag + (unsigned)(l * 16 + sid + 1); };
+  enum { S_QKV = 0, S_PS, S_AS, S_YO, S_QC, S_PC, S_AC, S_YOC, S_ACT, S_YDN };
+
+  // One layer = 8 stages.  The stage loop has ONE call site per building block (prologue kinds, attention, projection):
+  // the first version inlined them per stage and grew to 270 KB of SASS, which made the whole kernel instruction-fetch
+  // bound (69 us per layer with the weight stream switched off).
 #pragma unroll 1
   for (int l = 0; l < a.n_layers; ++l) {
     if (tid == 0) cur_layer = l;
@@ -650,17 +742,17 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
       const bool is_attn = (stage == 1 || stage == 4);
       if (stage == 0 || stage == 3 || stage == 6) {
         // qkv / cross q / gate|up consume pre_norm(h + post_norm(previous sub-layer output))
-        const float* y = (stage == 0 && l == 0) ? nullptr : a.y;
+        const uint2* y = stage == 0 ? (l == 0 ? nullptr : XB(X_YDN)) : stage == 3 ? XB(X_YO) : XB(X_YOC);
+        const unsigned tg = stage == 0 ? TAG(l - 1, S_YDN) : stage == 3 ? TAG(l, S_YO) : TAG(l, S_YOC);
         const float* g_post = stage == 0 ? (l > 0 ? lay[l - 1].g_post_ff : nullptr) : stage == 3 ? Ly.g_post_sa : Ly.g_post_ca;
         const float* g_pre = stage == 0 ? Ly.g_pre_sa : stage == 3 ? Ly.g_pre_ca : Ly.g_pre_ff;
-        sandwich(y, g_post, g_pre);
-      } else if (stage == 2 || stage == 5) {
-        merge_partials(stage == 2 ? ns_self : s_ns_cross);            // o projections consume the merged attention output
+        sandwich(y, tg, g_post, g_pre);
+      } else if (stage == 2) {
+        load_x(XB(X_AS), QD, TAG(l, S_AS));                              // o projections consume the attention output
+      } else if (stage == 5) {
+        load_x(XB(X_AC), QD, TAG(l, S_AC));
       } else if (stage == 7) {
-        const float4* av = reinterpret_cast<const float4*>(a.act);   // down projection consumes the GeGLU activations
-        float4* xv = reinterpret_cast<float4*>(xbuf);
-        for (int i = tid; i < (I >> 2); i += DP_CONS) xv[i] = __ldcg(av + i);
-        cons_sync();
+        load_x(XB(X_ACT), I, TAG(l, S_ACT));                             // down projection consumes the GeGLU activations
       }
       if (is_attn) {
         const bool cross = stage == 4;
@@ -668,19 +760,22 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
         if (cta < a.Hkv * ns) {
 #pragma unroll
           for (int i = 0; i < DP_NP; ++i) h_park[i * DP_CONS + tid] = hreg[i];
-          attention(l, cross, cross ? a.qc : a.qkv, cross ? nullptr : a.qkv + QD, ns);
+          if (cross) attention(l, true, XB(X_QC), nullptr, TAG(l, S_QC), ns, XB(X_PC_O), XB(X_PC_ML), TAG(l, S_PC), XB(X_AC), TAG(l, S_AC));
+          else attention(l, false, XB(X_QKV), XB(X_QKV) + QD, TAG(l, S_QKV), ns, XB(X_PS_O), XB(X_PS_ML), TAG(l, S_PS), XB(X_AS), TAG(l, S_AS));
 #pragma unroll
           for (int i = 0; i < DP_NP; ++i) hreg[i] = h_park[i * DP_CONS + tid];
         }
       } else {
         const int p = stage == 0 ? 0 : stage == 2 ? 1 : stage == 3 ? 2 : stage == 5 ? 3 : stage == 6 ? 4 : 5;
-        float* out = stage == 0 ? a.qkv : stage == 3 ? a.qc : stage == 6 ? a.act : a.y;
-        run_phase(p, out);
+        uint2* out = XB(stage == 0 ? X_QKV : stage == 2 ? X_YO : stage == 3 ? X_QC : stage == 5 ? X_YOC : stage == 6 ? X_ACT : X_YDN);
+        const int sid = stage == 0 ? S_QKV : stage == 2 ? S_YO : stage == 3 ? S_QC : stage == 5 ? S_YOC : stage == 6 ? S_ACT : S_YDN;
+        // the head kernel of the next step reads the last layer's MLP output as plain floats
+        run_phase(p, out, TAG(l, sid), (stage == 7 && l + 1 == a.n_layers) ? a.y : nullptr);
       }
       DP_PROBE(l);
-      if (!(stage == 7 && l + 1 == a.n_layers)) grid_barrier(a.barrier, bar_target, a.err);
     }
   }
+  if (cta == 0 && tid == 0) atomicAdd(a.epoch, 1u);     // every CTA read the epoch before it could hand CTA 0 anything
   // the head kernel applies post_ff of the last layer: hand it h (CTA 0) and y (already in a.y)
   if (cta == 0) {
 #pragma unroll
@@ -691,6 +786,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_layers_kernel(PersistArg
   }
   trace_end(a.trace);
 #undef DP_PROBE
+#undef XB
 }
 
 template <int G, int D>
@@ -721,6 +817,11 @@ int decode_persist_xbuf_floats(int d, int I, int QD, int G, int D) {
   const int attn = DP_CONS_WARPS * G * D;     // per-warp attention partials alias the x buffer
   if (attn > m) m = attn;
   return (m + 7) & ~7;
+}
+
+size_t decode_persist_xchg_entries(int d, int I, int Hq, int Hkv, int D) {
+  const size_t QD = (size_t)Hq * D, QKV = QD + 2 * (size_t)Hkv * D, part = (size_t)Hq * DP_MAX_NS * (D + 2);
+  return QKV + 2 * part + 3 * QD + 3 * (size_t)d + I + 64;
 }
 
 // ring slots that fit next to the x buffer and ~30 KB of static shared memory

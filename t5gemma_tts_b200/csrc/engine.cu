@@ -101,7 +101,7 @@ struct T5GEngine {
   int last_nodes_per_step = 0;
   bool prefill_pdl = true;
   int *d_order_self = nullptr, *d_order_cross = nullptr; bool use_row_order = true;   // batched attention: rows by descending length
-  PersistLayer* d_persist_layers = nullptr; float *d_part_o = nullptr, *d_part_ml = nullptr;   // decode_persist.cu
+  PersistLayer* d_persist_layers = nullptr; uint2* d_xchg = nullptr; unsigned* d_epoch = nullptr;   // decode_persist.cu
   bool use_persist = false; int persist_keys_per_split = 24, persist_slots = 0, persist_inflight = 12;
   unsigned long long* d_barrier = nullptr; bool use_pair = true;         // o_proj + cross q_proj in one kernel (gemv_pair.cu)
   int xf_max_keys = 0; bool use_xf = false;                              // capacity (encoder keys over live rows) of that kernel; opt-in (T5G_FUSE_XATTN=1):
@@ -355,7 +355,9 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_PERSIST_SLOTS")) e->persist_slots = atoi(s);
   if (const char* s = getenv("T5G_PERSIST_INFLIGHT")) e->persist_inflight = atoi(s);
   DM(e->d_persist_layers, cfg->n_dec_layers);
-  DM(e->d_part_o, (size_t)e->Hq * 8 * D); DM(e->d_part_ml, (size_t)e->Hq * 8 * 2);
+  { const size_t n = decode_persist_xchg_entries(d, I, e->Hq, e->Hkv, D);
+    DM(e->d_xchg, n); T5G_CUDA(cudaMemset(e->d_xchg, 0, sizeof(uint2) * n));
+    DM(e->d_epoch, 1); const unsigned one = 1; T5G_CUDA(cudaMemcpy(e->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice)); }
   DM(e->d_order_self, B); DM(e->d_order_cross, B);
   { std::vector<int> id(B); for (int i = 0; i < B; ++i) id[i] = i;
     T5G_CUDA(cudaMemcpy(e->d_order_self, id.data(), sizeof(int) * B, cudaMemcpyHostToDevice));
@@ -879,7 +881,7 @@ int enqueue_step_persist(T5GEngine* e, cudaStream_t st, int* n_launch) {
     a.n_slots = decode_persist_slots(a.xbuf_floats);
     if (e->persist_slots > 0) a.n_slots = std::max(8, std::min(a.n_slots, e->persist_slots / 4 * 4));
     a.max_inflight = std::max(1, std::min(a.n_slots - 4, e->persist_inflight));
-    a.qkv = e->d_qkv; a.qc = e->d_qc; a.act = e->d_act; a.y = e->d_y; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml;
+    a.xchg = e->d_xchg; a.epoch = e->d_epoch; a.y = e->d_y;
     a.h_out = hfin; a.barrier = e->d_barrier; a.err = &e->d_slots[0].error;
     a.probe = e->use_trace ? e->d_trace + 900 : nullptr; a.probe_layer = std::min(5, c.n_dec_layers - 1); a.trace = next_trace();
     if (const char* s = getenv("T5G_PERSIST_DBG")) a.dbg = atoi(s);

@@ -95,8 +95,9 @@ struct PersistArgs {
   int ns_max, keys_per_split;                        // split-KV: ns = clamp(ceil(keys / keys_per_split), 1, ns_max) CTAs per kv head
   int xbuf_floats;                                   // shared-memory activation buffer (decode_persist_xbuf_floats)
   int n_slots, max_inflight;                         // weight ring: slots of 4608 B (decode_persist_slots), units in flight
-  float *qkv, *qc, *act, *y;                         // [QKV], [QD], [I], [d] fp32 exchange buffers (global, L2-resident)
-  float *part_o, *part_ml;                           // attention partials [Hq][8][D], [Hq][8][2]
+  uint2* xchg;                                       // tagged (value, tag) exchange buffers, decode_persist_xchg_entries() pairs
+  unsigned* epoch;                                   // launch counter behind the tags (device, starts at 1)
+  float* y;                                          // [d] plain copy of the last layer's MLP output for the head kernel
   float* h_out;                                      // residual stream after the last layer's cross/MLP adds (pre post_ff)
   unsigned long long* barrier;                       // ticket counter, zeroed once at engine creation
   int* err;                                          // device error flags (4 = barrier timeout)
@@ -106,6 +107,7 @@ struct PersistArgs {
 };
 int decode_persist_xbuf_floats(int d, int I, int QD, int G, int D);
 int decode_persist_slots(int xbuf_floats);
+size_t decode_persist_xchg_entries(int d, int I, int Hq, int Hkv, int D);
 bool decode_persist_supported(int d, int I, int Hq, int Hkv, int D, int n_layers, int num_sms);
 cudaError_t launch_decode_persist(const PersistArgs& a, int num_sms, cudaStream_t st, bool pdl);
 

@@ -61,10 +61,9 @@ if os.environ.get("T5G_TRACE") == "1":
     L.check(eng.lib, eng.lib.t5g_debug_trace(eng._h, sp.ctypes.data_as(C.POINTER(C.c_uint64)), se.ctypes.data_as(C.POINTER(C.c_uint64)), 1024, C.byref(nn)))
     if n == 4:   # phase timestamps of CTA 0 for layer 5 of the persistent kernel
         pp = sp[900:918].astype(np.int64)
-        pp = sp[900:917].astype(np.int64)
-        lab = ["start", "norm+qkv", "bar", "sattn", "bar", "merge+o", "bar", "norm+qc", "bar", "cattn", "bar", "merge+oc", "bar",
-               "norm+gu", "bar", "act+down", "bar"]
-        print("persistent kernel, layer 5, CTA 0 (us):", ", ".join(f"{lab[i]} +{(pp[i] - pp[i - 1]) / 1000.0:.2f}" for i in range(1, 16)),
+        pp = sp[900:916].astype(np.int64)
+        lab = ["norm+qkv", "sattn", "load+o", "norm+qc", "cattn", "load+oc", "norm+gu", "act+down"]
+        print("persistent kernel, layer 5, CTA 0 (us):", ", ".join(f"{lab[i]} {(pp[2 * i + 1] - pp[2 * i]) / 1000.0:.2f}" for i in range(8)),
               f"| 8 stages {(pp[15] - pp[0]) / 1000.0:.2f}")
         fp = sp[932:996].astype(np.int64)
         fp = fp[(fp > 0) & (fp < 2**62)]

@@ -36,11 +36,6 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   __shared__ float recv_ml[ATD_MAX_NS][G][2];
   __shared__ float w_wt[ATD_WARPS][G], c_ml[G][2], f_wt[ATD_MAX_NS][G];
 
-  {
-    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, n = gridDim.x * gridDim.y * gridDim.z;
-    l2_prefetch_range(a.pf[0], cta, n);
-    l2_prefetch_range(a.pf[1], cta, n);
-  }
   pdl_launch_dependents();
   const int hk = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
   const int NS = a.n_splits;
@@ -324,13 +319,6 @@ cudaError_t launch_decode_gd(const AttnDecodeArgs& a, cudaStream_t st, bool pdl)
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = step_carveout(attn_decode_kernel<G, D, 8>);
-    if (e == cudaSuccess) e = step_carveout(attn_decode_kernel<G, D, 4>);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   if (wide) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D, 8>, a);
   return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D, 4>, a);
 }

@@ -90,18 +90,6 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p, uint64_t pol) {
 }
 
 #define T5G_TRACE_STRIDE 1024
-// Asynchronous L2 prefetch of an upcoming kernel's weight range (prefetch.global.L2 per line): issued by the
-// kernels of the decode step in their pre-dependency section so that HBM keeps streaming weights into the
-// 126 MB L2 while latency-bound kernels (attention, small projections) leave it idle.
-struct PrefetchRange { const void* ptr; unsigned long long bytes; };
-__device__ __forceinline__ void l2_prefetch_range(const PrefetchRange& r, int cta, int n_ctas) {
-  if (!r.ptr || r.bytes == 0) return;
-  const unsigned long long n = (r.bytes + 127) / 128;            // one prefetch per 128-byte line
-  for (unsigned long long i = (unsigned long long)cta * blockDim.x + threadIdx.x; i < n;
-       i += (unsigned long long)n_ctas * blockDim.x)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)r.ptr + i * 128) : "memory");
-}
-
 // optional in-step tracing (T5G_TRACE=1): per kernel, min over CTAs of the time after griddepcontrol.wait and
 // max over CTAs of the exit time, in %globaltimer nanoseconds
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -159,19 +147,8 @@ struct SlotDev {
   int pad_;
 };
 
-// Experiment hook: force one shared-memory carve-out (percent) on every kernel of the decode step (T5G_CARVEOUT;
-// default -1 = driver's choice).  Measured: the maximum carve-out slows the weight-streaming GEMVs (gate|up 15.5 ->
-// 19.8 us) because in-flight global loads are tracked in L1; kernels of the step therefore keep their shared memory
-// under the 100 KB configuration.
-inline int batched_carveout() {
-  static int pct = -2;
-  if (pct == -2) { const char* e = getenv("T5G_BATCHED_CARVEOUT"); pct = e ? atoi(e) : 100; }
-  return pct;
-}
-template <typename KernelT>
-inline cudaError_t step_carveout(KernelT kern) {
-  static int pct = -2;
-  if (pct == -2) { const char* e = getenv("T5G_CARVEOUT"); pct = e ? atoi(e) : -1; }
-  if (pct < 0) return cudaSuccess;
-  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-}
+// Kernels of the batched (tensor-core) decode step all ask for the maximum shared-memory carve-out: a uniform
+// configuration lets CTAs of consecutive kernels co-reside on an SM under programmatic dependent launch.  (The single-row
+// step keeps its kernels under 100 KB instead: in-flight global loads are tracked in L1, and a large carve-out left behind
+// by one kernel slowed the following weight-streaming GEMVs -- gate|up 15.5 -> 19.8 us, measured.)
+inline int batched_carveout() { return 100; }

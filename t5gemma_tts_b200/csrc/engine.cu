@@ -47,9 +47,7 @@ struct T5GEngine {
   int device = 0, num_sms = 148;
   int d, I, Hq, Hkv, D, QD, KD, QKV, V, Vpad, PT;
   int max_self_pages, max_cross_pages, n_pages;
-  bool use_pdl = true, use_graph = true, use_l2pf = false;   // L2 weight prefetch from kernels that wait on attention: measured
-                                                             // zero-sum (profiles/r1_gemv_design_experiments.md), opt-in
-  size_t l2pf_gu_elems = 0;                                 // gate|up elements prefetched by o_cross (T5G_L2PF_GU_MB)
+  bool use_pdl = true, use_graph = true;
   int gemm_impl = 1;                       // 1 tcgen05/TMEM/TMA (default), 0 = SIMT cross-check kernel
   cudaStream_t load_stream = nullptr;
   std::vector<void*> allocs;               // every cudaMalloc of this engine
@@ -78,7 +76,7 @@ struct T5GEngine {
   float *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_memory = nullptr, *p_ckv = nullptr, *p_final = nullptr;
   bf16 *p_xn = nullptr, *p_q = nullptr, *p_k = nullptr, *p_v = nullptr, *p_att = nullptr, *p_act = nullptr,
        *p_mem_bf = nullptr, *p_ck = nullptr, *p_cv = nullptr, *p_vt = nullptr;
-  int vt_ld = 0; bool use_tc_attn = true; int attn_preload = 1, attn_mma = 1, attn_mma_small = 0;
+  int vt_ld = 0; bool use_tc_attn = true; int attn_mma = 1;
   int *p_vt_off_e = nullptr, *p_vt_off_d = nullptr;          // 8-aligned V^T column offsets per request (encoder / decoder tokens)
   float* p_logits = nullptr; int logits_chunk = 128;
   int *p_ids = nullptr, *p_seg_of = nullptr, *p_seg_off_e = nullptr, *p_seg_off_d = nullptr, *p_tok_slot = nullptr,
@@ -96,16 +94,10 @@ struct T5GEngine {
   int ns_self = 8, ns_cross = 2;
   int h_end = 0;                                               // which h buffer holds the residual at step end
   cudaGraphExec_t step_graph = nullptr; cudaStream_t graph_built_for = nullptr; int nodes_per_step = 0;
-  cudaGraphExec_t multi_graph = nullptr, multi_graph_fx = nullptr; int nodes_multi = 0, nodes_multi_fx = 0, graph_steps = 4;
-  cudaGraphExec_t step_graph_fx = nullptr; int nodes_per_step_fx = 0;   // variant with cross-attention fused into its o_proj
+  cudaGraphExec_t multi_graph = nullptr; int nodes_multi = 0, graph_steps = 4;
   int last_nodes_per_step = 0;
-  bool prefill_pdl = true;
-  int *d_order_self = nullptr, *d_order_cross = nullptr; bool use_row_order = true;   // batched attention: rows by descending length
-  PersistLayer* d_persist_layers = nullptr; uint2* d_xchg = nullptr; unsigned* d_epoch = nullptr;   // decode_persist.cu
-  bool use_persist = false; int persist_keys_per_split = 24, persist_slots = 0, persist_inflight = 12;
+  int *d_order_self = nullptr, *d_order_cross = nullptr;                 // batched attention: rows by descending length
   unsigned long long* d_barrier = nullptr; bool use_pair = true;         // o_proj + cross q_proj in one kernel (gemv_pair.cu)
-  int xf_max_keys = 0; bool use_xf = false;                              // capacity (encoder keys over live rows) of that kernel; opt-in (T5G_FUSE_XATTN=1):
-                                                                         // measured 11.9 us vs 9.4 us for the two separate kernels (profiles/r1_gemv_design_experiments.md)
   int64_t launches = 0;
   cudaEvent_t ev[6] = {};
   float timings[4] = {0, 0, 0, 0};
@@ -207,7 +199,7 @@ cudaError_t gemm(T5GEngine* e, const bf16* A, const bf16* W, int M, int N, int K
   e->launches++;
   // programmatic dependent launch in the prefill chain as well: the GEMM streams its first weight tiles while the previous
   // kernel drains (kernels that are not PDL-aware simply complete first)
-  if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms, e->use_pdl && e->prefill_pdl);
+  if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms, e->use_pdl);
   return launch_gemm_simt(g, st);
 }
 
@@ -244,8 +236,6 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_GRAPH_STEPS")) e->graph_steps = atoi(s);
   if (const char* s = getenv("T5G_GEMM")) e->gemm_impl = atoi(s);
   if (const char* s = getenv("T5G_TRACE")) e->use_trace = atoi(s) != 0;
-  if (const char* s = getenv("T5G_L2PF")) e->use_l2pf = atoi(s) != 0;
-  if (const char* s = getenv("T5G_L2PF_GU_MB")) e->l2pf_gu_elems = (size_t)atoi(s) * 1024 * 512;
   *out = e;   // so that the caller can destroy on failure
   T5G_CUDA(cudaStreamCreateWithFlags(&e->load_stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev) T5G_CUDA(cudaEventCreate(&ev));
@@ -312,13 +302,8 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   e->vt_ld = (int)((T + 8 * (size_t)B + 64 + 7) & ~(size_t)7); DM(e->p_vt, (size_t)KD * e->vt_ld);
   DM(e->p_vt_off_e, B + 1); DM(e->p_vt_off_d, B + 1);
   if (const char* s = getenv("T5G_ATTN_TC")) e->use_tc_attn = atoi(s) != 0;
-  if (const char* s = getenv("T5G_ATTN_PRELOAD")) e->attn_preload = atoi(s) != 0;
-  if (const char* s = getenv("T5G_FUSE_XATTN")) e->use_xf = atoi(s) != 0;
   if (const char* s = getenv("T5G_GEMV_PAIR")) e->use_pair = atoi(s) != 0;
-  if (const char* s = getenv("T5G_ROW_ORDER")) e->use_row_order = atoi(s) != 0;
-  if (const char* s = getenv("T5G_PREFILL_PDL")) e->prefill_pdl = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA")) e->attn_mma = atoi(s) != 0;
-  if (const char* s = getenv("T5G_ATTN_MMA_SMALL")) e->attn_mma_small = atoi(s) != 0;
   DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
   DM(e->p_ids, T); DM(e->p_seg_of, T); DM(e->p_seg_off_e, B + 1); DM(e->p_seg_off_d, B + 1); DM(e->p_tok_slot, T); DM(e->p_tok_idx, T);
   DM(e->p_last_rows, B); DM(e->p_pos, T);
@@ -332,10 +317,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
     e->ns_self = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
     while (D % e->ns_self) e->ns_self >>= 1;
     e->ns_cross = std::min(2, e->ns_self);
-    if (const char* v = getenv("T5G_NS_SELF")) e->ns_self = atoi(v);
-    if (const char* v = getenv("T5G_NS_CROSS")) e->ns_cross = atoi(v);
   }
-  e->xf_max_keys = (B <= 4) ? xattn_oproj_max_keys(B, e->Hq, e->Hkv, D, QD, e->PT, e->num_sms) : 0;
   DM(e->d_hA, (size_t)B * d); DM(e->d_hB, (size_t)B * d); DM(e->d_y, (size_t)B * d); DM(e->d_qkv, (size_t)B * QKV);
   DM(e->d_qc, (size_t)B * QD); DM(e->d_act, (size_t)B * I); DM(e->d_t1, (size_t)B * d); DM(e->d_logits, (size_t)B * e->Vpad);
   DM(e->d_rope, (size_t)B * D);
@@ -347,17 +329,6 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   { const size_t V8 = ((size_t)e->V + 7) & ~(size_t)7; DM(e->d_samp_u64, (size_t)e->samp_scratch_rows * 2 * V8); DM(e->d_samp_f32, (size_t)e->samp_scratch_rows * 2 * V8); }
   DM(e->d_attn, (size_t)B * QD); DM(e->d_trace, 2 * T5G_TRACE_STRIDE);
   DM(e->d_barrier, 2); T5G_CUDA(cudaMemset(e->d_barrier, 0, 2 * sizeof(unsigned long long)));
-  // single-row engines run all decoder layers of a step in one persistent cooperative kernel (decode_persist.cu)
-  e->use_persist = (B == 1) && cfg->n_dec_layers <= T5G_PERSIST_MAX_LAYERS &&
-                   decode_persist_supported(d, I, e->Hq, e->Hkv, D, cfg->n_dec_layers, e->num_sms);
-  if (const char* s = getenv("T5G_PERSIST")) e->use_persist = e->use_persist && atoi(s) != 0;
-  if (const char* s = getenv("T5G_PERSIST_KEYS")) e->persist_keys_per_split = std::max(1, atoi(s));
-  if (const char* s = getenv("T5G_PERSIST_SLOTS")) e->persist_slots = atoi(s);
-  if (const char* s = getenv("T5G_PERSIST_INFLIGHT")) e->persist_inflight = atoi(s);
-  DM(e->d_persist_layers, cfg->n_dec_layers);
-  { const size_t n = decode_persist_xchg_entries(d, I, e->Hq, e->Hkv, D);
-    DM(e->d_xchg, n); T5G_CUDA(cudaMemset(e->d_xchg, 0, sizeof(uint2) * n));
-    DM(e->d_epoch, 1); const unsigned one = 1; T5G_CUDA(cudaMemcpy(e->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice)); }
   DM(e->d_order_self, B); DM(e->d_order_cross, B);
   { std::vector<int> id(B); for (int i = 0; i < B; ++i) id[i] = i;
     T5G_CUDA(cudaMemcpy(e->d_order_self, id.data(), sizeof(int) * B, cudaMemcpyHostToDevice));
@@ -372,9 +343,7 @@ extern "C" int t5g_destroy(T5GEngine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
-  if (e->step_graph_fx) cudaGraphExecDestroy(e->step_graph_fx);
   if (e->multi_graph) cudaGraphExecDestroy(e->multi_graph);
-  if (e->multi_graph_fx) cudaGraphExecDestroy(e->multi_graph_fx);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_mirror) cudaFreeHost(e->h_mirror);
   if (e->h_tokens) cudaFreeHost(e->h_tokens);
@@ -429,16 +398,6 @@ extern "C" int t5g_finalize_weights(T5GEngine* e) {
   T5G_CHECK(e, T5G_ERR_INVALID, "null engine");
   for (const auto& r : e->required)
     T5G_CHECK(e->loaded.count(r), T5G_ERR_STATE, "missing tensor '%s' (%zu of %zu loaded)", r.c_str(), e->loaded.size(), e->required.size());
-  {   // device table of the decoder layers for the persistent kernel
-    std::vector<PersistLayer> tab(e->c.n_dec_layers);
-    for (int l = 0; l < e->c.n_dec_layers; ++l) {
-      const DecLayer& L = e->dec[l];
-      tab[l] = PersistLayer{L.wqkv, L.wo, L.wq_c, L.wo_c, L.wgu, L.wd, L.g_pre_sa, L.g_post_sa, L.g_pre_ca, L.g_post_ca,
-                            L.g_pre_ff, L.g_post_ff, e->c.dec_layer_sliding[l] ? 1 : 0, 0};
-    }
-    T5G_CUDA(cudaSetDevice(e->device));
-    T5G_CUDA(cudaMemcpy(e->d_persist_layers, tab.data(), sizeof(PersistLayer) * tab.size(), cudaMemcpyHostToDevice));
-  }
   e->finalized = true;
   return T5G_OK;
 }
@@ -633,8 +592,8 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   for (int l = 0; l < c.n_enc_layers; ++l) {
     const EncLayer& L = e->enc[l];
     // h += post_ff(prev y) ; xn = pre_sa(h)
-    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl));
-    else CU(launch_norm(e->p_h, e->p_y, e->enc[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl));
+    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl));
+    else CU(launch_norm(e->p_h, e->p_y, e->enc[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl));
     e->launches++;
     CU(gemm(e, e->p_xn, L.wqkv, Te, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st));
     RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Te;
@@ -645,12 +604,12 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
     CU(prefill_attention(e, aa, e->p_v, e->p_vt_off_e, Te, n_req, max_text, max_text, st));
     CU(gemm(e, e->p_att, L.wo, Te, d, QD, GE_F32, nullptr, e->p_y, d, st));
-    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl)); e->launches++;
     CU(gemm(e, e->p_xn, L.wgu, Te, 2 * I, d, GE_GEGLU_BF16, nullptr, e->p_act, I, st));
     CU(gemm(e, e->p_act, L.wd, Te, d, I, GE_F32, nullptr, e->p_y, d, st));
   }
   // memory = final_norm(h + post_ff(y))
-  CU(launch_norm(e->p_h, e->p_y, e->enc[c.n_enc_layers - 1].g_post_ff, e->g_enc_final, nullptr, e->p_mem_bf, e->p_memory, Te, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
+  CU(launch_norm(e->p_h, e->p_y, e->enc[c.n_enc_layers - 1].g_post_ff, e->g_enc_final, nullptr, e->p_mem_bf, e->p_memory, Te, d, c.rms_eps, st, e->use_pdl)); e->launches++;
   CU(cudaEventRecord(e->ev[1], st));
 
   // ================= decoder over BOS + prompt (HF:748-828; models/t5gemma.py:183-243) =================
@@ -670,8 +629,8 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   CU(launch_embed(e->audio_emb, e->p_ids, sqrtf((float)d), e->p_h, Td, d, st)); e->launches++;
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
-    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl));
-    else CU(launch_norm(e->p_h, e->p_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl));
+    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl));
+    else CU(launch_norm(e->p_h, e->p_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl));
     e->launches++;
     CU(gemm(e, e->p_xn, L.wqkv, Td, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st));
     RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Td;
@@ -683,7 +642,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
     CU(prefill_attention(e, aa, e->p_v, e->p_vt_off_d, Td, n_req, max_dec, max_dec, st));
     CU(gemm(e, e->p_att, L.wo, Td, d, QD, GE_F32, nullptr, e->p_y, d, st));
-    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ca, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ca, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl)); e->launches++;
     // cross attention: q = RoPE(q_proj(x), decoder pos); K/V of this layer computed once from memory
     CU(gemm(e, e->p_xn, L.wq_c, Td, QD, d, GE_F32, nullptr, e->p_qkv, QD, st));
     RopeSplitArgs rq{}; rq.qkv = e->p_qkv; rq.ld = QD; rq.q_off = 0; rq.k_off = -1; rq.v_off = -1; rq.pos = e->p_pos; rq.M = Td;
@@ -698,12 +657,12 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     ac.Tq = Td; ac.Hq = e->Hq; ac.Hkv = e->Hkv; ac.D = D; ac.causal = 0; ac.window = 0; ac.scale = c.attn_scale; ac.softcap = c.attn_softcap; ac.out = e->p_att;
     CU(prefill_attention(e, ac, e->p_cv, e->p_vt_off_e, Te, n_req, max_dec, max_text, st));
     CU(gemm(e, e->p_att, L.wo_c, Td, d, QD, GE_F32, nullptr, e->p_y, d, st));
-    CU(launch_norm(e->p_h, e->p_y, L.g_post_ca, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_ca, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl)); e->launches++;
     CU(gemm(e, e->p_xn, L.wgu, Td, 2 * I, d, GE_GEGLU_BF16, nullptr, e->p_act, I, st));
     CU(gemm(e, e->p_act, L.wd, Td, d, I, GE_F32, nullptr, e->p_y, d, st));
   }
   // h = h + post_ff(y) (kept, pre-final-norm) ; p_qkv <- final_norm(h) fp32 for teacher-forced logits
-  CU(launch_norm(e->p_h, e->p_y, e->dec[c.n_dec_layers - 1].g_post_ff, e->g_dec_final, e->p_h, nullptr, e->p_final, Td, d, c.rms_eps, st, e->use_pdl && e->prefill_pdl)); e->launches++;
+  CU(launch_norm(e->p_h, e->p_y, e->dec[c.n_dec_layers - 1].g_post_ff, e->g_dec_final, e->p_h, nullptr, e->p_final, Td, d, c.rms_eps, st, e->use_pdl)); e->launches++;
   // hand the last token of every request to the decode buffers: h_end buffer <- h, y <- 0
   {
     for (int r = 0; r < n_req; ++r) {
@@ -726,7 +685,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) {
+int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch) {
   const T5GConfig& c = e->c;
   const int d = e->d, I = e->I, QD = e->QD, QKV = e->QKV, D = e->D;
   const int B = c.max_slots;
@@ -756,13 +715,6 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
     return cudaSuccess;
   };
   GemvArgs z{}; z.eps = c.rms_eps; z.slots = e->d_slots;
-  const bool l2pf = e->use_l2pf && B <= 4;
-  auto PF = [&](const void* p, size_t elems, size_t off_elems = 0, size_t n_elems = (size_t)-1) -> PrefetchRange {
-    if (!l2pf) return PrefetchRange{nullptr, 0};
-    if (n_elems == (size_t)-1) n_elems = elems - off_elems;
-    return PrefetchRange{(const char*)p + off_elems * 2, (unsigned long long)n_elems * 2};
-  };
-  const size_t GU = (size_t)2 * I * d;
   if (e->use_trace) {
     CU(cudaMemsetAsync(e->d_trace, 0xFF, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
     CU(cudaMemsetAsync(e->d_trace + T5G_TRACE_STRIDE, 0, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
@@ -795,8 +747,8 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-      a.out = e->d_attn; a.preload = e->attn_preload; a.trace = next_trace();
-      if (e->attn_mma_small && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl)); else CU(launch_attn_decode(a, st, pdl));
+      a.out = e->d_attn; a.preload = 1; a.trace = next_trace();
+      CU(launch_attn_decode(a, st, pdl));
       nl++; }
     GemvPairArgs gp{};
     gp.W1 = L.wo; gp.N1 = d; gp.K1 = QD; gp.x = e->d_attn; gp.y = e->d_y; gp.W2 = L.wq_c; gp.N2 = QD; gp.K2 = d;
@@ -807,26 +759,19 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
       CU(launch_gemv_pair(gp, e->num_sms, st, pdl)); nl++; t ^= 1;
     } else {
       { GemvArgs a = z; a.W = L.wo; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
-        a.pf[0] = PF(L.wq_c, (size_t)QD * d);                 // issued while this kernel waits on the attention kernel
         CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
       { GemvArgs a = z; a.W = L.wq_c; a.N = QD; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_sa; a.g_pre = L.g_pre_ca; a.h_out = hbuf[t ^ 1]; t ^= 1;
         a.out = e->d_qc; a.out_stride = QD;
         CU(gemv_all(a, P_RES_NORM, E_STORE, 0, QD)); }
     }
-    if (fuse_cross) {   // cross-attention + o_proj in one kernel (short texts)
-      XAttnOprojArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
-      a.slots = e->d_slots; a.slot0 = 0; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.scale = c.attn_scale; a.softcap = c.attn_softcap;
-      a.rope_cs = e->d_rope; a.max_keys = e->xf_max_keys; a.W = L.wo_c; a.N = d; a.K = QD; a.out = e->d_y; a.out_stride = d; a.trace = next_trace();
-      CU(launch_xattn_oproj(a, e->num_sms, st, pdl)); nl++;
-    } else {
+    {
       { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
         a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
         a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
-        a.out = e->d_attn; a.preload = e->attn_preload; a.trace = next_trace();
-        if (e->attn_mma_small && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl)); else CU(launch_attn_decode(a, st, pdl));
+        a.out = e->d_attn; a.preload = 1; a.trace = next_trace();
+        CU(launch_attn_decode(a, st, pdl));
       nl++; }
       { GemvArgs a = z; a.W = L.wo_c; a.N = d; a.K = QD; a.x = e->d_attn; a.out = e->d_y; a.out_stride = d;
-        a.pf[0] = PF(L.wgu, GU, 0, std::min(GU, e->l2pf_gu_elems));
         CU(gemv_all(a, P_PLAIN, E_STORE, QD, d)); }
     }
     { GemvArgs a = z; a.W = L.wgu; a.N = 2 * I; a.K = d; a.h_in = hbuf[t]; a.y = e->d_y; a.g_post = L.g_post_ca; a.g_pre = L.g_pre_ff; a.h_out = hbuf[t ^ 1]; t ^= 1;
@@ -841,55 +786,6 @@ int enqueue_step(T5GEngine* e, cudaStream_t st, int* n_launch, bool fuse_cross) 
 }
 
 
-// Single-row decode step with the persistent layers kernel: head fc1 -> vocabulary projection -> sampler -> all layers.
-int enqueue_step_persist(T5GEngine* e, cudaStream_t st, int* n_launch) {
-  const T5GConfig& c = e->c;
-  const int d = e->d, D = e->D;
-  const bool pdl = e->use_pdl;
-  int nl = 0, kidx = 0;
-  auto next_trace = [&]() -> unsigned long long* {
-    if (!e->use_trace || kidx >= T5G_TRACE_STRIDE) return nullptr;
-    return e->d_trace + (kidx++);
-  };
-  if (e->use_trace) {
-    CU(cudaMemsetAsync(e->d_trace, 0xFF, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
-    CU(cudaMemsetAsync(e->d_trace + T5G_TRACE_STRIDE, 0, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
-  }
-  float* hfin = e->h_end == 0 ? e->d_hA : e->d_hB;
-  const DecLayer& Llast = e->dec[c.n_dec_layers - 1];
-  GemvArgs z{}; z.eps = c.rms_eps; z.slots = e->d_slots; z.B = 1; z.slot0 = 0;
-  { GemvArgs a = z; a.W = e->head_w1; a.N = d; a.K = d; a.h_in = hfin; a.y = e->d_y; a.g_post = Llast.g_post_ff; a.g_pre = e->g_dec_final;
-    a.h_out = nullptr; a.bias = e->head_b1; a.out = e->d_t1; a.out_stride = d; a.trace = next_trace();
-    CU(launch_gemv(a, P_RES_NORM, E_BIAS_GELU, e->num_sms, st, pdl)); nl++; }
-  { GemvArgs a = z; a.W = e->head_w2; a.N = e->Vpad; a.K = d; a.x = e->d_t1; a.bias = e->head_b2; a.out = e->d_logits; a.out_stride = e->Vpad;
-    a.trace = next_trace();
-    CU(launch_gemv(a, P_PLAIN, E_BIAS, e->num_sms, st, pdl)); nl++; }
-  { SamplerArgs s{}; s.logits = e->d_logits; s.ld = e->Vpad; s.V = e->V; s.slots = e->d_slots; s.topk_sched_pool = e->d_topk_pool;
-    s.eos = c.eos_token; s.encodec_sr = c.encodec_sr; s.text_guard = c.text_guard_frames_per_token; s.progress_scale = c.progress_scale;
-    s.tokens_out = e->d_tokens; s.tokens_stride = c.max_dec_len; s.argmax_out = nullptr; s.rows = 1; s.host_mirror = e->d_mirror;
-    s.picks_out = e->d_picks; s.forced_pool = e->d_forced; s.rope_out = e->d_rope; s.inv_freq = e->inv_freq; s.head_dim = D;
-    s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32;
-    s.trace = next_trace(); s.probe = e->use_trace ? e->d_trace + 1000 : nullptr;
-    CU(launch_sampler(s, st, pdl)); nl++; }
-  { PersistArgs a{}; a.layers = e->d_persist_layers; a.n_layers = c.n_dec_layers;
-    a.d = d; a.I = e->I; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.QD = e->QD; a.KD = e->KD; a.QKV = e->QKV;
-    a.emb = e->audio_emb; a.emb_scale = sqrtf((float)d); a.eps = c.rms_eps; a.pool = e->pool;
-    a.self_bt = e->d_self_bt; a.self_bt_stride = e->max_self_pages; a.cross_bt = e->d_cross_bt; a.cross_bt_stride = e->max_cross_pages;
-    a.slots = e->d_slots; a.rope_cs = e->d_rope; a.window = c.sliding_window; a.scale = c.attn_scale; a.softcap = c.attn_softcap;
-    a.ns_max = std::max(1, std::min(8, e->num_sms / e->Hkv)); a.keys_per_split = e->persist_keys_per_split;
-    a.xbuf_floats = decode_persist_xbuf_floats(d, e->I, e->QD, e->Hq / e->Hkv, D);
-    a.n_slots = decode_persist_slots(a.xbuf_floats);
-    if (e->persist_slots > 0) a.n_slots = std::max(8, std::min(a.n_slots, e->persist_slots / 4 * 4));
-    a.max_inflight = std::max(1, std::min(a.n_slots - 4, e->persist_inflight));
-    a.xchg = e->d_xchg; a.epoch = e->d_epoch; a.y = e->d_y;
-    a.h_out = hfin; a.barrier = e->d_barrier; a.err = &e->d_slots[0].error;
-    a.probe = e->use_trace ? e->d_trace + 900 : nullptr; a.probe_layer = std::min(5, c.n_dec_layers - 1); a.trace = next_trace();
-    if (const char* s = getenv("T5G_PERSIST_DBG")) a.dbg = atoi(s);
-    CU(launch_decode_persist(a, e->num_sms, st, pdl)); nl++; }
-  *n_launch = nl;
-  return T5G_OK;
-}
-
 // Batched decode step (B > 4 rows): the projections become skinny tensor-core GEMMs with M = B (weights are
 // streamed once for the whole batch); attention and sampling are the same kernels as the bs=1 path.
 int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
@@ -898,8 +794,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
   const int B = c.max_slots;
   int nl = 0;
   const bool pdl = e->use_pdl;
-  int mask = 31; if (const char* m = getenv("T5G_PDL_MASK")) mask = atoi(m);
-  const bool pdl_norm = pdl && (mask & 1), pdl_gemm = pdl && (mask & 2), pdl_attn = pdl && (mask & 4), pdl_samp = pdl && (mask & 8), pdl_emb = pdl && (mask & 16);
+  const bool pdl_norm = pdl, pdl_gemm = pdl, pdl_attn = pdl, pdl_samp = pdl;
   int kidx = 0;
   auto next_trace = [&]() -> unsigned long long* {
     if (!e->use_trace || kidx >= T5G_TRACE_STRIDE) return nullptr;
@@ -930,7 +825,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
     s.scratch_u64 = e->d_samp_u64; s.scratch_f32 = e->d_samp_f32; s.trace = next_trace();
     CU(launch_sampler(s, st, pdl_samp)); nl++; }
   // no programmatic overlap with the sampler: later kernels read the slot state before their griddepcontrol.wait
-  CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st, false)); nl++; (void)pdl_emb;
+  CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st, false)); nl++;
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
     if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d, next_trace()));
@@ -942,7 +837,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
       a.row_order = e->d_order_self;
       a.probe = (e->use_trace && l == 5) ? e->d_trace + 300 : nullptr;
-      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload; a.mma = e->attn_mma; a.trace = next_trace();
+      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = 1; a.mma = e->attn_mma; a.trace = next_trace();
       if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
       nl++; }
     CU(G(e->d_attn_bf, L.wo, d, QD, GE_F32, nullptr, e->d_y, d));
@@ -952,7 +847,7 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
       a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
       a.row_order = e->d_order_cross;
-      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = e->attn_preload; a.mma = e->attn_mma; a.trace = next_trace();
+      a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = 1; a.mma = e->attn_mma; a.trace = next_trace();
       if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
       nl++; }
     CU(G(e->d_attn_bf, L.wo_c, d, QD, GE_F32, nullptr, e->d_y, d));
@@ -972,7 +867,7 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
   T5G_CUDA(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream_;
   CU(cudaEventRecord(e->ev[3], st));
-  if (e->c.max_slots > 4 && e->use_row_order) {
+  if (e->c.max_slots > 4) {
     // rows by descending key count (host's last known lengths: prompt + tokens generated at the last poll)
     const int B = e->c.max_slots;
     std::vector<int> os(B), oc(B), ls(B), lc(B);
@@ -986,16 +881,8 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
     CU(cudaMemcpyAsync(e->d_order_self, os.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(e->d_order_cross, oc.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
   }
-  // cross-attention fused into o_proj when the encoder keys of all rows in use fit its shared-memory staging
-  bool fuse = false;
-  if (e->c.max_slots <= 4 && e->use_xf && e->xf_max_keys > 0) {
-    int keys = 0;
-    for (int s = 0; s < e->c.max_slots; ++s) if (e->hslots[s].in_use) keys += e->hslots[s].n_text;
-    fuse = keys > 0 && keys <= e->xf_max_keys;
-  }
   auto enqueue = [&](cudaStream_t s_, int* nl) -> int {
-    if (e->use_persist) return enqueue_step_persist(e, s_, nl);
-    return (e->c.max_slots > 4) ? enqueue_step_batched(e, s_, nl) : enqueue_step(e, s_, nl, fuse);
+    return (e->c.max_slots > 4) ? enqueue_step_batched(e, s_, nl) : enqueue_step(e, s_, nl);
   };
   if (e->use_graph) {
     // one graph = one step, plus a graph of `graph_steps` consecutive steps: inside it the head of step t+1 is a
@@ -1019,10 +906,10 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
       return T5G_OK;
     };
     const int MS = (e->use_trace || e->graph_steps < 2) ? 1 : e->graph_steps;
-    cudaGraphExec_t& g1 = fuse ? e->step_graph_fx : e->step_graph;
-    int& n1 = fuse ? e->nodes_per_step_fx : e->nodes_per_step;
-    cudaGraphExec_t& gm = fuse ? e->multi_graph_fx : e->multi_graph;
-    int& nm = fuse ? e->nodes_multi_fx : e->nodes_multi;
+    cudaGraphExec_t& g1 = e->step_graph;
+    int& n1 = e->nodes_per_step;
+    cudaGraphExec_t& gm = e->multi_graph;
+    int& nm = e->nodes_multi;
     int done = 0;
     if (MS > 1 && max_steps >= MS) {
       int rc = get_graph(gm, nm, MS);

@@ -237,224 +237,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Weight-streaming variant for skinny problems (M <= 64 tokens: batched decode).  Same tcgen05/TMEM math, but the
-// operand tiles are fetched with per-thread 16-byte cp.async (LDGSTS) copies written straight into the 128-byte
-// swizzled layout the UMMA descriptor expects: 128 producer threads keep NSTAGE x (16 KB + TOKT*128 B) in flight
-// per SM with no register cost, which sustains HBM streaming where the TMA path is limited by its per-CTA request
-// depth (profiles/r1_gemv_design_experiments.md).  Completion is tracked with cp.async.mbarrier.arrive.noinc, so
-// producers never block; the four producer warps become the epilogue warps once their loads are issued.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int ST_THREADS = 288;     // warps 0-3: cp.async producers, then epilogue; warp 4: MMA issuer + TMEM alloc;
-                                    // warps 5-8: producers only (the producer side is instruction-issue bound: two
-                                    // producer warps per scheduler and 3-4 instructions per 16-byte copy)
-constexpr int ST_PROD = 256;
-
-__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <int TOKT, int NSTAGE>
-__global__ void __launch_bounds__(ST_THREADS, 1) gemm_stream_kernel(const bf16* __restrict__ W, const bf16* X, TcParams p) {
-  extern __shared__ __align__(1024) unsigned char smraw[];
-  TcSmem<TOKT, NSTAGE>& S = *reinterpret_cast<TcSmem<TOKT, NSTAGE>*>(
-      (reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
-  constexpr int TMEM_COLS = TOKT < 32 ? 32 : TOKT;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int f0 = blockIdx.x * TC_BM, t0 = blockIdx.y * TOKT;
-  const int kb_total = p.K / TC_BK;
-  const int kb0 = blockIdx.z * p.k_blocks_per_split;
-  const int nkb = min(p.k_blocks_per_split, kb_total - kb0);
-  unsigned long long* probe = (p.probe && blockIdx.x == gridDim.x / 2 && blockIdx.z == 0) ? p.probe : nullptr;
-#define GS_PROBE(k) do { if (probe && lane == 0) probe[k] = globaltimer_ns(); } while (0)
-  if (warp == 0) GS_PROBE(0);
-
-  if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&S.full[i], ST_PROD / ((NSTAGE % 4 == 0) ? 4 : 2)); mbar_init(&S.empty[i], 1); }
-    mbar_init(&S.acc_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = S.tmem_base;
-
-  if (warp != 4) {
-    // ===== producers.  HBM locality decides this kernel: fetching one 128-byte K-slab of 128 different weight rows per
-    //       stage touches 128 DRAM pages for 128 bytes each (measured 3.2 TB/s on gate|up).  Stages are therefore filled
-    //       in GROUPS of 4 (2 for the 128-token tile) consecutive k-blocks: a warp copies 512 contiguous bytes of one
-    //       weight row (one swizzle atom per ring stage of the group).  Lanes 8j..8j+7 feed stage j of the group, so each
-    //       stage's "full" barrier counts ST_PROD / GRP threads.  Per-thread constants keep a
-    //       16-byte copy at ~3 instructions. =====
-    const int ptid = warp < 4 ? tid : tid - 32;
-    constexpr int GRP = (NSTAGE % 4 == 0) ? 4 : 2;                               // k-blocks (ring stages) filled together
-    constexpr int CPG = 8 * GRP, RSTEP = ST_PROD / CPG;                          // 16-byte chunks per row per group; rows per pass
-    static_assert(NSTAGE % GRP == 0 && RSTEP % 8 == 0, "ring/group geometry");
-    const int j = (ptid % CPG) >> 3, col = ptid & 7, row0 = ptid / CPG;          // stage of the group, 16-byte column, first row
-    const uint32_t swz = (uint32_t)((col ^ (row0 & 7)) << 4);                   // (row & 7) == (row0 & 7) for rows row0 + RSTEP*u
-    const uint32_t wdst0 = smem_u32(S.w[0]) + row0 * 128 + swz, xdst0 = smem_u32(S.x[0]) + row0 * 128 + swz;
-    constexpr uint32_t W_STAGE = TC_BM * TC_BK * 2, X_STAGE = TOKT * TC_BK * 2;
-    const bf16* wbase = W + (size_t)kb0 * TC_BK + col * 8;
-    const bf16* xbase = X + (size_t)kb0 * TC_BK + col * 8;
-    auto load_w = [&](int i, int s) {                                            // k-block i (relative to kb0) -> ring stage s
-#pragma unroll
-      for (int u = 0; u < TC_BM / RSTEP; ++u) {
-        const int n = f0 + row0 + RSTEP * u;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(wdst0 + s * W_STAGE + u * (RSTEP * 128)),
-                     "l"(wbase + (size_t)min(n, p.N - 1) * p.K + (size_t)i * TC_BK), "r"(n < p.N ? 16 : 0) : "memory");
-      }
-    };
-    auto load_x = [&](int i, int s) {
-#pragma unroll
-      for (int u = 0; u < (TOKT + RSTEP - 1) / RSTEP; ++u) {
-        const int r = row0 + RSTEP * u, m = t0 + r;
-        if (r < TOKT)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xdst0 + s * X_STAGE + u * (RSTEP * 128)),
-                       "l"(xbase + (size_t)min(m, p.M - 1) * p.K + (size_t)i * TC_BK), "r"(m < p.M ? 16 : 0) : "memory");
-      }
-    };
-    constexpr int NGRP = NSTAGE / GRP;                                           // groups in the ring
-    const int ngroups = (nkb + GRP - 1) / GRP;
-    // weights are immutable: the first ring-full is requested before the PDL dependency resolves
-    for (int g = 0; g < min(ngroups, NGRP); ++g) { const int i = g * GRP + j; if (i < nkb) load_w(i, i); }
-    pdl_launch_dependents();
-    pdl_wait();
-    trace_begin(p.trace);
-    if (warp == 0) GS_PROBE(1);
-    for (int g = 0; g < min(ngroups, NGRP); ++g) { const int i = g * GRP + j; if (i < nkb) { load_x(i, i); cp_async_arrive(&S.full[i]); } }
-    for (int g = NGRP; g < ngroups; ++g) {
-      // tcgen05.commit releases stages in order: once the LAST stage of the group is free all four are, and the
-      // whole warp issues its 512-byte row segments together (no divergence on four different barriers)
-      const int ilast = min(g * GRP + GRP - 1, nkb - 1);
-      mbar_wait(&S.empty[ilast % NSTAGE], ((ilast / NSTAGE) - 1) & 1);
-      const int i = g * GRP + j, s = i % NSTAGE;
-      if (i < nkb) {
-        load_w(i, s);
-        load_x(i, s);
-        cp_async_arrive(&S.full[s]);
-      }
-    }
-    if (warp == 0) GS_PROBE(2);
-  } else if (lane == 0) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TOKT >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % NSTAGE;
-      mbar_wait(&S.full[s], (i / NSTAGE) & 1);
-      if (i == 0) GS_PROBE(5);
-      if (i == nkb / 2) GS_PROBE(6);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // cp.async (generic proxy) -> tcgen05 (async proxy)
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t wa = smem_u32(S.w[s]), xa = smem_u32(S.x[s]);
-#pragma unroll
-      for (int k = 0; k < TC_BK / 16; ++k)
-        umma_bf16(tmem_d, umma_desc_sw128(wa + k * 32), umma_desc_sw128(xa + k * 32), idesc, (i | k) ? 1u : 0u);
-      umma_commit(&S.empty[s]);
-    }
-    umma_commit(&S.acc_full);
-    GS_PROBE(7);
-  }
-  if (warp != 4) {
-    // ===== epilogue: all 8 producer warps.  A warp may only read the TMEM lane quarter (warp id % 4); warps 0-3 take the
-    //       first half of the token columns, warps 5-8 the second half (one 16-column chunk is the granule). =====
-    const int q = warp & 3, fl = q * 32 + lane, f = f0 + fl;
-    constexpr int NCH = TOKT / 16;
-    const int ch0 = (NCH >= 2) ? (warp < 4 ? 0 : NCH / 2) : 0;
-    const int ch1 = (NCH >= 2) ? (warp < 4 ? NCH / 2 : NCH) : (warp < 4 ? NCH : 0);
-    mbar_wait(&S.acc_full, 0);
-    if (warp == 0) GS_PROBE(3);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* red = reinterpret_cast<float*>(&S.w[0][0]);
-    const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
-    const bool even = (lane & 1) == 0;
-#pragma unroll 1
-    for (int ch = ch0; ch < ch1; ++ch) {
-      const int c = ch * 16;
-      if (t0 + c >= p.M) break;
-      float v[16];
-      tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (p.atomic) {
-        float* o = reinterpret_cast<float*>(p.out) + (size_t)(t0 + c) * p.ldo + f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (t0 + c + j < p.M && f < p.N) atomicAdd(o + (size_t)j * p.ldo, v[j]);
-      } else if (p.split_k > 1) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) red[(c + j) * TC_BM + fl] = v[j];
-      } else {
-        switch (p.epilogue) {
-          case GE_F32: store_chunk<GE_F32>(p, v, t0 + c, f, bias, even); break;
-          case GE_BF16: store_chunk<GE_BF16>(p, v, t0 + c, f, bias, even); break;
-          case GE_BIAS_F32: store_chunk<GE_BIAS_F32>(p, v, t0 + c, f, bias, even); break;
-          case GE_BIAS_GELU_BF16: store_chunk<GE_BIAS_GELU_BF16>(p, v, t0 + c, f, bias, even); break;
-          default: store_chunk<GE_GEGLU_BF16>(p, v, t0 + c, f, bias, even); break;
-        }
-      }
-    }
-  }
-  if (p.split_k > 1 && !p.atomic) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();
-    if (warp < 4) {
-      const int rank = (int)cluster.block_rank(), nr = p.split_k;
-      const int fl = warp * 32 + lane, f = f0 + fl;
-      const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
-      float* red = reinterpret_cast<float*>(&S.w[0][0]);
-      for (int j = rank; j < TOKT && t0 + j < p.M; j += nr) {
-        float acc = 0.f, acc_up = 0.f;
-        for (int r = 0; r < nr; ++r) {
-          const float* rr = cluster.map_shared_rank(red, r);
-          acc += rr[j * TC_BM + fl];
-          if (p.epilogue == GE_GEGLU_BF16) acc_up += rr[j * TC_BM + (fl | 1)];
-        }
-        epilogue_store(p, t0 + j, f, acc, acc_up, bias, (fl & 1) == 0);
-      }
-    }
-    cluster.sync();
-  }
-  if (warp == 0) GS_PROBE(4);
-  trace_end(p.trace);
-#undef GS_PROBE
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
-  }
-}
-
-template <int TOKT, int NSTAGE>
-cudaError_t launch_stream(const GemmArgs& a, const TcParams& p, dim3 grid, cudaStream_t st, bool pdl) {
-  auto kern = gemm_stream_kernel<TOKT, NSTAGE>;
-  const size_t smem = sizeof(TcSmem<TOKT, NSTAGE>) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    // batched-step kernels all ask for the maximum shared-memory carve-out: CTAs of consecutive kernels can then share an SM
-    if (batched_carveout() >= 0 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, batched_carveout())) != cudaSuccess) return e;
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(ST_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = p.atomic ? 1 : p.split_k;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, kern, a.W, a.A, p);
-}
-
 template <int TOKT, int NSTAGE>
 cudaError_t launch_tc(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, dim3 grid, cudaStream_t st, bool pdl) {
   auto kern = gemm_tc_kernel<TOKT, NSTAGE>;
@@ -511,29 +293,6 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
   }
   TcParams p{a.M, a.N, a.K, a.epilogue, a.bias, a.out, a.ldo, kbps, split, atomic, a.trace, a.probe};
   dim3 grid((a.N + TC_BM - 1) / TC_BM, (a.M + tokt - 1) / tokt, split);
-  static int use_stream = -1;
-  // TMA front end by default.  The cp.async front end (T5G_GEMM_STREAM=1) looked faster while both kernels were bound by
-  // the old 4-warp epilogue; with the epilogue fixed the TMA ring wins on every decode GEMM at 64 rows (gate|up 17.9 ->
-  // 16.8 us, down 10.1 -> 8.9, vocabulary 71.8 -> 63.8; step 2.31 -> 2.22 ms; 16 rows 2.02 -> 1.84 ms)
-  if (use_stream < 0) { const char* e = getenv("T5G_GEMM_STREAM"); use_stream = e ? atoi(e) : 0; }
-  if (use_stream && tokt <= 128) {
-    switch (tokt) {
-      case 16: return launch_stream<16, 8>(a, p, grid, st, pdl);
-      case 32: return launch_stream<32, 8>(a, p, grid, st, pdl);
-      case 64: return launch_stream<64, 6>(a, p, grid, st, pdl);   // 145 KB: an 80 KB attention CTA of the next kernel fits beside it
-      default: return launch_stream<128, 6>(a, p, grid, st, pdl);
-    }
-  }
-  static int small_ring = -1;       // experiment: rings of <= 100 KB so that two CTAs (of consecutive kernels) share an SM
-  if (small_ring < 0) { const char* e = getenv("T5G_TC_SMALL_RING"); small_ring = e ? atoi(e) : 0; }
-  if (small_ring) {
-    switch (tokt) {
-      case 16: return launch_tc<16, 5>(mw, mx, p, grid, st, pdl);
-      case 32: return launch_tc<32, 5>(mw, mx, p, grid, st, pdl);
-      case 64: return launch_tc<64, 4>(mw, mx, p, grid, st, pdl);
-      default: break;
-    }
-  }
   switch (tokt) {
     case 16: return launch_tc<16, 8>(mw, mx, p, grid, st, pdl);
     case 32: return launch_tc<32, 8>(mw, mx, p, grid, st, pdl);

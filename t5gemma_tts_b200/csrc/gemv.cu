@@ -96,8 +96,6 @@ __global__ void __launch_bounds__(GV_THREADS, (NB == 1) ? 2 : 1) gemv_kernel(Gem
       }
     }
   }
-  l2_prefetch_range(a.pf[0], blockIdx.x, gridDim.x);
-  l2_prefetch_range(a.pf[1], blockIdx.x, gridDim.x);
   // RMSNorm gains are weights: fetch them before the dependency resolves as well
   float gpre[NP], gpost[NP];
   if (P == P_NORM || P == P_RES_NORM || P == P_EMBED_NORM) {
@@ -271,7 +269,6 @@ cudaError_t launch_one(const GemvArgs& a, int grid, size_t smem, cudaStream_t st
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    if ((e = step_carveout(kern)) != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -315,15 +312,9 @@ cudaError_t launch_gemv(const GemvArgs& a, int P, int E, int num_sms, cudaStream
   if (a.N % unit_rows) return cudaErrorInvalidValue;
   const int nchunks = a.K / 8, kseg = (nchunks + SEG_CHUNKS - 1) / SEG_CHUNKS, parts = kseg * unit_rows;
   const int n_out = a.N / unit_rows;
-  static int mult = -1;
-  // CTAs per SM; 1 was measured (room for the next kernel to become resident early): gate|up 15.6 -> 22.4 us, too few bytes in flight
-  if (mult < 0) { const char* e = getenv("T5G_GEMV_GRID_MULT"); mult = e ? atoi(e) : 2; }
-  // experiment (T5G_GEMV_SMALL_1CTA=1): projections whose units fit one per warp at ONE CTA per SM would leave half of every
-  // SM's registers free, so the next kernel's CTAs become resident and pre-load their weights while this one runs
-  static int small_one = -1;
-  if (small_one < 0) { const char* e = getenv("T5G_GEMV_SMALL_1CTA"); small_one = e ? atoi(e) : 0; }   // measured: 1.571 -> 1.604 ms/step (cross-attention +0.8 us), off
-  const bool one_per_sm = small_one && NB == 1 && (long long)n_out * parts <= (long long)num_sms * GV_WARPS;
-  const int grid = (NB == 1 ? (one_per_sm ? 1 : mult) : 1) * num_sms;
+  // two CTAs per SM for single-row launches: 147 KB of weight loads in flight per SM (one CTA per SM was measured at
+  // 22.4 instead of 15.6 us on the gate|up projection)
+  const int grid = (NB == 1 ? 2 : 1) * num_sms;
   const int outs_per_cta = (n_out + grid - 1) / grid;
   const size_t part_floats = (parts == 1) ? 0 : (size_t)outs_per_cta * parts * NB;
   if (part_floats > MAX_PARTS_PER_CTA * 4) return cudaErrorInvalidValue;

@@ -21,7 +21,6 @@ struct GemvArgs {
   float* out; int out_stride;
   const SlotDev* slots; int slot0;   // optional activity gating / last_token source
   unsigned long long* trace;         // optional [2]: begin/end timestamps
-  PrefetchRange pf[2];               // upcoming weights to pull into L2 (see l2_prefetch_range)
 };
 cudaError_t launch_gemv(const GemvArgs& a, int P, int E, int num_sms, cudaStream_t st, bool pdl);
 
@@ -66,7 +65,6 @@ struct AttnDecodeArgs {
   const float* rope_cs;                    // optional [B][D]: cos[D/2] | sin[D/2] of the row's position (written by the sampler)
   float* out;                              // [B, Hq*D] final (normalised) attention output (fp32), or
   bf16* out_bf;                            // bf16 copy for the tensor-core o_proj of the batched path (either may be null)
-  PrefetchRange pf[2];
   unsigned long long* trace;
   unsigned long long* probe;               // optional [B][11] in-kernel checkpoints of the (kv head 0, split 0) CTAs (debug)
   const int* row_order;                    // optional [B]: blockIdx.z -> row; longest rows first so they are scheduled first
@@ -74,58 +72,6 @@ struct AttnDecodeArgs {
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
 bool attn_decode_mma_supported(const AttnDecodeArgs& a);
 cudaError_t launch_attn_decode_mma(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);   // attention_mma.cu
-
-// ---------------- all decoder layers of the single-row decode step in one persistent cooperative kernel (decode_persist.cu) ----------------
-#define T5G_PERSIST_MAX_LAYERS 64
-#define T5G_PERSIST_MAX_HEADS 32
-struct PersistLayer {
-  const bf16 *wqkv, *wo, *wq_c, *wo_c, *wgu, *wd;
-  const float *g_pre_sa, *g_post_sa, *g_pre_ca, *g_post_ca, *g_pre_ff, *g_post_ff;
-  int sliding, pad_;
-};
-struct PersistArgs {
-  const PersistLayer* layers; int n_layers;          // device table
-  int d, I, Hq, Hkv, D, QD, KD, QKV;
-  const bf16* emb; float emb_scale, eps;
-  KVPool pool;
-  const int* self_bt; int self_bt_stride; const int* cross_bt; int cross_bt_stride;   // block tables of row 0
-  const SlotDev* slots;                              // row 0
-  const float* rope_cs;                              // [D]: cos | sin of the row's position (written by the sampler)
-  int window; float scale, softcap;
-  int ns_max, keys_per_split;                        // split-KV: ns = clamp(ceil(keys / keys_per_split), 1, ns_max) CTAs per kv head
-  int xbuf_floats;                                   // shared-memory activation buffer (decode_persist_xbuf_floats)
-  int n_slots, max_inflight;                         // weight ring: slots of 4608 B (decode_persist_slots), units in flight
-  uint2* xchg;                                       // tagged (value, tag) exchange buffers, decode_persist_xchg_entries() pairs
-  unsigned* epoch;                                   // launch counter behind the tags (device, starts at 1)
-  float* y;                                          // [d] plain copy of the last layer's MLP output for the head kernel
-  float* h_out;                                      // residual stream after the last layer's cross/MLP adds (pre post_ff)
-  unsigned long long* barrier;                       // ticket counter, zeroed once at engine creation
-  int* err;                                          // device error flags (4 = barrier timeout)
-  unsigned long long* probe; int probe_layer;        // optional [96] phase timestamps of CTA 0 for one layer (T5G_TRACE)
-  int dbg;                                           // measurement switches (T5G_PERSIST_DBG): 1 = skip the FMAs, 2 = no weight streaming
-  unsigned long long* trace;                         // optional kernel begin/end record like the other step kernels
-};
-int decode_persist_xbuf_floats(int d, int I, int QD, int G, int D);
-int decode_persist_slots(int xbuf_floats);
-size_t decode_persist_xchg_entries(int d, int I, int Hq, int Hkv, int D);
-bool decode_persist_supported(int d, int I, int Hq, int Hkv, int D, int n_layers, int num_sms);
-cudaError_t launch_decode_persist(const PersistArgs& a, int num_sms, cudaStream_t st, bool pdl);
-
-// ---------------- cross-attention fused into its output projection, bs<=4 decode (xattn_fused.cu) ----------------
-struct XAttnOprojArgs {
-  KVPool pool; int layer;
-  const int* block_table; int bt_stride;   // cross block table [slot][bt_stride]
-  const float* q; int q_stride;            // raw (pre-RoPE) cross queries [B, q_stride]
-  const SlotDev* slots; int slot0; int B;
-  int Hq, Hkv, D; float scale, softcap;
-  const float* rope_cs;                    // [slot][D]: cos | sin of the row's PM-RoPE angle (written by the sampler)
-  int max_keys;                            // shared-memory capacity in encoder keys (sum over live rows)
-  const bf16* W; int N; int K;             // o_proj [N, K = Hq*D]
-  float* out; int out_stride;
-  unsigned long long* trace;
-};
-int xattn_oproj_max_keys(int B, int Hq, int Hkv, int D, int K, int page_tokens, int num_sms);
-cudaError_t launch_xattn_oproj(const XAttnOprojArgs& a, int num_sms, cudaStream_t st, bool pdl);
 
 // ---------------- prefill-side kernels (prefill.cu) ----------------
 // varlen packing: token t belongs to request seg_of[t]; seg_off[r]..seg_off[r+1] are its tokens
@@ -195,7 +141,6 @@ struct SamplerArgs {
   int* host_mirror;                   // optional mapped-host [rows][8]: active, finished, n_generated, cur_len, error flags
   float* rope_out; const float* inv_freq; int head_dim;   // optional: cos|sin table of the new position per row
   unsigned long long* trace;
-  PrefetchRange pf[4];
   unsigned long long* scratch_u64;    // general path: [rows][2][V8] composites (V8 = V rounded up to 8), may be null
   float* scratch_f32;                 // [rows][2][V8]
   int* argmax_out;                    // optional [rows]

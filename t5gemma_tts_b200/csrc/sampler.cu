@@ -212,7 +212,6 @@ __device__ __noinline__ int sample_large(const SamplerArgs& a, Shared& S, int ro
 __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   Shared& S = *reinterpret_cast<Shared*>(smraw);
-  for (int i = 0; i < 4; ++i) l2_prefetch_range(a.pf[i], blockIdx.x, gridDim.x);
   pdl_launch_dependents();
   pdl_wait();
   trace_begin(a.trace);
@@ -691,7 +690,6 @@ cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st, bool pdl) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
-    if (e == cudaSuccess) e = step_carveout(sampler_kernel);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }

@@ -391,13 +391,13 @@ template <int G, int D>
 cudaError_t launch_am(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   auto kern = attn_decode_mma_kernel<G, D>;
   const size_t smem = AmGeo<D>::dyn_bytes(G, a.n_splits);
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
+  static PerDeviceFlag attr_set;
+  if (smem > attr_set.here()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // batched-step kernels all ask for the maximum shared-memory carve-out: CTAs of consecutive kernels can then share an SM
     if (batched_carveout() >= 0 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, batched_carveout())) != cudaSuccess) return e;
-    attr_set = smem;
+    attr_set.here() = smem;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.Hkv, a.n_splits, a.B);

@@ -242,11 +242,11 @@ cudaError_t launch_fa(const AttnPrefillArgs& a, const bf16* vt, const int* vt_se
     return cudaErrorNotSupported;
   auto kern = attn_prefill_tc_kernel<D>;
   const size_t smem = sizeof(FaSmem<D>) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.here()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.here() = 1;
   }
   FaParams p{a.q_seg_off, a.k_seg_off, vt_seg_off, a.Hq, a.Hkv, a.causal, a.window, a.scale, a.softcap, a.out};
   dim3 grid((max_lq + FA_BQ - 1) / FA_BQ, a.Hq, n_seg);

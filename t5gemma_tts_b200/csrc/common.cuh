@@ -147,6 +147,14 @@ struct SlotDev {
   int pad_;
 };
 
+// Function attributes (dynamic shared memory limit, carve-out) are per DEVICE: the "already set" state of a kernel is
+// tracked per device ordinal so that engines on several GPUs of one process all get them (setting one twice is harmless).
+#define T5G_MAX_DEVICES 64
+struct PerDeviceFlag {
+  size_t v[T5G_MAX_DEVICES] = {};
+  size_t& here() { int d = 0; cudaGetDevice(&d); return v[(d >= 0 && d < T5G_MAX_DEVICES) ? d : 0]; }
+};
+
 // Kernels of the batched (tensor-core) decode step all ask for the maximum shared-memory carve-out: a uniform
 // configuration lets CTAs of consecutive kernels co-reside on an SM under programmatic dependent launch.  (The single-row
 // step keeps its kernels under 100 KB instead: in-flight global loads are tracked in L1, and a large carve-out left behind

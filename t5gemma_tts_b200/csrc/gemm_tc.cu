@@ -241,13 +241,13 @@ template <int TOKT, int NSTAGE>
 cudaError_t launch_tc(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, dim3 grid, cudaStream_t st, bool pdl) {
   auto kern = gemm_tc_kernel<TOKT, NSTAGE>;
   const size_t smem = sizeof(TcSmem<TOKT, NSTAGE>) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.here()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // batched-step kernels all ask for the maximum shared-memory carve-out: CTAs of consecutive kernels can then share an SM
     if (batched_carveout() >= 0 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, batched_carveout())) != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.here() = 1;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;

@@ -265,11 +265,11 @@ __global__ void __launch_bounds__(GV_THREADS, (NB == 1) ? 2 : 1) gemv_kernel(Gem
 template <int NB, int P, int E, int NP>
 cudaError_t launch_one(const GemvArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl) {
   auto kern = gemv_kernel<NB, P, E, NP>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.here()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.here() = 1;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);

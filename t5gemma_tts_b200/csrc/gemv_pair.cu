@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemv_pair_kernel(GemvPairArgs a
   pdl_launch_dependents();
   pdl_wait();
   trace_begin(a.trace);
-  if (!any) return;                                        // uniform over the grid: nobody reaches the barrier
+  if (!any) { trace_end(a.trace); return; }                // uniform over the grid: nobody reaches the barrier
   // phase B's weights are requested now (not before the wait: 19 MB of early traffic slowed the attention kernel this
   // grid overlaps with); they have phase A and the barrier to arrive
   if (gw < a.N2) gp_load_row(w2, a.W2 + (size_t)gw * K2, K2 >> 3, lane, pol);
@@ -128,21 +128,30 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemv_pair_kernel(GemvPairArgs a
       const int k = tid + i * GP_THREADS;
       hpre[b][i] = (b < a.B && k < K2) ? __ldcg(a.h_in + (size_t)b * K2 + k) : 0.f;
     }
-  // ---- grid-wide barrier (ticket counter) ----
+  // ---- grid-wide barrier (ticket counter).  The launch is cooperative, so the driver guarantees that all gridDim.x CTAs
+  //      are co-resident (the launch fails otherwise).  The wait is still bounded by time: after one second of
+  //      %globaltimer the step raises the slot's error flag and skips phase B instead of publishing a partial result ----
+  __shared__ int gp_timed_out;
   __syncthreads();                                         // this CTA's y stores are issued; xs is free
   if (tid == 0) {
     __threadfence();                                       // ... and visible before the arrival
     const unsigned long long ticket = atomicAdd(a.barrier, 1ULL);
     const unsigned long long target = (ticket / gridDim.x + 1ULL) * gridDim.x;
-    // bounded spin: if the grid is ever not co-resident (foreign work hogging SMs) the step reports an error through the
-    // slot record instead of hanging the device
-    long long spins = 0;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    int bad = 0;
     while (*reinterpret_cast<volatile unsigned long long*>(a.barrier) < target) {
-      if (++spins > (1LL << 28)) { if (a.err_slots) a.err_slots[0].error |= 4; break; }
+      if ((++spins & 0x3ff) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 1000000000ULL) { if (a.err_slots) atomicOr(&a.err_slots[0].error, 4); bad = 1; break; }
+      }
     }
+    gp_timed_out = bad;
     __threadfence();
   }
   __syncthreads();
+  if (gp_timed_out) { trace_end(a.trace); return; }
 
   // ---- phase B: RMSNorm sandwich (h = h_in + rmsnorm(y) g_post ; x = rmsnorm(h) g_pre), then out = W2 . x ----
   {
@@ -198,22 +207,24 @@ template <int NB>
 cudaError_t launch_gp(const GemvPairArgs& a, int num_sms, cudaStream_t st, bool pdl) {
   auto kern = gemv_pair_kernel<NB>;
   const size_t smem = (size_t)NB * (a.K1 > a.K2 ? a.K1 : a.K2) * sizeof(float);
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
+  static PerDeviceFlag attr_set;
+  if (smem > attr_set.here()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = smem;
+    attr_set.here() = smem;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(num_sms);
   cfg.blockDim = dim3(GP_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;             // co-residency of the grid is requested, not assumed
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 

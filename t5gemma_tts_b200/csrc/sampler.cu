@@ -687,11 +687,11 @@ __global__ void __launch_bounds__(SAMP_THREADS, 1) sampler_kernel(SamplerArgs a)
 
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st, bool pdl) {
   if (a.V > MAX_CHUNKS * CHUNK) return cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  if (!attr_set.here()) {
     cudaError_t e = cudaFuncSetAttribute(sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.here() = 1;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.rows);

@@ -191,7 +191,9 @@ int t5g_abi_version(void);
  * this returns the records of the last executed step in launch order. */
 int t5g_debug_trace(T5GEngine* eng, uint64_t* begin_ns, uint64_t* end_ns, int max_entries, int* n_out);
 int t5g_debug_gemm(T5GEngine* eng, const void* x_bf16 /* dev [M,K] */, const void* w_bf16 /* dev [N,K] */,
-                   float* out /* dev [M,N] */, int M, int N, int K, int impl /* 0 = simt, 1 = tcgen05 */, void* stream);
+                   float* out /* dev [M,N] */, int M, int N, int K,
+                   int impl /* low byte: 0 = simt, 1 = tcgen05; bits 8-15: epilogue (0 fp32 [M,N], 4 bf16 [M,N], 1 GeGLU bf16 [M,N/2]) */,
+                   void* stream);
 /* Prefill attention kernel alone (impl 0 = CUDA-core kernel, 1 = tcgen05 kernel) on caller device buffers: q [Tq, Hq*D],
  * k/v [Tk, Hkv*D] bf16, varlen segments (device int32 arrays: q_seg_off/k_seg_off [n_seg+1], q_seg_of [Tq]), out bf16
  * [Tq, Hq*D].  Geometry (heads, head_dim, scale) comes from the engine config. */

@@ -1136,7 +1136,12 @@ extern "C" int t5g_debug_trace(T5GEngine* e, uint64_t* begin_ns, uint64_t* end_n
 extern "C" int t5g_debug_gemm(T5GEngine* e, const void* x, const void* w, float* out, int M, int N, int K, int impl, void* stream_) {
   T5G_CHECK(e && x && w && out, T5G_ERR_INVALID, "bad arguments");
   T5G_CUDA(cudaSetDevice(e->device));
-  GemmArgs g{(const bf16*)x, (const bf16*)w, M, N, K, GE_F32, nullptr, out, N, 0};
+  // impl: low byte 1 = tcgen05 path, 0 = CUDA-core cross-check; bits 8-15 = epilogue kind (GE_*, no bias; `out` is fp32 [M,N],
+  // bf16 [M,N] for GE_BF16 or bf16 [M,N/2] for GE_GEGLU_BF16)
+  const int epi = (impl >> 8) & 0xff;
+  impl &= 0xff;
+  T5G_CHECK(epi == GE_F32 || ((epi == GE_BF16 || epi == GE_GEGLU_BF16) && impl == 1), T5G_ERR_INVALID, "unsupported debug epilogue %d", epi);
+  GemmArgs g{(const bf16*)x, (const bf16*)w, M, N, K, epi, nullptr, out, epi == GE_GEGLU_BF16 ? N / 2 : N, 0};
   e->launches++;
   CU(impl == 1 ? launch_gemm_tc(g, (cudaStream_t)stream_, e->num_sms) : launch_gemm_simt(g, (cudaStream_t)stream_));
   return T5G_OK;

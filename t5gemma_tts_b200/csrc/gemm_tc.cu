@@ -16,6 +16,7 @@
 #include "tc_common.cuh"
 
 #include <cooperative_groups.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -264,6 +265,201 @@ cudaError_t launch_tc(const CUtensorMap& mw, const CUtensorMap& mx, const TcPara
   return cudaLaunchKernelEx(&cfg, kern, mw, mx, p);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Prefill GEMM (tokens >> 128): persistent CTA PAIRS, tcgen05.mma.cta_group::2, two TMEM accumulators.
+//
+// What the one-tile-per-CTA kernel above left on the table at 8192 tokens (measured, B200): 9 us of fixed cost per 128x256
+// tile (launch, ring fill, a TMEM -> global epilogue that nothing overlaps) against 9.4 us of MMAs at K = 2304, and a main
+// loop that ran at 64 % of the MMA rate: a single SM reads 12 KB of operands per 128-cycle MMA (96 B/clk) while TMA writes
+// 48 KB per K-slab into the same shared memory (96 B/clk) -- together 1.5x the 128 B/clk the SM's shared memory moves.
+// (Multicasting the activation tile over a cluster did not help: it removes L2 reads, not shared-memory traffic.)
+//
+// Here a cluster of two CTAs (the two SMs of a TPC) owns a 256-feature x 256-token tile: each CTA stages ITS 128 weight
+// rows and ITS 128 token rows (32 KB per K-slab instead of 48), the leader's single thread issues 256x256x16 MMAs that
+// read both CTAs' shared memory, and each CTA's TMEM receives its 128 features x 256 tokens.  Pairs are persistent: they
+// walk a rasterised tile list (groups of 8 feature tiles x all token tiles, so a wave re-reads ~2k weight rows and ~2.4k
+// token rows from L2), the 6-stage TMA ring runs ahead across tile boundaries, and the accumulator ping-pongs between
+// TMEM columns [0,256) and [256,512) so the 8 epilogue warps drain tile i while the MMAs of tile i+1 are in flight.
+// Barriers: full[s] lives in the leader (both CTAs' TMA bytes complete there), empty[s] / acc_full[a] are signalled in
+// both CTAs by multicast tcgen05.commit, acc_empty[a] lives in the leader and collects the 16 epilogue warps of the pair.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int P2_TOK = 256;         // tokens per tile (UMMA N)
+constexpr int P2_STAGES = 6;
+constexpr int P2_GROUP = 8;         // feature tiles (of 256) per raster group
+
+struct __align__(1024) Tc2Smem {
+  unsigned char w[P2_STAGES][TC_BM * 128];     // this CTA's 128 weight rows of the K-slab
+  unsigned char x[P2_STAGES][128 * 128];       // this CTA's 128 token rows of the K-slab
+  uint64_t full[P2_STAGES], empty[P2_STAGES], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tc2_tile(int id, int nfp, int mt, int& fp, int& tt) {
+  const int per_group = P2_GROUP * mt;
+  const int g = id / per_group, r = id - g * per_group;
+  const int gw = min(P2_GROUP, nfp - g * P2_GROUP);
+  tt = r / gw;
+  fp = g * P2_GROUP + (r - tt * gw);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  Tc2Smem& S = *reinterpret_cast<Tc2Smem*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nfp = (p.N + 255) / 256, mt = (p.M + P2_TOK - 1) / P2_TOK;
+  const int ntiles = nfp * mt;
+  const int nkb = p.K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P2_STAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&S.acc_full[a], 1); mbar_init(&S.acc_empty[a], 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  if (warp == 1) {      // the same warp of both CTAs allocates all 512 columns in both TMEMs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                  // the peer's barriers exist before anything is signalled on them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = S.tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer (one thread in each CTA) =====
+    if (lane == 0) {
+      pdl_launch_dependents();
+      pdl_wait();
+      trace_begin(p.trace);
+      const uint32_t full_leader = mapa_u32(smem_u32(&S.full[0]), 0);
+      int s = 0; uint32_t round = 0;
+      for (int tile = pair; tile < ntiles; tile += npairs) {
+        int fp, tt;
+        tc2_tile(tile, nfp, mt, fp, tt);
+        const int f0 = fp * 256 + (int)crank * 128, t0 = tt * P2_TOK + (int)crank * 128;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (round > 0) mbar_wait(&S.empty[s], (round - 1) & 1);
+          if (crank == 0) mbar_expect_tx(&S.full[s], 2u * (TC_BM * 128 + 128 * 128));
+          tma_load_2d_cg2(S.w[s], &map_w, kb * TC_BK, f0, full_leader + 8u * s);
+          tma_load_2d_cg2(S.x[s], &map_x, kb * TC_BK, t0, full_leader + 8u * s);
+          if (++s == P2_STAGES) { s = 0; ++round; }
+        }
+      }
+      // drain: the leader's multicast commits of the last ring-full still arrive on THIS CTA's empty barriers
+      for (int i = 0; i < P2_STAGES; ++i) {
+        if (round > 0 || i < s) {                      // slot s was last filled in round (i < s ? round : round - 1)
+          const uint32_t r = (i < s) ? round : round - 1;
+          mbar_wait(&S.empty[i], r & 1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA =====
+    if (lane == 0 && crank == 0) {
+      // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P2_TOK >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int s = 0; uint32_t round = 0, tl = 0;
+      for (int tile = pair; tile < ntiles; tile += npairs, ++tl) {
+        const uint32_t a = tl & 1;
+        if (tl >= 2) {                                 // both CTAs' epilogue warps have drained this accumulator
+          mbar_wait(&S.acc_empty[a], ((tl >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t tmem_d = tmem_base + a * P2_TOK;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&S.full[s], round & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t wa = smem_u32(S.w[s]), xa = smem_u32(S.x[s]);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16_cg2(tmem_d, umma_desc_sw128(wa + k * 32), umma_desc_sw128(xa + k * 32), idesc, (kb | k) ? 1u : 0u);
+          umma_commit_cg2(&S.empty[s], 3);             // slot free in both CTAs once these MMAs have read it
+          if (++s == P2_STAGES) { s = 0; ++round; }
+        }
+        umma_commit_cg2(&S.acc_full[a], 3);            // accumulator complete: wakes both CTAs' epilogue warps
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): this CTA's 128 features x 256 tokens, TMEM -> registers -> global =====
+    const int q = warp & 3;
+    const int fl = q * 32 + lane;
+    const int hsel = (warp - 2) >> 2;                  // warps 2-5: tokens [0,128), warps 6-9: tokens [128,256)
+    const bool even = (lane & 1) == 0;
+    const uint32_t acc_empty_leader = mapa_u32(smem_u32(&S.acc_empty[0]), 0);
+    pdl_wait();                                        // the output buffer may still be read by the previous kernel
+    uint32_t tl = 0;
+    for (int tile = pair; tile < ntiles; tile += npairs, ++tl) {
+      int fp, tt;
+      tc2_tile(tile, nfp, mt, fp, tt);
+      const int f = fp * 256 + (int)crank * 128 + fl, t0 = tt * P2_TOK;
+      const uint32_t a = tl & 1;
+      const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
+      mbar_wait(&S.acc_full[a], (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int ch = hsel * 8; ch < hsel * 8 + 8; ++ch) {
+        const int c = ch * 16;
+        if (t0 + c >= p.M) break;                      // warp-uniform
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + a * P2_TOK + (uint32_t)c, v);
+        switch (p.epilogue) {
+          case GE_F32: store_chunk<GE_F32>(p, v, t0 + c, f, bias, even); break;
+          case GE_BF16: store_chunk<GE_BF16>(p, v, t0 + c, f, bias, even); break;
+          case GE_BIAS_F32: store_chunk<GE_BIAS_F32>(p, v, t0 + c, f, bias, even); break;
+          case GE_BIAS_GELU_BF16: store_chunk<GE_BIAS_GELU_BF16>(p, v, t0 + c, f, bias, even); break;
+          default: store_chunk<GE_GEGLU_BF16>(p, v, t0 + c, f, bias, even); break;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * a);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                  // no MMA of the pair still reads this CTA's shared memory / TMEM
+  trace_end(p.trace);
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// T5G_GEMM_PAIR=0 keeps the one-tile-per-CTA kernel for prefill shapes (A/B measurements)
+bool use_tc2() {
+  static const bool on = [] { const char* v = getenv("T5G_GEMM_PAIR"); return !v || atoi(v) != 0; }();
+  return on;
+}
+
+cudaError_t launch_tc2(const CUtensorMap& mw, const CUtensorMap& mx, const TcParams& p, int num_sms, cudaStream_t st, bool pdl) {
+  const size_t smem = sizeof(Tc2Smem) + 1024;
+  static PerDeviceFlag attr_set;
+  if (!attr_set.here()) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set.here() = 1;
+  }
+  const int ntiles = ((p.N + 255) / 256) * ((p.M + P2_TOK - 1) / P2_TOK);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (unsigned)std::min(num_sms / 2, ntiles));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel, mw, mx, p);
+}
+
 }  // namespace
 
 bool gemm_tc_supported(const GemmArgs& a) {
@@ -293,6 +489,11 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
   }
   TcParams p{a.M, a.N, a.K, a.epilogue, a.bias, a.out, a.ldo, kbps, split, atomic, a.trace, a.probe};
   dim3 grid((a.N + TC_BM - 1) / TC_BM, (a.M + tokt - 1) / tokt, split);
+  if (tokt == 256 && split == 1 && use_tc2()) {            // prefill: persistent CTA pairs
+    CUtensorMap mxh;
+    if (!make_map_2d(&mxh, a.A, a.M, a.K, a.K, 128)) return cudaErrorNotSupported;
+    return launch_tc2(mw, mxh, p, num_sms, st, pdl);
+  }
   switch (tokt) {
     case 16: return launch_tc<16, 8>(mw, mx, p, grid, st, pdl);
     case 32: return launch_tc<32, 8>(mw, mx, p, grid, st, pdl);

@@ -25,6 +25,43 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: the two CTAs of a (2,1,1) cluster sit on the two SMs of one TPC ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair into its OWN shared memory; the bytes complete on `bar_cluster_addr`, which may
+// be the leader CTA's barrier (the single MMA issuer of the pair waits there for both halves)
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+// D[tmem, 128 lanes in EACH CTA] (+)= A[256 x 16: 128 rows from each CTA's shared memory] * B[N x 16: N/2 rows from each]
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+// arrives on the same-offset mbarrier of every CTA in `mask` once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
 // LBO=1 [16,30), SBO = 1024 B >> 4 [32,46), version 1 [46,48), layout SWIZZLE_128B = 2 [61,64)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {

@@ -2,13 +2,19 @@
 // Replaces the q_len>1 uses of HF:modeling_t5gemma.py:209-240 (encoder bidirectional, decoder causal, cross) incl. the
 // Gemma-2 attn-logit softcap and sliding windows.
 //
-// One CTA = 128 queries of one query head of one request.  Keys are processed in blocks of 64 in TWO passes so that no
-// accumulator rescaling is ever needed:
-//   pass 1: S = Q K^T (UMMA, fp32 in TMEM) -> per-row running max / sum (one thread owns one query row = one TMEM lane)
-//   pass 2: S again -> P = exp(S - m) / l as bf16 written by the softmax threads straight into the 128-byte-swizzled
-//           K-major shared-memory layout of a UMMA A operand -> O += P V  (V^T tile as B operand, fp32 O in TMEM)
-// The recomputed Q K^T costs 1.5x the attention flops but keeps the kernel a straight pipeline:
-// TMA producer warp -> MMA issuer thread -> 4 softmax/epilogue warps, all handshakes on mbarriers / tcgen05.commit.
+// One CTA = 128 queries of one query head of one request, ONE pass over the keys in blocks of 64 (online softmax):
+//   S_j = Q K_j^T          UMMA, A = Q and B = K_j from shared memory, fp32 scores in TMEM (two S buffers, ping-pong)
+//   softmax                4 warps, thread = query row = TMEM lane: tcgen05.ld S_j -> scale / softcap / mask -> running max
+//                          in the log2 domain -> P_j = exp2(y - m) as packed bf16 written back with tcgen05.st OVER S_j
+//   O  += P_j V_j          UMMA with the A operand read straight from TMEM (no shared-memory round trip for P), B = V_j^T
+// The MMA thread issues S_{j+1} before it waits for P_j, so the tensor pipe computes the next scores while the softmax
+// warps work on the current ones.  The running max is only raised when it grows by more than 8 (a factor 256 in P, exact in
+// bf16/fp32 range): the O accumulator in TMEM is then rescaled in place by the owning warp, which happens a handful of
+// times per row instead of once per block; the 1/l normalisation is applied in the epilogue.
+// Separate TMA rings for K (3 stages, freed as soon as S_j has been issued and completed) and V^T (2 stages, freed after
+// O += P_j V_j) keep K two blocks ahead of the score MMAs.  Interior key blocks (no causal / window / length edge inside
+// the tile) skip the per-element mask arithmetic.  Softcap uses one MUFU (tanh.approx, rel. error 2^-11 -- below the bf16
+// rounding of P) so a score costs two MUFU operations (tanh, ex2).
 // V is consumed as V^T [Hkv*D, tokens] (K-major B operand); `launch_transpose_v` produces it once per layer.
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -18,17 +24,18 @@ using namespace tc;
 namespace {
 
 constexpr int FA_BQ = 128;       // queries per CTA (UMMA M)
-constexpr int FA_BK = 64;        // keys per block (one 128-byte swizzle atom of P / V^T, UMMA N of the score MMA)
-constexpr int FA_THREADS = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 softmax/epilogue
+constexpr int FA_BK = 64;        // keys per block (one 128-byte swizzle atom of V^T, UMMA N of the score MMA)
+constexpr int FA_KST = 3;        // K ring stages
+constexpr int FA_VST = 2;        // V^T ring stages
+constexpr int FA_THREADS = 224;  // warp 0: Q + K TMA, warp 1: MMA + TMEM alloc, warps 2-5: softmax / epilogue, warp 6: V^T TMA
 
 template <int D>
 struct __align__(1024) FaSmem {
   static constexpr int NA = D / 64;                         // 64-element K atoms along head_dim
   unsigned char q[NA][FA_BQ * 128];                         // Q tile: NA atoms of [128 rows x 128 B]
-  unsigned char k[2][NA][FA_BK * 128];                      // K block stages: NA atoms of [64 keys x 128 B]
-  unsigned char vt[2][D * 128];                             // V^T block stages: [D rows x 64 keys (128 B)]
-  unsigned char p[FA_BQ * 128];                             // P block: [128 queries x 64 keys (128 B)]
-  uint64_t q_full, kv_full[2], kv_empty[2], s_full, sm_done, o_full;
+  unsigned char k[FA_KST][NA][FA_BK * 128];                 // K block stages: NA atoms of [64 keys x 128 B]
+  unsigned char vt[FA_VST][D * 128];                        // V^T block stages: [D rows x 64 keys (128 B)]
+  uint64_t q_full, k_full[FA_KST], k_empty[FA_KST], v_full[FA_VST], v_empty[FA_VST], s_full[2], p_ready[2], pv_done;
   uint32_t tmem_base;
 };
 
@@ -39,6 +46,45 @@ struct FaParams {
   bf16* out;                                               // [Tq, Hq*D]
 };
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+               "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                 "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                 "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem: row m in lane m, 16 bf16 of K packed in 8 columns] * B[smem descriptor]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int D>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -46,7 +92,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   extern __shared__ __align__(1024) unsigned char smraw[];
   FaSmem<D>& S = *reinterpret_cast<FaSmem<D>*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
   constexpr int NA = D / 64;
-  constexpr int O_COL = 0, S_COL = 256;                     // TMEM: O at columns [0,D), S at [256,320) (N-aligned bases)
+  constexpr uint32_t O_COL = 0, S_COL = 256, S_STRIDE = 64;   // TMEM: O at columns [0,D), S/P buffers at [256,320) and [320,384)
   constexpr int TMEM_COLS = 512;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seg = blockIdx.z, h = blockIdx.y, hk = h / (p.Hq / p.Hkv);
@@ -55,17 +101,18 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   const int vt_beg = p.vt_seg_off[seg];
   const int q0 = blockIdx.x * FA_BQ;                        // first query (within the request) of this tile
   if (q0 >= Lq) return;                                     // uniform: tiles beyond this request's length
-  // key range this tile can attend to (block granularity; exact masks are applied per element)
+  // key range this tile can attend to (block granularity; exact masks are applied per element in the edge blocks)
   int k_hi = Lk, k_lo = 0;
   if (p.causal) { k_hi = min(Lk, q0 + FA_BQ); if (p.window > 0) k_lo = max(0, q0 - p.window + 1); }
   else if (p.window > 0) { k_lo = max(0, q0 - p.window); k_hi = min(Lk, q0 + FA_BQ + p.window); }
   const int b0 = k_lo / FA_BK, nb = (k_hi + FA_BK - 1) / FA_BK - b0;      // key blocks [b0, b0+nb)
-  const int nsteps = 2 * nb;
 
   if (threadIdx.x == 0) {
     mbar_init(&S.q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&S.kv_full[i], 1); mbar_init(&S.kv_empty[i], 1); }
-    mbar_init(&S.s_full, 1); mbar_init(&S.sm_done, 128); mbar_init(&S.o_full, 1);
+    for (int i = 0; i < FA_KST; ++i) { mbar_init(&S.k_full[i], 1); mbar_init(&S.k_empty[i], 1); }
+    for (int i = 0; i < FA_VST; ++i) { mbar_init(&S.v_full[i], 1); mbar_init(&S.v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&S.s_full[i], 1); mbar_init(&S.p_ready[i], 128); }
+    mbar_init(&S.pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
@@ -81,126 +128,170 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   const uint32_t tmem = S.tmem_base;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer: Q once, then the K ring =====
+    if (lane == 0 && nb > 0) {
       mbar_expect_tx(&S.q_full, NA * FA_BQ * 128);
       for (int a = 0; a < NA; ++a) tma_load_2d(S.q[a], &map_q, h * D + a * 64, q_beg + q0, &S.q_full);
-      for (int j = 0; j < nsteps; ++j) {
-        const int st = j & 1, f = j >> 1;
-        const bool pass2 = j >= nb;
-        const int blk = b0 + (pass2 ? j - nb : j);
-        if (f >= 1) mbar_wait(&S.kv_empty[st], (f - 1) & 1);
-        mbar_expect_tx(&S.kv_full[st], NA * FA_BK * 128 + (pass2 ? D * 128 : 0));
-        for (int a = 0; a < NA; ++a) tma_load_2d(S.k[st][a], &map_k, hk * D + a * 64, k_beg + blk * FA_BK, &S.kv_full[st]);
-        if (pass2) tma_load_2d(S.vt[st], &map_vt, vt_beg + blk * FA_BK, hk * D, &S.kv_full[st]);   // 16-byte aligned start
+      int st = 0; uint32_t round = 0;
+      for (int j = 0; j < nb; ++j) {
+        if (round > 0) mbar_wait(&S.k_empty[st], (round - 1) & 1);
+        mbar_expect_tx(&S.k_full[st], NA * FA_BK * 128);
+        for (int a = 0; a < NA; ++a) tma_load_2d(S.k[st][a], &map_k, hk * D + a * 64, k_beg + (b0 + j) * FA_BK, &S.k_full[st]);
+        if (++st == FA_KST) { st = 0; ++round; }
+      }
+    }
+  } else if (warp == 6) {
+    // ===== TMA producer: the V^T ring =====
+    if (lane == 0) {
+      for (int j = 0; j < nb; ++j) {
+        const int st = j & 1;
+        if (j >= FA_VST) mbar_wait(&S.v_empty[st], ((j >> 1) - 1) & 1);
+        mbar_expect_tx(&S.v_full[st], D * 128);
+        tma_load_2d(S.vt[st], &map_vt, vt_beg + (b0 + j) * FA_BK, hk * D, &S.v_full[st]);   // 16-byte aligned start
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (lane == 0 && nb > 0) {
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BK >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
       constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
       mbar_wait(&S.q_full, 0);
-      for (int j = 0; j < nsteps; ++j) {
-        const int st = j & 1, f = j >> 1;
-        const bool pass2 = j >= nb;
-        mbar_wait(&S.kv_full[st], f & 1);
-        if (j > 0) mbar_wait(&S.sm_done, (j - 1) & 1);       // softmax threads are done with the previous S
+      int kst = 0; uint32_t kround = 0;
+      auto issue_scores = [&](int j) {
+        mbar_wait(&S.k_full[kst], kround & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem + S_COL + (uint32_t)(j & 1) * S_STRIDE;
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
-          const uint32_t qa = smem_u32(S.q[a]), ka = smem_u32(S.k[st][a]);
+          const uint32_t qa = smem_u32(S.q[a]), ka = smem_u32(S.k[kst][a]);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem + S_COL, umma_desc_sw128(qa + kk * 32), umma_desc_sw128(ka + kk * 32), idesc_s, (a | kk) ? 1u : 0u);
+            umma_bf16(d, umma_desc_sw128(qa + kk * 32), umma_desc_sw128(ka + kk * 32), idesc_s, (a | kk) ? 1u : 0u);
         }
-        umma_commit(&S.s_full);
-        if (!pass2) {
-          umma_commit(&S.kv_empty[st]);
-        } else {
-          mbar_wait(&S.sm_done, j & 1);                      // P block is in shared memory
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t pa = smem_u32(S.p), va = smem_u32(S.vt[st]);
+        umma_commit(&S.k_empty[kst]);
+        umma_commit(&S.s_full[j & 1]);
+        if (++kst == FA_KST) { kst = 0; ++kround; }
+      };
+      issue_scores(0);
+      for (int j = 0; j < nb; ++j) {
+        if (j + 1 < nb) issue_scores(j + 1);                 // runs on the tensor pipe while the softmax warps work on S_j
+        const int b = j & 1;
+        mbar_wait(&S.v_full[b], (j >> 1) & 1);
+        mbar_wait(&S.p_ready[b], (j >> 1) & 1);             // P_j sits in TMEM over S_j
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t pa = tmem + S_COL + (uint32_t)b * S_STRIDE, va = smem_u32(S.vt[b]);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem + O_COL, umma_desc_sw128(pa + kk * 32), umma_desc_sw128(va + kk * 32), idesc_o, (j > nb || kk) ? 1u : 0u);
-          umma_commit(&S.kv_empty[st]);
-        }
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_ts(tmem + O_COL, pa + kk * 8, umma_desc_sw128(va + kk * 32), idesc_o, (j > 0 || kk) ? 1u : 0u);
+        umma_commit(&S.v_empty[b]);
+        umma_commit(&S.pv_done);
       }
-      umma_commit(&S.o_full);
     }
   } else {
     // ===== softmax / epilogue: thread = query row = TMEM lane =====
     const int qtr = warp & 3;
     const int row = qtr * 32 + lane;
     const int qi = q0 + row;                                  // query index inside the request
-    const uint32_t lane_addr = (uint32_t)(qtr * 32) << 16;
-    const float inv_cap = p.softcap > 0.f ? 1.f / p.softcap : 0.f;
-    float m = -INFINITY, l = 0.f, inv_l = 0.f;
-    for (int j = 0; j < nsteps; ++j) {
-      const bool pass2 = j >= nb;
-      const int blk = b0 + (pass2 ? j - nb : j);
-      mbar_wait(&S.s_full, j & 1);
+    const uint32_t lane_addr = tmem + ((uint32_t)(qtr * 32) << 16);
+    constexpr float LOG2E = 1.4426950408889634f;
+    const bool capped = p.softcap > 0.f;
+    const float k_in = capped ? p.scale / p.softcap : p.scale * LOG2E;
+    const float k_out = p.softcap * LOG2E;
+    float m = -INFINITY, l = 0.f;                             // running max (log2 domain) and sum of P
+    for (int j = 0; j < nb; ++j) {
+      const int b = j & 1;
+      const int kb = (b0 + j) * FA_BK, ke = kb + FA_BK - 1;   // first / last key of the block
+      bool interior = ke < Lk;
+      if (p.causal) { interior = interior && ke <= q0; if (p.window > 0) interior = interior && kb > q0 + FA_BQ - 1 - p.window; }
+      else if (p.window > 0) interior = interior && kb >= q0 + FA_BQ - 1 - p.window && ke <= q0 + p.window;
+      mbar_wait(&S.s_full[b], (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float s[FA_BK];
-#pragma unroll
-      for (int c = 0; c < FA_BK; c += 16) tmem_ld16(tmem + lane_addr + (uint32_t)(S_COL + c), s + c);
+      uint32_t r[FA_BK];
+      tmem_ld32_nowait(lane_addr + S_COL + (uint32_t)b * S_STRIDE, r);
+      tmem_ld32_nowait(lane_addr + S_COL + (uint32_t)b * S_STRIDE + 32, r + 32);
+      tmem_ld_wait();
       float bm = -INFINITY;
+      if (interior) {
 #pragma unroll
-      for (int c = 0; c < FA_BK; ++c) {
-        const int kk = blk * FA_BK + c;
-        bool ok = kk < Lk && qi < Lq;
-        if (p.causal) { ok = ok && kk <= qi; if (p.window > 0) ok = ok && kk > qi - p.window; }
-        else if (p.window > 0) ok = ok && (kk >= qi - p.window) && (kk <= qi + p.window);
-        float v = s[c] * p.scale;
-        if (p.softcap > 0.f) { const float e2 = __expf(2.f * v * inv_cap); v = p.softcap * (1.f - __fdividef(2.f, e2 + 1.f)); }
-        s[c] = ok ? v : -INFINITY;
-        bm = fmaxf(bm, s[c]);
-      }
-      if (!pass2) {
-        const float mn = fmaxf(m, bm);
-        if (mn > -INFINITY) {
-          float acc = 0.f;
-#pragma unroll
-          for (int c = 0; c < FA_BK; ++c) acc += __expf(s[c] - mn);
-          l = l * __expf(m - mn) + acc;
-          m = mn;
+        for (int c = 0; c < FA_BK; ++c) {
+          float v = __uint_as_float(r[c]) * k_in;
+          if (capped) v = tanh_approx(v) * k_out;
+          r[c] = __float_as_uint(v);
+          bm = fmaxf(bm, v);
         }
-        if (j == nb - 1) inv_l = l > 0.f ? 1.f / l : 0.f;
       } else {
-        // P row -> bf16 -> swizzled K-major smem (chunk c16 of row r lives at ((c16 ^ (r & 7)) * 16)
-        unsigned char* prow = S.p + row * 128;
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
+        for (int c = 0; c < FA_BK; ++c) {
+          const int kk = kb + c;
+          bool ok = kk < Lk;
+          if (p.causal) { ok = ok && kk <= qi; if (p.window > 0) ok = ok && kk > qi - p.window; }
+          else if (p.window > 0) ok = ok && (kk >= qi - p.window) && (kk <= qi + p.window);
+          float v = __uint_as_float(r[c]) * k_in;
+          if (capped) v = tanh_approx(v) * k_out;
+          v = ok ? v : -INFINITY;
+          r[c] = __float_as_uint(v);
+          bm = fmaxf(bm, v);
+        }
+      }
+      // lazy running max: raise it only when it would grow by more than 8 (P stays <= 2^8)
+      const float mn = fmaxf(m, bm);
+      float alpha = 1.f;
+      bool raise = false;
+      if (m == -INFINITY) m = mn;                             // nothing accumulated for this row yet (its O row is 0)
+      else if (mn > m + 8.f) { alpha = ex2_approx(m - mn); m = mn; raise = true; }
+      if (__any_sync(0xffffffffu, raise)) {                   // rescale this warp's O rows in place (rare)
+        l *= alpha;
+        mbar_wait(&S.pv_done, (j - 1) & 1);                   // O += P_{j-1} V_{j-1} has landed; P_j V_j is not issued yet
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+          uint32_t o[32];
+          tmem_ld32_nowait(lane_addr + O_COL + (uint32_t)c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * alpha);
+          tmem_st32(lane_addr + O_COL + (uint32_t)c, o);
+        }
+        tmem_st_wait();
+      }
+      const float ms = (m == -INFINITY) ? 0.f : m;
+      float sum = 0.f;
+      uint32_t pk[FA_BK / 2];
+#pragma unroll
+      for (int c = 0; c < FA_BK; c += 2) {
+        const float a = ex2_approx(__uint_as_float(r[c]) - ms), bb = ex2_approx(__uint_as_float(r[c + 1]) - ms);
+        sum += a + bb;
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(a, bb);
+        pk[c >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+      }
+      l += sum;
+      tmem_st32(lane_addr + S_COL + (uint32_t)b * S_STRIDE, pk);   // P_j (bf16 pairs) over the first 32 columns of S_j
+      tmem_st_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.p_ready[b])) : "memory");
+    }
+    // epilogue: O / l -> bf16 -> out[token][h*D + d]
+    if (nb > 0) {
+      mbar_wait(&S.pv_done, (nb - 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    bf16* orow = p.out + (size_t)(q_beg + min(qi, Lq - 1)) * p.Hq * D + (size_t)h * D;
+#pragma unroll 1
+    for (int c = 0; c < D; c += 32) {
+      uint32_t o[32];
+      if (nb > 0) { tmem_ld32_nowait(lane_addr + O_COL + (uint32_t)c, o); tmem_ld_wait(); }   // .sync.aligned: whole warp
+      if (qi < Lq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
           uint32_t w[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float a = (m > -INFINITY) ? __expf(s[c16 * 8 + 2 * t] - m) * inv_l : 0.f;
-            const float b = (m > -INFINITY) ? __expf(s[c16 * 8 + 2 * t + 1] - m) * inv_l : 0.f;
-            __nv_bfloat162 pk = __floats2bfloat162_rn(a, b);
-            w[t] = *reinterpret_cast<uint32_t*>(&pk);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o[g * 8 + 2 * t]) * inv_l, __uint_as_float(o[g * 8 + 2 * t + 1]) * inv_l);
+            w[t] = (nb > 0) ? *reinterpret_cast<uint32_t*>(&t2) : 0u;
           }
-          *reinterpret_cast<uint4*>(prow + ((c16 ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          reinterpret_cast<uint4*>(orow + c)[g] = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> tcgen05 (async proxy) reads
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.sm_done)) : "memory");
-    }
-    // epilogue: O (already normalised) -> bf16 -> out[token][h*D + d]
-    mbar_wait(&S.o_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    bf16* orow = p.out + (size_t)(q_beg + min(qi, Lq - 1)) * p.Hq * D + (size_t)h * D;
-#pragma unroll 1
-    for (int c = 0; c < D; c += 16) {
-      float v[16];
-      tmem_ld16(tmem + lane_addr + (uint32_t)(O_COL + c), v);          // .sync.aligned: executed by the whole warp
-      if (qi < Lq) {
-        uint32_t w[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) { __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]); w[t] = *reinterpret_cast<uint32_t*>(&pk); }
-        reinterpret_cast<uint4*>(orow + c)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        reinterpret_cast<uint4*>(orow + c)[1] = make_uint4(w[4], w[5], w[6], w[7]);
       }
     }
   }

@@ -71,11 +71,14 @@ ATTN_CASES = [
     (256, 8, 4, [300], [300], False, 37, 0.0),                 # bidirectional window
     (256, 8, 4, [152, 20], [64, 96], False, 0, 50.0),          # cross-attention shapes
     (128, 4, 4, [257], [257], True, 0, 5.0),
+    (256, 8, 4, [300, 200], [300, 200], True, 0, 0.0, 0, 8.0),   # wide score spread: running-max raises rescale O in TMEM
+    (256, 8, 4, [300], [300], False, 0, 50.0, 0, 30.0),          # scores saturating the softcap
+    (64, 4, 2, [200], [700], False, 0, 0.0, 1, 6.0),             # 11 key blocks, K ring wraps several times
 ]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ATTN_CASES, ids=[f"D{c[0]}-q{'_'.join(map(str, c[3]))}-c{int(c[5])}w{c[6]}" for c in ATTN_CASES])
+@pytest.mark.parametrize("case", ATTN_CASES, ids=[f"D{c[0]}-q{'_'.join(map(str, c[3]))}-c{int(c[5])}w{c[6]}" + ("-wide" if len(c) > 8 else "") for c in ATTN_CASES])
 def test_prefill_attention_vs_torch(case):
     """Both prefill attention kernels (CUDA-core varlen and the tcgen05/TMA one) against an fp32 torch softmax(QK^T)V with
     the reference's masks (modeling_t5gemma_voice.py make_attention_mask / sliding window) and softcap."""

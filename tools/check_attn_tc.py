@@ -37,14 +37,14 @@ def ref_attention(q, k, v, q_off, k_off, Hq, Hkv, D, causal, window, scale, soft
     return out
 
 
-def run(D, Hq, Hkv, q_lens, k_lens, causal, window, softcap, seed=0):
+def run(D, Hq, Hkv, q_lens, k_lens, causal, window, softcap, seed=0, qscale=1.0):
     cfg = EngineConfig(hidden=256, inter=512, n_enc_layers=1, n_dec_layers=1, n_heads=Hq, n_kv_heads=Hkv, head_dim=D,
                        query_pre_attn_scalar=float(D), text_vocab=64, audio_vocab=64, max_slots=1, max_text_len=64,
                        max_dec_len=64, max_prefill_tokens=max(sum(q_lens), sum(k_lens)) + 64)
     eng = T5GemmaVoiceEngine(cfg)
     g = torch.Generator(device="cuda").manual_seed(seed)
     Tq, Tk = sum(q_lens), sum(k_lens)
-    q = torch.randn(Tq, Hq * D, device="cuda", generator=g).to(torch.bfloat16)
+    q = (torch.randn(Tq, Hq * D, device="cuda", generator=g) * qscale).to(torch.bfloat16)   # qscale > 1: score spread that forces running-max raises
     k = torch.randn(Tk, Hkv * D, device="cuda", generator=g).to(torch.bfloat16)
     v = torch.randn(Tk, Hkv * D, device="cuda", generator=g).to(torch.bfloat16)
     q_off = np.concatenate([[0], np.cumsum(q_lens)]).astype(np.int32)
@@ -103,4 +103,6 @@ if __name__ == "__main__":
         run(256, 8, 4, [300], [300], False, 37, 0.0)
         run(256, 8, 4, [152, 20], [64, 96], False, 0, 50.0)          # cross attention shapes
         run(128, 4, 4, [257], [257], True, 0, 5.0)
+        run(256, 8, 4, [300, 200], [300, 200], True, 0, 0.0, 0, 8.0)     # wide score spread: O rescale path
+        run(256, 8, 4, [300], [300], False, 0, 50.0, 0, 30.0)
         run(256, 8, 4, [512] * 16, [512] * 16, False, 4096, 50.0)    # configs[4] encoder layer

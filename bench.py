@@ -501,7 +501,7 @@ def main():
     if not args.no_extra and world == 1:
         try:
             B, S = 16, 512
-            cfgL = engine_config(B, max_text_len=S, max_dec_len=256, max_prefill_tokens=B * S)
+            cfgL = engine_config(B, max_text_len=S, max_dec_len=512, max_prefill_tokens=B * S)
             engL = new_engine(cfgL, dev)
             rng = np.random.default_rng(5)
             reqs = [GenerationRequest(text_ids=rng.integers(2, 255000, S), prompt_ids=np.zeros(0, np.int64), target_total=100,

@@ -5,7 +5,8 @@
 // instructions per warp, 1-2 warps per scheduler, < 1 % of the time waiting on memory).  Here the CTA of a
 // (request, kv head, split) walks its key range in tiles of 32 tokens:
 //   * K/V rows travel with cp.async into a 2-stage shared-memory ring (first tiles issued BEFORE
-//     griddepcontrol.wait; rows padded by 16 bytes so ldmatrix is conflict-free);
+//     griddepcontrol.wait; rows padded by 16 bytes so ldmatrix is conflict-free); the page lookups of the whole range
+//     are resolved once before the loop;
 //   * scores  S^T[token, head] = K_tile . Q^T  on mma.sync m16n8k16 (the G query heads of the group sit in the
 //     n = 8 columns), scale / softcap / mask in the accumulator registers;
 //   * one online-softmax update per tile and head (warp h owns head h), probabilities rounded to bf16 like the
@@ -14,6 +15,12 @@
 // ~120 instructions per warp per 32 tokens.  tcgen05 is not used: the useful M is G = 2 rows and the work is
 // bandwidth / latency bound.  Same fused glue as attention.cu: PM-RoPE of q and of the new k, in-place KV
 // append, split-KV merge of the NS CTAs of a cluster through distributed shared memory.
+// Chunked mode (the batched step's default): blockIdx.y = chunk.  A row's key range is cut into ceil(range / chunk_tokens)
+// equal pieces, so a step's attention is dealt in pieces of similar size whatever the spread of the rows' contexts (one
+// CTA per row made the kernel as long as its longest row: 53.6 -> 32.6 us per layer at contexts U[0,900), +27 % on a
+// ragged job); the chunks of a (row, kv head) park (m, l, O) in global scratch and the last one to arrive merges them.
+// Measured and rejected for the tile loads: one producer warp issuing the 16-byte cp.async (63.6 us: a single warp's
+// instruction stream is too slow) and one cp.async.bulk per 512-byte row (38.9 us: 64 small bulk copies per tile).
 #include "kernels.h"
 #include <cooperative_groups.h>
 
@@ -24,6 +31,8 @@ constexpr int AM_TT = 32;                 // tokens per tile
 constexpr int AM_NST = 2;                 // ring stages
 constexpr int AM_MAX_NS = 8;
 constexpr int AM_BT_CACHE = 256;
+constexpr int AM_ROWS_PRE = 512;          // key ranges up to this length resolve their page lookups once, before the tile loop
+constexpr int AM_MAX_CHUNKS = 16;         // chunked mode: chunks per (row, kv head)
 
 __device__ __forceinline__ void am_cp_async16(void* dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;          // src-size 0: zero fill (rows past the key range must not hold NaN bit patterns)
@@ -81,7 +90,10 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   __shared__ float scp[2][G][AM_TT];                                    // partial q.k of the two k-halves
   __shared__ float corr_s[8];
   __shared__ unsigned rowoff[AM_NST][AM_TT];                            // row offsets (elements) inside the layer's K plane
+  __shared__ unsigned rowoff_all[AM_ROWS_PRE];                          // ... of the whole key range when it is short enough
   __shared__ float ml_s[G][2];
+  __shared__ float cw_s[AM_MAX_CHUNKS][G], cl_s[AM_MAX_CHUNKS][G];      // chunked mode: merge weights / sums of the chunks
+  __shared__ int last_s;
   float* recv_o = reinterpret_cast<float*>(am_dyn + Geo::ring_bytes(G)); // [NS][G][D]  (src rank, g, dslice; NS > 1 only)
   float* recv_ml = recv_o + (size_t)a.n_splits * G * D;                 // [NS][G][2]
   float* f_wt = recv_ml + (size_t)a.n_splits * G * 2;                   // [NS][G]
@@ -119,6 +131,12 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
   int chunk = (L - lo + NS - 1) / NS;
   chunk = (chunk + 15) / 16 * 16;
+  int n_chunks = 1;
+  if (a.chunk_tokens > 0) {                                 // chunked mode: equal pieces of at most chunk_tokens keys, NS == 1
+    n_chunks = min(max((L - lo + a.chunk_tokens - 1) / a.chunk_tokens, 1), a.max_chunks);
+    if (!active || split >= n_chunks) return;               // nothing to do for this CTA (exited CTAs release the dependents)
+    chunk = ((L - lo + n_chunks - 1) / n_chunks + AM_TT - 1) / AM_TT * AM_TT;
+  }
   const int t_begin = lo + split * chunk, t_end = min(L, t_begin + chunk);
   const bool has_new = (!a.is_cross) && (t_end == L) && (t_end > t_begin);
   const int n_tiles = (t_end > t_begin) ? (t_end - t_begin + AM_TT - 1) / AM_TT : 0;
@@ -130,23 +148,39 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   // (the naive per-chunk address computation made the ISSUE loop the critical path: 3.7 us per 32-token tile).
   const bf16* kbase = a.pool.ptr(a.layer, 0, 0);
   const size_t kv_stride = (size_t)a.pool.n_pages * a.pool.page_elems();
+  // row offsets of the whole key range, resolved once (a chunk is at most AM_ROWS_PRE keys unless chunking is off)
+  const bool ro_pre = n_tiles * AM_TT <= AM_ROWS_PRE;
+  if (ro_pre) {
+    for (int i = tid; i < n_tiles * AM_TT; i += AM_NT) {
+      const int t = t_begin + i;
+      const bool valid = t < t_end && !(has_new && t == L - 1);
+      unsigned ro = 0xFFFFFFFFu;
+      if (valid) { const int page = page_of(t), off = t % PT; ro = (unsigned)((size_t)page * a.pool.page_elems() + ((size_t)hk * PT + off) * D); }
+      rowoff_all[i] = ro;
+    }
+    __syncthreads();
+  }
   auto issue_tile = [&](int ti) {
     if (ti < n_tiles) {                                       // CTA-uniform
       const int stage = ti % AM_NST;
-      if (tid < AM_TT) {
-        const int t = t_begin + ti * AM_TT + tid;
-        const bool valid = t < t_end && !(has_new && t == L - 1);
-        unsigned ro = 0xFFFFFFFFu;
-        if (valid) { const int page = page_of(t), off = t % PT; ro = (unsigned)((size_t)page * a.pool.page_elems() + ((size_t)hk * PT + off) * D); }
-        rowoff[stage][tid] = ro;
+      const unsigned* ro_t = rowoff_all + ti * AM_TT;
+      if (!ro_pre) {
+        if (tid < AM_TT) {
+          const int t = t_begin + ti * AM_TT + tid;
+          const bool valid = t < t_end && !(has_new && t == L - 1);
+          unsigned ro = 0xFFFFFFFFu;
+          if (valid) { const int page = page_of(t), off = t % PT; ro = (unsigned)((size_t)page * a.pool.page_elems() + ((size_t)hk * PT + off) * D); }
+          rowoff[stage][tid] = ro;
+        }
+        __syncthreads();
+        ro_t = rowoff[stage];
       }
-      __syncthreads();
       constexpr int CPR = D / 8;                              // 16-byte chunks per row
       bf16* kst = stage_ptr(stage, 0);
 #pragma unroll 4
       for (int c = tid; c < AM_TT * CPR * 2; c += AM_NT) {
         const int tok = c / (2 * CPR), rem = c - tok * (2 * CPR), kv = rem / CPR, col = rem - kv * CPR;
-        const unsigned ro = rowoff[stage][tok];
+        const unsigned ro = ro_t[tok];
         const bool valid = ro != 0xFFFFFFFFu;                 // rows past the range / the new token: zero fill
         am_cp_async16(kst + (size_t)kv * AM_TT * LD + (size_t)tok * LD + col * 8,
                       kbase + (kv ? kv_stride : 0) + (valid ? ro : 0u) + col * 8, valid);
@@ -154,7 +188,7 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
     }
     asm volatile("cp.async.commit_group;" ::: "memory");   // one group per tile, empty ones included
   };
-  if (active) {
+  if (active) {                                               // in flight while the producer kernel is still running
 #pragma unroll
     for (int s_ = 0; s_ < AM_NST; ++s_) issue_tile(s_);
   }
@@ -306,6 +340,80 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   AM_PROBE(8);
 
   if (warp < G && lane == 0) { ml_s[warp][0] = m_run; ml_s[warp][1] = l_run; }
+  if (n_chunks > 1) {
+    // ---- chunked mode, several chunks in this row's range: park the unnormalised partial, last arriver merges ----
+    const size_t slot = ((size_t)b * a.Hkv + hk) * AM_MAX_CHUNKS;
+    float* po = a.part_o + (slot + split) * G * D;
+#pragma unroll
+    for (int i = 0; i < MTW; ++i) {
+      const int mt = warp + i * AM_WARPS;
+      if (mt < NMT) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int head = 2 * t4 + (r & 1), dim = mt * 16 + g8 + (r >> 1) * 8;
+          if (head < G) __stcg(po + head * D + dim, acc[i][r]);
+        }
+      }
+    }
+    if (warp < G && lane == 0) { __stcg(a.part_ml + ((slot + split) * G + warp) * 2, m_run); __stcg(a.part_ml + ((slot + split) * G + warp) * 2 + 1, l_run); }
+    __syncthreads();
+    // one acq_rel atomic by thread 0 orders the CTA's partial (observed through the barrier above) before the count and
+    // the other chunks' partials before this CTA's reads below -- no membar.gl by all 256 threads
+    if (tid == 0) {
+      unsigned old;
+      asm volatile("atom.add.acq_rel.gpu.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.part_cnt + (size_t)b * a.Hkv + hk) : "memory");
+      last_s = (old == (unsigned)(n_chunks - 1));
+    }
+    __syncthreads();
+    if (!last_s) { trace_end(a.trace); return; }
+    if (tid == 0) a.part_cnt[(size_t)b * a.Hkv + hk] = 0;   // every chunk has arrived: ready for the next launch
+    // partial outputs first (independent loads, in flight while the weights are computed)
+    constexpr int OPT = (G * D + AM_NT - 1) / AM_NT;
+    float po_r[OPT][AM_MAX_CHUNKS];
+#pragma unroll
+    for (int u = 0; u < OPT; ++u)
+#pragma unroll
+      for (int c = 0; c < AM_MAX_CHUNKS; ++c) {
+        const int i = tid + u * AM_NT;
+        po_r[u][c] = (c < n_chunks && i < G * D) ? __ldcg(a.part_o + (slot + c) * G * D + i) : 0.f;
+      }
+    if (tid < G * AM_MAX_CHUNKS) {                            // (chunk, head) -> m and l, one load each
+      const int c = tid / G, g = tid % G;
+      const bool ok = c < n_chunks;
+      cw_s[c][g] = ok ? __ldcg(a.part_ml + ((slot + c) * G + g) * 2) : -INFINITY;
+      cl_s[c][g] = ok ? __ldcg(a.part_ml + ((slot + c) * G + g) * 2 + 1) : 0.f;
+    }
+    __syncthreads();
+    if (tid < G) {
+      float M = -INFINITY;
+      for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, cw_s[c][tid]);
+      float den = 0.f;
+      for (int c = 0; c < n_chunks; ++c) {
+        const float m = cw_s[c][tid];
+        const float wt = (m == -INFINITY) ? 0.f : __expf(m - M);
+        den = fmaf(wt, cl_s[c][tid], den);
+        cw_s[c][tid] = wt;
+      }
+      const float inv = den > 0.f ? 1.f / den : 0.f;
+      for (int c = 0; c < n_chunks; ++c) cw_s[c][tid] *= inv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < OPT; ++u) {
+      const int i = tid + u * AM_NT;
+      if (i >= G * D) break;
+      const int g = i / D;
+      float o = 0.f;
+#pragma unroll
+      for (int c = 0; c < AM_MAX_CHUNKS; ++c) if (c < n_chunks) o = fmaf(cw_s[c][g], po_r[u][c], o);
+      const size_t idx = (size_t)b * a.Hq * D + (size_t)(hk * G) * D + i;
+      if (a.out) a.out[idx] = o;
+      if (a.out_bf) a.out_bf[idx] = __float2bfloat16(o);
+    }
+    AM_PROBE(10);
+    trace_end(a.trace);
+    return;
+  }
   if (NS == 1) {
     // ---- no split: normalise and store straight from the accumulator registers ----
     __syncthreads();
@@ -400,7 +508,7 @@ cudaError_t launch_am(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
     attr_set.here() = smem;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(a.Hkv, a.n_splits, a.B);
+  cfg.gridDim = dim3(a.Hkv, a.chunk_tokens > 0 ? a.max_chunks : a.n_splits, a.B);
   cfg.blockDim = dim3(AM_NT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -419,6 +527,8 @@ cudaError_t launch_am(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
 bool attn_decode_mma_supported(const AttnDecodeArgs& a) {
   const int G = a.Hkv > 0 ? a.Hq / a.Hkv : 0;
   const bool d_ok = a.D == 16 || a.D == 32 || a.D == 64 || a.D == 128 || a.D == 256;
+  if (a.chunk_tokens > 0 && (a.n_splits != 1 || a.chunk_tokens % AM_TT || a.max_chunks < 1 || a.max_chunks > AM_MAX_CHUNKS ||
+                             !a.part_o || !a.part_ml || !a.part_cnt)) return false;
   return d_ok && (G == 1 || G == 2 || G == 4) && a.n_splits >= 1 && a.n_splits <= AM_MAX_NS &&
          !(a.n_splits & (a.n_splits - 1)) && a.D % a.n_splits == 0;
 }

@@ -93,8 +93,12 @@ struct T5GEngine {
   unsigned long long* d_trace = nullptr; bool use_trace = false;    // [2][T5G_TRACE_STRIDE] begin/end timestamps
   int ns_self = 8, ns_cross = 2;
   int h_end = 0;                                               // which h buffer holds the residual at step end
-  cudaGraphExec_t step_graph = nullptr; cudaStream_t graph_built_for = nullptr; int nodes_per_step = 0;
-  cudaGraphExec_t multi_graph = nullptr; int nodes_multi = 0, graph_steps = 4;
+  // decode graphs, keyed by (steps per graph, self-attention chunks, cross-attention chunks): the chunk counts are grid
+  // dimensions of the batched attention kernels and follow the longest live row
+  struct StepGraph { cudaGraphExec_t exec = nullptr; int nodes = 0; };
+  std::map<int, StepGraph> graphs; int graph_steps = 4;
+  int attn_chunk = 256, chunks_self = 1, chunks_cross = 1;    // batched rows: keys per attention CTA, current grid.y
+  float *d_part_o = nullptr, *d_part_ml = nullptr; int* d_part_cnt = nullptr;
   int last_nodes_per_step = 0;
   int *d_order_self = nullptr, *d_order_cross = nullptr;                 // batched attention: rows by descending length
   unsigned long long* d_barrier = nullptr; bool use_pair = true;         // o_proj + cross q_proj in one kernel (gemv_pair.cu)
@@ -334,6 +338,18 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
     T5G_CUDA(cudaMemcpy(e->d_order_self, id.data(), sizeof(int) * B, cudaMemcpyHostToDevice));
     T5G_CUDA(cudaMemcpy(e->d_order_cross, id.data(), sizeof(int) * B, cudaMemcpyHostToDevice)); }
   DM(e->d_xn, (size_t)B * d); DM(e->d_attn_bf, (size_t)B * QD); DM(e->d_act_bf, (size_t)B * I); DM(e->d_t1_bf, (size_t)B * d);
+  if (B > 4) {
+    // chunked attention of the batched step: <= 16 chunks of attn_chunk keys per (row, kv head)
+    if (const char* s = getenv("T5G_ATTN_CHUNK")) e->attn_chunk = atoi(s);
+    if (e->attn_chunk > 0) {
+      e->attn_chunk = std::max(32, (e->attn_chunk + 31) / 32 * 32);
+      const int longest = std::max(cfg->max_dec_len, cfg->max_text_len);
+      while (cdiv(longest, e->attn_chunk) > 16) e->attn_chunk += 32;
+      DM(e->d_part_o, (size_t)B * e->Hkv * 16 * (e->Hq / e->Hkv) * D); DM(e->d_part_ml, (size_t)B * e->Hkv * 16 * (e->Hq / e->Hkv) * 2);
+      DM(e->d_part_cnt, (size_t)B * e->Hkv);
+      T5G_CUDA(cudaMemset(e->d_part_cnt, 0, sizeof(int) * (size_t)B * e->Hkv));
+    }
+  }
   T5G_CUDA(cudaDeviceSynchronize());
   return T5G_OK;
 }
@@ -342,8 +358,7 @@ extern "C" int t5g_destroy(T5GEngine* e) {
   if (!e) return T5G_OK;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
-  if (e->multi_graph) cudaGraphExecDestroy(e->multi_graph);
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_mirror) cudaFreeHost(e->h_mirror);
   if (e->h_tokens) cudaFreeHost(e->h_tokens);
@@ -836,6 +851,8 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
       a.row_order = e->d_order_self;
+      a.n_splits = 1;   // batched rows: key ranges are cut into chunks (grid.y), not into cluster splits
+      if (e->attn_chunk > 0) { a.chunk_tokens = e->attn_chunk; a.max_chunks = e->chunks_self; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml; a.part_cnt = e->d_part_cnt; }
       a.probe = (e->use_trace && l == 5) ? e->d_trace + 300 : nullptr;
       a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = 1; a.mma = e->attn_mma; a.trace = next_trace();
       if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
@@ -847,6 +864,8 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
       a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
       a.row_order = e->d_order_cross;
+      a.n_splits = 1;
+      if (e->attn_chunk > 0) { a.chunk_tokens = e->attn_chunk; a.max_chunks = e->chunks_cross; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml; a.part_cnt = e->d_part_cnt; }
       a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = 1; a.mma = e->attn_mma; a.trace = next_trace();
       if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
       nl++; }
@@ -880,6 +899,18 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
     std::stable_sort(oc.begin(), oc.end(), [&](int x, int y) { return lc[x] > lc[y]; });
     CU(cudaMemcpyAsync(e->d_order_self, os.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(e->d_order_cross, oc.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+    if (e->attn_chunk > 0) {
+      // grid.y of the attention kernels: enough chunks for the longest row at the END of this call (a row that outgrows
+      // the bound is still computed correctly: its last chunk takes the remainder)
+      int longest = 1, longest_text = 1;
+      for (int s = 0; s < B; ++s) if (e->hslots[s].in_use) {
+        longest = std::max(longest, ls[s] + (e->decode_pending ? e->pending_steps : 0) + max_steps + 1);
+        longest_text = std::max(longest_text, lc[s]);
+      }
+      longest = std::min(longest, e->c.max_dec_len);
+      e->chunks_self = std::min(16, cdiv(longest, e->attn_chunk));
+      e->chunks_cross = std::min(16, cdiv(longest_text, e->attn_chunk));
+    }
   }
   auto enqueue = [&](cudaStream_t s_, int* nl) -> int {
     return (e->c.max_slots > 4) ? enqueue_step_batched(e, s_, nl) : enqueue_step(e, s_, nl);
@@ -888,7 +919,8 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
     // one graph = one step, plus a graph of `graph_steps` consecutive steps: inside it the head of step t+1 is a
     // programmatic dependent of the last kernel of step t, which removes the ~20 us gap between graph launches
     auto get_graph = [&](cudaGraphExec_t& graph, int& nodes, int steps) -> int {
-      if (graph) return T5G_OK;
+      T5GEngine::StepGraph& sg = e->graphs[(steps * 32 + e->chunks_self) * 32 + e->chunks_cross];
+      if (sg.exec) { graph = sg.exec; nodes = sg.nodes; return T5G_OK; }
       cudaStream_t cs;
       CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
       int nl_total = 0;
@@ -903,13 +935,12 @@ extern "C" int t5g_decode(T5GEngine* e, int max_steps, void* stream_) {
       cudaGraphDestroy(g);
       cudaStreamDestroy(cs);
       nodes = nl_total;
+      sg.exec = graph; sg.nodes = nodes;
       return T5G_OK;
     };
     const int MS = (e->use_trace || e->graph_steps < 2) ? 1 : e->graph_steps;
-    cudaGraphExec_t& g1 = e->step_graph;
-    int& n1 = e->nodes_per_step;
-    cudaGraphExec_t& gm = e->multi_graph;
-    int& nm = e->nodes_multi;
+    cudaGraphExec_t g1 = nullptr, gm = nullptr;
+    int n1 = 0, nm = 0;
     int done = 0;
     if (MS > 1 && max_steps >= MS) {
       int rc = get_graph(gm, nm, MS);

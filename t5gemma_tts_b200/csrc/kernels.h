@@ -68,6 +68,14 @@ struct AttnDecodeArgs {
   unsigned long long* trace;
   unsigned long long* probe;               // optional [B][11] in-kernel checkpoints of the (kv head 0, split 0) CTAs (debug)
   const int* row_order;                    // optional [B]: blockIdx.z -> row; longest rows first so they are scheduled first
+  // chunked mode of the tile kernel (batched rows): blockIdx.y = chunk of `chunk_tokens` keys of the row's range, so the
+  // work of a step is dealt in equal pieces whatever the spread of the rows' contexts; the chunks of a (row, kv head)
+  // leave their partial (m, l, O) in global scratch and the last one to arrive merges them (arrival counter, self-resetting)
+  int chunk_tokens;                        // 0: off (one CTA per split as above); else a multiple of 32, n_splits must be 1
+  int max_chunks;                          // grid.y; chunks past a row's range exit at once (<= 16)
+  float* part_o;                           // [B][Hkv][16][G][D] unnormalised partial outputs
+  float* part_ml;                          // [B][Hkv][16][G][2] running max / sum of every chunk
+  int* part_cnt;                           // [B][Hkv] arrival counters, zero between launches
 };
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
 bool attn_decode_mma_supported(const AttnDecodeArgs& a);

@@ -25,10 +25,11 @@ __global__ void embed_slots_kernel(const bf16* __restrict__ table, const SlotDev
 // one CTA per token: h_out = h_in + rmsnorm(y)*g_post ; xn/xf = rmsnorm(h_out)*g_pre  (HF:66-74 in fp32).
 // Single reduction pass: with r = rsqrt(mean(y^2)+eps), sum(h + y r g)^2 = S2 + 2 r S3 + r^2 S4; all loads are
 // 128-bit and issued before the reduction; the gains are fetched before griddepcontrol.wait (PDL).
-constexpr int NK_THREADS = 512;
-constexpr int NK_MAXV = 2;                       // float4 per thread: d <= 512*4*2 = 4096
+// Two shapes: 512 threads x 2 float4 for the batched decode step (few rows: the row's latency is what counts) and
+// 192 threads x 4 float4 for prefill (thousands of rows: d = 2304 is exactly 3 float4 per thread, ten CTAs per SM).
 // (activations are read with ld.global.cg: under PDL this kernel is launched while its producer is still running, so
 // they must not come from the non-coherent read-only path)
+template <int NK_THREADS, int NK_MAXV>
 __global__ void __launch_bounds__(NK_THREADS) norm_kernel(const float* h_in, const float* y,
                                                           const float* __restrict__ g_post, const float* __restrict__ g_pre,
                                                           float* h_out, bf16* xn, float* xf, int d, float eps,
@@ -280,10 +281,11 @@ cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, 
                         bf16* xn, float* xf, int M, int d, float eps, cudaStream_t st, bool pdl,
                         float* zero_a, int na, float* zero_b, int nb, unsigned long long* trace) {
   if (M <= 0) return cudaSuccess;
-  if (d % 4 != 0 || d > NK_THREADS * 4 * NK_MAXV || (na & 3) || (nb & 3)) return cudaErrorInvalidValue;
+  if (d % 4 != 0 || d > 512 * 4 * 2 || (na & 3) || (nb & 3)) return cudaErrorInvalidValue;
+  const bool many = M >= 1024 && d <= 192 * 4 * 4;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(M);
-  cfg.blockDim = dim3(NK_THREADS);
+  cfg.blockDim = dim3(many ? 192 : 512);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -291,7 +293,8 @@ cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, norm_kernel, h_in, y, g_post, g_pre, h_out, xn, xf, d, eps, zero_a, na, zero_b, nb, trace);
+  if (many) return cudaLaunchKernelEx(&cfg, norm_kernel<192, 4>, h_in, y, g_post, g_pre, h_out, xn, xf, d, eps, zero_a, na, zero_b, nb, trace);
+  return cudaLaunchKernelEx(&cfg, norm_kernel<512, 2>, h_in, y, g_post, g_pre, h_out, xn, xf, d, eps, zero_a, na, zero_b, nb, trace);
 }
 
 cudaError_t launch_rope_split(const RopeSplitArgs& a, cudaStream_t st) {

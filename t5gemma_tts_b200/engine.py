@@ -57,7 +57,13 @@ class T5GemmaVoiceEngine:
             self.device = torch.device("cuda", torch.cuda.current_device())
         # reference-facing attributes (inference_tts_utils.py:163-172 reads model_args.*; CLI reads model.config)
         self.config = ref_config if ref_config is not None else SimpleNamespace(**self._args_dict())
-        self.args = ref_config if ref_config is not None else self.config
+        self.args = self.config
+        if ref_config is not None and not all(hasattr(ref_config, k) for k in ("y_sep_token", "eos", "empty_token")):
+            # a partial config (e.g. a dict of the fields EngineConfig needs): the front door still finds every
+            # model_args field it reads, derived from the engine's own special-token layout
+            merged = self._args_dict()
+            merged.update({k: v for k, v in vars(ref_config).items() if not k.startswith("_")} if hasattr(ref_config, "__dict__") else {})
+            self.args = SimpleNamespace(**merged)
         self.training = False
         self._h = C.c_void_p()
         c = L.T5GConfig()

@@ -347,14 +347,17 @@ def test_from_pretrained_hf_dir(tmp_path):
     eng.close()
 
 
-@pytest.mark.parametrize("max_slots,env", [(1, {}), (8, {}), (3, {"T5G_GEMV_PAIR": "0"})],
-                         ids=["single", "batched-mma", "three-rows-unpaired"])
+@pytest.mark.parametrize("max_slots,env", [(1, {}), (8, {}), (3, {"T5G_GEMV_PAIR": "0"}), (8, {"T5G_ATTN_CHUNK": "32"}),
+                                           (8, {"T5G_ATTN_CHUNK": "0"})],
+                         ids=["single", "batched-mma", "three-rows-unpaired", "batched-mma-4-chunks", "batched-mma-unchunked"])
 def test_head_dim_256_decode_matches_oracle(max_slots, env, monkeypatch):
     """The production head geometry (head_dim 256, 2 query heads per KV head) on a narrow 2+2-layer model with a
     sliding window of 48: exercises the D=256 instantiations of both decode attention kernels (CUDA-core for
     max_slots <= 4, cp.async + mma.sync tile kernel for batched rows) with contexts that cross the 32-token tile
     and the window, teacher-forced along the oracle's greedy sequences; logits within the bf16 tolerance.  The third
-    case runs three rows through the GEMV path with o_proj and the cross q projection as two kernels."""
+    case runs three rows through the GEMV path with o_proj and the cross q projection as two kernels; the last two run the
+    batched attention with 32-key chunks (up to 4 chunks per row and kv head, merged by the last CTA to arrive; the text
+    of 70 tokens gives the cross-attention 3 chunks) and with chunking off (one CTA per row and kv head)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)                     # read by t5g_create
     from oracle.t5gemma_voice_oracle import Oracle, OracleConfig

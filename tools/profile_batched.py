@@ -7,10 +7,20 @@ from bench_batched import make_requests
 from t5gemma_tts_b200 import EngineConfig, T5GemmaVoiceEngine
 from t5gemma_tts_b200.random_init import iter_random_state_dict
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-cfg = EngineConfig(max_slots=B, max_text_len=128, max_dec_len=1536, max_prefill_tokens=max(8192, 160 * B))
+cfg = EngineConfig(max_slots=B, max_text_len=128, max_dec_len=1536, max_prefill_tokens=max(8192, 920 * B))
 eng = T5GemmaVoiceEngine(cfg)
 eng.load_state_dict(iter_random_state_dict(cfg, seed=0, device="cuda"))
 reqs = make_requests(B, cfg)
+if len(sys.argv) > 2 and sys.argv[2] == "spread":
+    # contexts like the middle of a continuous-batching job: prompts U[0, 900) tokens, every row alive for the whole run
+    import numpy as np
+    from t5gemma_tts_b200 import GenerationRequest
+    rng = np.random.default_rng(3)
+    reqs = []
+    for i in range(B):
+        P = int(rng.integers(0, 900))
+        reqs.append(GenerationRequest(text_ids=rng.integers(2, 255000, int(rng.integers(32, 129))), prompt_ids=rng.integers(0, cfg.audio_vocab, P),
+                                      target_total=P + 300, prompt_frames=P, top_k=30, top_p=0.9, temperature=0.8))
 eng.prefill(reqs, list(range(B)))
 eng.decode(8); eng.poll()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

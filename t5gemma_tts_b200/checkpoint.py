@@ -55,8 +55,19 @@ def load_pth_bundle(path: str, t5_config_dict: Dict[str, Any] | None = None):
     args = ckpt.get("args", None)
     a = vars(args) if args is not None and not isinstance(args, dict) else dict(args or {})
     if t5_config_dict is None:
-        from transformers.models.t5gemma import T5GemmaConfig
-        t5_config_dict = T5GemmaConfig().to_dict()
+        # the reference builds the backbone from args.t5gemma_model_name (hub name); offline, only the 2b-2b default
+        # geometry is known -- any other backbone must come from the local HF cache or from the caller
+        name = str(a.get("t5gemma_model_name") or "")
+        if name and "2b-2b" not in name:
+            try:
+                from transformers import AutoConfig
+                t5_config_dict = AutoConfig.from_pretrained(name, local_files_only=True).to_dict()
+            except Exception as ex:
+                raise ValueError(f"{path}: the bundle was trained on backbone '{name}', whose geometry is neither stored in the "
+                                 "bundle nor found in the local Hugging Face cache; pass t5_config_dict=<its config dict>") from ex
+        else:
+            from transformers.models.t5gemma import T5GemmaConfig
+            t5_config_dict = T5GemmaConfig().to_dict()
     V = int(a.get("audio_vocab_size", 65536) if not isinstance(a.get("audio_vocab_size"), (list, tuple)) else a["audio_vocab_size"][0])
     cfg = dict(t5_config_dict=t5_config_dict, attn_implementation=a.get("attn_implementation", "eager"),
                audio_vocab_size=V, n_special=int(a.get("n_special", 5)), n_codebooks=int(a.get("n_codebooks", 1)),

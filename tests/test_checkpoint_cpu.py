@@ -67,3 +67,21 @@ def test_pth_bundle(tmp_path):
     ec = EngineConfig.from_reference(cfg)
     assert ec.n_audio_tokens == 105 and ec.stop_token == 103 and ec.n_dec_layers == 3
     assert set(sd2) == set(sd)
+
+
+def test_pth_bundle_names_missing_backbone_geometry(tmp_path):
+    """A bundle trained on a non-default backbone carries only its hub name (models/t5gemma.py builds the backbone from
+    args.t5gemma_model_name): without t5_config_dict the loader must say so instead of failing later on tensor shapes."""
+    _, sd, meta = fixtures.load_model_fixture("tinyA_eager")
+    args = argparse.Namespace(audio_vocab_size=100, t5gemma_model_name="google/t5gemma-b-b-ul2")
+    p = tmp_path / "bundle_bb.pth"
+    torch.save({"model": sd, "args": args}, str(p))
+    with pytest.raises(ValueError, match="t5gemma-b-b-ul2"):
+        ck.load_pth_bundle(str(p))
+    cfg, _ = ck.load_pth_bundle(str(p), t5_config_dict=meta["t5_config_dict"])
+    assert EngineConfig.from_reference(cfg).hidden == 64
+    # the 2b-2b names fall back to transformers' default geometry
+    args.t5gemma_model_name = "google/t5gemma-2b-2b-ul2"
+    torch.save({"model": sd, "args": args}, str(p))
+    cfg, _ = ck.load_pth_bundle(str(p))
+    assert EngineConfig.from_reference(cfg).hidden == 2304

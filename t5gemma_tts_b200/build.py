@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libt5gtts.so")
-SOURCES = ["engine.cu", "gemv.cu", "gemv_pair.cu", "attention.cu", "attention_tc.cu", "attention_mma.cu", "prefill.cu", "sampler.cu", "gemm_tc.cu"]
+SOURCES = ["engine.cu", "gemv.cu", "gemv_pair.cu", "attention.cu", "attention_tc.cu", "attention_mma.cu", "attention_tma.cu", "prefill.cu", "sampler.cu", "gemm_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas",

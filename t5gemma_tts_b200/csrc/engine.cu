@@ -76,7 +76,7 @@ struct T5GEngine {
   float *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_memory = nullptr, *p_ckv = nullptr, *p_final = nullptr;
   bf16 *p_xn = nullptr, *p_q = nullptr, *p_k = nullptr, *p_v = nullptr, *p_att = nullptr, *p_act = nullptr,
        *p_mem_bf = nullptr, *p_ck = nullptr, *p_cv = nullptr, *p_vt = nullptr;
-  int vt_ld = 0; bool use_tc_attn = true; int attn_mma = 1;
+  int vt_ld = 0; bool use_tc_attn = true; int attn_mma = 1, attn_tma = 1;
   int *p_vt_off_e = nullptr, *p_vt_off_d = nullptr;          // 8-aligned V^T column offsets per request (encoder / decoder tokens)
   float* p_logits = nullptr; int logits_chunk = 128;
   int *p_ids = nullptr, *p_seg_of = nullptr, *p_seg_off_e = nullptr, *p_seg_off_d = nullptr, *p_tok_slot = nullptr,
@@ -279,6 +279,8 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   e->n_pages = B * (e->max_self_pages + e->max_cross_pages);
   e->pool.n_pages = e->n_pages; e->pool.page_tokens = e->PT; e->pool.Hkv = e->Hkv; e->pool.D = D;
   DM(e->pool.base, (size_t)cfg->n_dec_layers * 2 * e->n_pages * e->pool.page_elems());
+  // the TMA front end of the batched attention loads whole pages: rows that were never written must hold finite values
+  T5G_CUDA(cudaMemset(e->pool.base, 0, sizeof(bf16) * (size_t)cfg->n_dec_layers * 2 * e->n_pages * e->pool.page_elems()));
   for (int p = e->n_pages - 1; p >= 0; --p) e->free_pages.push_back(p);
   DM(e->d_self_bt, (size_t)B * e->max_self_pages); DM(e->d_cross_bt, (size_t)B * e->max_cross_pages);
   T5G_CUDA(cudaMemset(e->d_self_bt, 0, sizeof(int) * (size_t)B * e->max_self_pages));
@@ -308,6 +310,7 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   if (const char* s = getenv("T5G_ATTN_TC")) e->use_tc_attn = atoi(s) != 0;
   if (const char* s = getenv("T5G_GEMV_PAIR")) e->use_pair = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA")) e->attn_mma = atoi(s) != 0;
+  if (const char* s = getenv("T5G_ATTN_TMA")) e->attn_tma = atoi(s) != 0;
   DM(e->p_logits, (size_t)e->logits_chunk * e->Vpad);
   DM(e->p_ids, T); DM(e->p_seg_of, T); DM(e->p_seg_off_e, B + 1); DM(e->p_seg_off_d, B + 1); DM(e->p_tok_slot, T); DM(e->p_tok_idx, T);
   DM(e->p_last_rows, B); DM(e->p_pos, T);
@@ -855,7 +858,10 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       if (e->attn_chunk > 0) { a.chunk_tokens = e->attn_chunk; a.max_chunks = e->chunks_self; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml; a.part_cnt = e->d_part_cnt; }
       a.probe = (e->use_trace && l == 5) ? e->d_trace + 300 : nullptr;
       a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = 1; a.mma = e->attn_mma; a.trace = next_trace();
-      if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
+      a.n_layers_pool = c.n_dec_layers;
+      if (a.mma && e->attn_tma && attn_decode_tma_supported(a)) CU(launch_attn_decode_tma(a, st, pdl_attn));
+      else if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn));
+      else CU(launch_attn_decode(a, st, pdl_attn));
       nl++; }
     CU(G(e->d_attn_bf, L.wo, d, QD, GE_F32, nullptr, e->d_y, d));
     CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qc, QD, e->d_y, d, next_trace())); nl++;
@@ -867,7 +873,10 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       a.n_splits = 1;
       if (e->attn_chunk > 0) { a.chunk_tokens = e->attn_chunk; a.max_chunks = e->chunks_cross; a.part_o = e->d_part_o; a.part_ml = e->d_part_ml; a.part_cnt = e->d_part_cnt; }
       a.out = nullptr; a.out_bf = e->d_attn_bf; a.preload = 1; a.mma = e->attn_mma; a.trace = next_trace();
-      if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn)); else CU(launch_attn_decode(a, st, pdl_attn));
+      a.n_layers_pool = c.n_dec_layers;
+      if (a.mma && e->attn_tma && attn_decode_tma_supported(a)) CU(launch_attn_decode_tma(a, st, pdl_attn));
+      else if (a.mma && attn_decode_mma_supported(a)) CU(launch_attn_decode_mma(a, st, pdl_attn));
+      else CU(launch_attn_decode(a, st, pdl_attn));
       nl++; }
     CU(G(e->d_attn_bf, L.wo_c, d, QD, GE_F32, nullptr, e->d_y, d));
     CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_y, d, nullptr, 0, next_trace())); nl++;

@@ -76,10 +76,13 @@ struct AttnDecodeArgs {
   float* part_o;                           // [B][Hkv][16][G][D] unnormalised partial outputs
   float* part_ml;                          // [B][Hkv][16][G][2] running max / sum of every chunk
   int* part_cnt;                           // [B][Hkv] arrival counters, zero between launches
+  int n_layers_pool;                       // layers in the pool (the TMA front end addresses the whole pool as one tensor)
 };
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);
 bool attn_decode_mma_supported(const AttnDecodeArgs& a);
 cudaError_t launch_attn_decode_mma(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);   // attention_mma.cu
+bool attn_decode_tma_supported(const AttnDecodeArgs& a);                                    // head_dim 64/128/256, 16-token pages
+cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, cudaStream_t st, bool pdl);   // attention_tma.cu (same math, TMA tile loads)
 
 // ---------------- prefill-side kernels (prefill.cu) ----------------
 // varlen packing: token t belongs to request seg_of[t]; seg_off[r]..seg_off[r+1] are its tokens

@@ -67,7 +67,7 @@ template <int D> struct AtGeo {
   static constexpr int TILE_BYTES = AM_TT * D * 2;         // K (or V) tile: [NA][32][128 B]
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;       // K tile + V tile
   static constexpr int KS = D / 16;                        // k-steps of the score MMA
-  static constexpr int KSH = (KS + 1) / 2;                 // ... per k-half (two warps share a 16-token group)
+  static constexpr int KSH = (KS + 3) / 4;                 // ... per k-quarter (four warps share a 16-token group)
   static constexpr int NMT = D / 16;                       // 16-dim m-tiles of the output MMA
   static constexpr int MTW = (NMT + AM_WARPS - 1) / AM_WARPS;   // m-tiles per warp
   // q / probability operand tiles hold G real rows + one shared zero row (the MMA's n = 8 columns beyond G read it).
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(AM_NT, 3) attn_decode_tma_kernel(const __grid_
   __shared__ float cs[D / 2], sn[D / 2];
   __shared__ float knew[D], vnew[D];
   __shared__ int bt_s[AM_BT_CACHE];
-  __shared__ float scp[2][G][AM_TT];                                    // partial q.k of the two k-halves
+  __shared__ float scp[4][G][AM_TT];                                    // partial q.k of the four k-quarters
   __shared__ float corr_s[8];
   __shared__ float ml_s[G][2];
   __shared__ float cw_s[AM_MAX_CHUNKS][G], cl_s[AM_MAX_CHUNKS][G];      // merge weights / sums of the chunks
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(AM_NT, 3) attn_decode_tma_kernel(const __grid_
     if (tid < D) { kd[tid] = __float2bfloat16(knew[tid]); vd[tid] = __float2bfloat16(vnew[tid]); }
   }
   // q fragments (B operand of the score MMA): B[k = dim][n = head] from qb[head][dim]; this warp's k-half only
-  const int tg = warp & 1, kh = (warp >> 1) & 1;      // score phase (warps 0-3): 16-token group, k-half
+  const int tg = warp & 1, kh = warp >> 1;            // score phase (all 8 warps): 16-token group, k-quarter
   uint32_t qf[KSH][2];
 #pragma unroll
   for (int i = 0; i < KSH; ++i) {
@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(AM_NT, 3) attn_decode_tma_kernel(const __grid_
       }
       am_cons_sync();
     }
-    // ---- partial scores: warps 0-3 = (16-token group tg) x (k-half kh); rows past the range are zero-filled ----
-    if (warp < 4) {
+    // ---- partial scores: warp = (16-token group tg) x (k-quarter kh) ----
+    {
       float c[4] = {0.f, 0.f, 0.f, 0.f};
       const int atok = tg * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ad0 = (lane >> 4) * 8 + kh * KSH * 16;
 #pragma unroll
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(AM_NT, 3) attn_decode_tma_kernel(const __grid_
     am_cons_sync();
     // ---- scale / softcap / mask + online softmax: warp h owns head h, lane = token of the tile ----
     if (warp < G) {
-      float s = (scp[0][warp][lane] + scp[1][warp][lane]) * a.scale;
+      float s = ((scp[0][warp][lane] + scp[1][warp][lane]) + (scp[2][warp][lane] + scp[3][warp][lane])) * a.scale;
       if (a.softcap > 0.f) {
         const float e2 = __expf(2.f * s * inv_cap);
         s = a.softcap * (1.f - __fdividef(2.f, e2 + 1.f));

@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr int ATD_MAX_NS = 8;
+constexpr int ATD_MAX_NS = 16;       // 16-CTA clusters need cudaFuncAttributeNonPortableClusterSizeAllowed
 constexpr int ATD_BT_CACHE = 256;      // block-table entries staged in shared memory (covers 4096 tokens at 16/page)
 
 // grid (Hkv, NS, B), thread-block cluster (1, NS, 1): the NS split CTAs of one (request, kv head) exchange
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   __shared__ int bt_s[ATD_BT_CACHE];
   __shared__ __align__(16) float w_o[ATD_WARPS][G][D];
   __shared__ float w_ml[ATD_WARPS][G][2];
-  __shared__ __align__(16) float recv_o[ATD_MAX_NS][G][D / 1];   // [src rank][g][dslice] (only D/NS used per rank)
+  __shared__ __align__(16) float recv_o[G * D];                  // [src rank][g][dslice = D / NS]
   __shared__ float recv_ml[ATD_MAX_NS][G][2];
   __shared__ float w_wt[ATD_WARPS][G], c_ml[G][2], f_wt[ATD_MAX_NS][G];
 
@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   __syncthreads();
   auto page_of = [&](int t) -> int { const int pi = t / PT; return pi < ATD_BT_CACHE ? bt_s[pi] : bt[pi]; };
   // K/V rows of the first two token groups of this warp: in flight while the producer kernel is still running
-  uint4 ku[2][NV], vu[2][NV];
-  auto load_groups = [&](int t0) {
+  // two register buffers of two token groups each: the rows of iteration i+1 are in flight while iteration i is consumed
+  // (with one buffer every iteration after the first paid a full memory round trip: 5.8 us at ctx 160, 10.3 us at ctx 720)
+  uint4 ku[2][NV], vu[2][NV], ku2[2][NV], vu2[2][NV];
+  auto load_groups_into = [&](uint4 (&kd)[2][NV], uint4 (&vd)[2][NV], int t0) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int t = t0 + u * ATD_WARPS * TPW + grp;
@@ -92,12 +94,18 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
         const bf16* kp = a.pool.ptr(a.layer, 0, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
         const bf16* vp = a.pool.ptr(a.layer, 1, page) + ((size_t)hk * PT + off) * D + l8 * DPL;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) { ku[u][i] = *reinterpret_cast<const uint4*>(kp + i * 8); vu[u][i] = *reinterpret_cast<const uint4*>(vp + i * 8); }
+        for (int i = 0; i < NV; ++i) { kd[u][i] = *reinterpret_cast<const uint4*>(kp + i * 8); vd[u][i] = *reinterpret_cast<const uint4*>(vp + i * 8); }
       }
     }
   };
+  auto load_groups = [&](int t0) { load_groups_into(ku, vu, t0); };
   const int t_first = t_begin + warp * TPW;
-  if (active && a.preload) load_groups(t_first);
+  constexpr int STEP = 2 * ATD_WARPS * TPW;               // tokens of the CTA's range covered per iteration
+  bool pre2 = false;
+  if (active && a.preload) {
+    load_groups(t_first);
+    if (t_first + STEP < t_end) { load_groups_into(ku2, vu2, t_first + STEP); pre2 = true; }
+  }
 
   pdl_wait();
   trace_begin(a.trace);
@@ -157,8 +165,7 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   GroupState<G, DPL> st;
   st.init();
   // two token groups per iteration: both K/V row loads are in flight before either is consumed
-  for (int t0 = t_first; t0 < t_end; t0 += 2 * ATD_WARPS * TPW) {
-    if (t0 != t_first) load_groups(t0);
+  auto consume = [&](const uint4 (&kd)[2][NV], const uint4 (&vd)[2][NV], int t0) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (t0 + u * ATD_WARPS * TPW >= t_end) break;      // warp-uniform
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
         for (int i = 0; i < DPL; ++i) { kf[i] = knew[l8 * DPL + i]; vf[i] = vnew[l8 * DPL + i]; }
       } else if (valid) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) { bf16x8_to_f32(ku[u][i], kf + i * 8); bf16x8_to_f32(vu[u][i], vf + i * 8); }
+        for (int i = 0; i < NV; ++i) { bf16x8_to_f32(kd[u][i], kf + i * 8); bf16x8_to_f32(vd[u][i], vf + i * 8); }
       } else {
 #pragma unroll
         for (int i = 0; i < DPL; ++i) { kf[i] = 0.f; vf[i] = 0.f; }
@@ -178,6 +185,13 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
       // all lanes execute the shuffles; invalid groups contribute nothing
       group_update<G, D>(st, qreg, kf, vf, a.scale, a.softcap, valid);
     }
+  };
+  for (int t0 = t_first; t0 < t_end; t0 += 2 * STEP) {
+    if (t0 + STEP < t_end && !(pre2 && t0 == t_first)) load_groups_into(ku2, vu2, t0 + STEP);
+    consume(ku, vu, t0);
+    if (t0 + STEP >= t_end) break;
+    if (t0 + 2 * STEP < t_end) load_groups_into(ku, vu, t0 + 2 * STEP);
+    consume(ku2, vu2, t0 + STEP);
   }
   warp_merge<G, D>(st);
   if (grp == 0) {
@@ -214,8 +228,8 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
 #pragma unroll
     for (int w = 0; w < ATD_WARPS; ++w) num = fmaf(w_wt[w][g], w_o[w][g][d], num);
     const int dst = d / dslice;                          // rank that finalises this dim
-    float* ro = cluster.map_shared_rank(&recv_o[0][0][0], dst);
-    ro[((size_t)split * G + g) * D + (d - dst * dslice)] = num;
+    float* ro = cluster.map_shared_rank(&recv_o[0], dst);
+    ro[((size_t)split * G + g) * dslice + (d - dst * dslice)] = num;
   }
   if (tid < G * NS) {                                    // (m, l) of this CTA to every rank
     const int g = tid % G, dst = tid / G;
@@ -241,7 +255,7 @@ __global__ void __launch_bounds__(ATD_WARPS * 32) attn_decode_kernel(AttnDecodeA
   for (int i = tid; i < G * dslice; i += blockDim.x) {
     const int g = i / dslice, dd = i - g * dslice;
     float o = 0.f;
-    for (int r = 0; r < NS; ++r) o = fmaf(f_wt[r][g], recv_o[r][g][dd], o);
+    for (int r = 0; r < NS; ++r) o = fmaf(f_wt[r][g], recv_o[(r * G + g) * dslice + dd], o);
     const int d = split * dslice + dd;
     if (a.out) a.out[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = o;
     if (a.out_bf) a.out_bf[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = __float2bfloat16(o);
@@ -319,6 +333,15 @@ cudaError_t launch_decode_gd(const AttnDecodeArgs& a, cudaStream_t st, bool pdl)
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
+  if (a.n_splits > 8) {                                  // non-portable cluster size
+    static PerDeviceFlag np_set;
+    if (!np_set.here()) {
+      cudaError_t e = wide ? cudaFuncSetAttribute(attn_decode_kernel<G, D, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)
+                           : cudaFuncSetAttribute(attn_decode_kernel<G, D, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+      np_set.here() = 1;
+    }
+  }
   if (wide) return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D, 8>, a);
   return cudaLaunchKernelEx(&cfg, attn_decode_kernel<G, D, 4>, a);
 }
@@ -350,7 +373,7 @@ cudaError_t launch_prefill_gd(const AttnPrefillArgs& a, cudaStream_t st) {
 
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   const int G = a.Hq / a.Hkv;
-  if (a.n_splits < 1 || a.n_splits > 8 || (a.n_splits & (a.n_splits - 1)) || a.D % a.n_splits) return cudaErrorInvalidValue;
+  if (a.n_splits < 1 || a.n_splits > ATD_MAX_NS || (a.n_splits & (a.n_splits - 1)) || a.D % a.n_splits) return cudaErrorInvalidValue;
   DISPATCH_GD(G, a.D, launch_decode_gd, a, st, pdl);
   return cudaErrorInvalidValue;
 }

@@ -13,6 +13,7 @@ from t5gemma_tts_b200.random_init import iter_random_state_dict  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--ctx", type=int, default=150)
+ap.add_argument("--warm", type=int, default=0, help="decode steps before the timed ones (longer context)")
 a = ap.parse_args()
 cfg = engine_config(1)
 eng = T5GemmaVoiceEngine(cfg)
@@ -21,6 +22,9 @@ x, xl, y, tgt = make_inputs(1234, cfg)
 rq = GenerationRequest(text_ids=x[0].numpy(), prompt_ids=y[0, : a.ctx + 1, 0].numpy(), target_total=int(tgt[0]),
                        prompt_frames=a.ctx + 1, top_k=30, top_p=0.9, temperature=0.8)
 eng.prefill([rq], [0])
+if a.warm > 0:
+    eng.decode(a.warm)
+    eng.poll()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 eng.decode(a.steps)
 eng.poll()

@@ -348,8 +348,11 @@ def test_from_pretrained_hf_dir(tmp_path):
 
 
 @pytest.mark.parametrize("max_slots,env", [(1, {}), (8, {}), (3, {"T5G_GEMV_PAIR": "0"}), (8, {"T5G_ATTN_CHUNK": "32"}),
-                                           (8, {"T5G_ATTN_CHUNK": "0"})],
-                         ids=["single", "batched-mma", "three-rows-unpaired", "batched-mma-4-chunks", "batched-mma-unchunked"])
+                                           (8, {"T5G_ATTN_CHUNK": "0"}), (8, {"T5G_ATTN_TMA": "0", "T5G_ATTN_CHUNK": "32"}),
+                                           (8, {"GEOM": "4x1x64", "T5G_ATTN_CHUNK": "32"}), (8, {"GEOM": "2x2x128"}),
+                                           (2, {"GEOM": "4x1x64"})],
+                         ids=["single", "batched-mma", "three-rows-unpaired", "batched-mma-4-chunks", "batched-mma-unchunked",
+                              "batched-cp.async-4-chunks", "batched-G4-D64-chunks", "batched-G1-D128", "two-rows-G4-D64"])
 def test_head_dim_256_decode_matches_oracle(max_slots, env, monkeypatch):
     """The production head geometry (head_dim 256, 2 query heads per KV head) on a narrow 2+2-layer model with a
     sliding window of 48: exercises the D=256 instantiations of both decode attention kernels (CUDA-core for
@@ -357,14 +360,18 @@ def test_head_dim_256_decode_matches_oracle(max_slots, env, monkeypatch):
     and the window, teacher-forced along the oracle's greedy sequences; logits within the bf16 tolerance.  The third
     case runs three rows through the GEMV path with o_proj and the cross q projection as two kernels; the last two run the
     batched attention with 32-key chunks (up to 4 chunks per row and kv head, merged by the last CTA to arrive; the text
-    of 70 tokens gives the cross-attention 3 chunks) and with chunking off (one CTA per row and kv head)."""
+    of 70 tokens gives the cross-attention 3 chunks) and with chunking off (one CTA per row and kv head); then the `cp.async`
+    front end of the tile kernel, and the other head geometries the TMA front end is instantiated for (4 query heads per kv
+    head at head_dim 64, one at head_dim 128)."""
+    env = dict(env)
+    nh, nkv, hd = (int(v) for v in env.pop("GEOM", "2x1x256").split("x"))   # other head geometries of the attention kernels
     for k, v in env.items():
         monkeypatch.setenv(k, v)                     # read by t5g_create
     from oracle.t5gemma_voice_oracle import Oracle, OracleConfig
     from t5gemma_tts_b200 import EngineConfig, T5GemmaVoiceEngine
     from t5gemma_tts_b200.random_init import iter_random_state_dict
-    cfg = EngineConfig(hidden=512, inter=1024, n_enc_layers=2, n_dec_layers=2, n_heads=2, n_kv_heads=1, head_dim=256,
-                       query_pre_attn_scalar=256.0, sliding_window=48, text_vocab=300, audio_vocab=400,
+    cfg = EngineConfig(hidden=512, inter=1024, n_enc_layers=2, n_dec_layers=2, n_heads=nh, n_kv_heads=nkv, head_dim=hd,
+                       query_pre_attn_scalar=float(hd), sliding_window=48, text_vocab=300, audio_vocab=400,
                        max_slots=max_slots, max_text_len=96, max_dec_len=512, max_prefill_tokens=1024)
     sd = {k: v.float().cpu() for k, v in iter_random_state_dict(cfg, seed=3, device="cuda")}
     ocfg = OracleConfig(hidden=cfg.hidden, inter=cfg.inter, n_enc_layers=cfg.n_enc_layers, n_dec_layers=cfg.n_dec_layers,

@@ -350,9 +350,9 @@ def test_from_pretrained_hf_dir(tmp_path):
 @pytest.mark.parametrize("max_slots,env", [(1, {}), (8, {}), (3, {"T5G_GEMV_PAIR": "0"}), (8, {"T5G_ATTN_CHUNK": "32"}),
                                            (8, {"T5G_ATTN_CHUNK": "0"}), (8, {"T5G_ATTN_TMA": "0", "T5G_ATTN_CHUNK": "32"}),
                                            (8, {"GEOM": "4x1x64", "T5G_ATTN_CHUNK": "32"}), (8, {"GEOM": "2x2x128"}),
-                                           (2, {"GEOM": "4x1x64"})],
+                                           (3, {"GEOM": "4x1x64"})],
                          ids=["single", "batched-mma", "three-rows-unpaired", "batched-mma-4-chunks", "batched-mma-unchunked",
-                              "batched-cp.async-4-chunks", "batched-G4-D64-chunks", "batched-G1-D128", "two-rows-G4-D64"])
+                              "batched-cp.async-4-chunks", "batched-G4-D64-chunks", "batched-G1-D128", "three-rows-G4-D64"])
 def test_head_dim_256_decode_matches_oracle(max_slots, env, monkeypatch):
     """The production head geometry (head_dim 256, 2 query heads per KV head) on a narrow 2+2-layer model with a
     sliding window of 48: exercises the D=256 instantiations of both decode attention kernels (CUDA-core for

@@ -415,3 +415,54 @@ def test_head_dim_256_decode_matches_oracle(max_slots, env, monkeypatch):
     for (gen, _), s in zip(refs, slots):
         assert np.array_equal(eng.read_tokens(s)[:len(gen)], gen)
     eng.close()
+
+
+@pytest.mark.parametrize("max_slots", [1, 64], ids=["single-row-gemv", "64-row-tcgen05"])
+def test_production_width_two_layers_matches_oracle(max_slots):
+    """2b-2b WIDTH (hidden 2304, 8 query / 4 kv heads of 256, MLP 9216, audio vocabulary 65 536) with 2 + 2 layers, so that the
+    fp32 CPU oracle stays a few seconds: a 300-token voice prompt (prefill through the CTA-pair GEMM and the single-pass
+    tcgen05 attention), then 32 teacher-forced decode steps through the production-width decode kernels (K = 2304 / 9216
+    GEMVs and the paired projection at one row; tcgen05 GEMMs, chunked TMA attention and the full-vocabulary sampler at 64
+    rows).  Encoder states and every step's logits within the bf16 tolerance.  (`bench.py` `parity_2b` does the same over
+    all 26 + 26 layers.)"""
+    from oracle.t5gemma_voice_oracle import Oracle, OracleConfig
+    from t5gemma_tts_b200 import EngineConfig, T5GemmaVoiceEngine
+    from t5gemma_tts_b200.random_init import iter_random_state_dict
+    cfg = EngineConfig(hidden=2304, inter=9216, n_enc_layers=2, n_dec_layers=2, n_heads=8, n_kv_heads=4, head_dim=256,
+                       query_pre_attn_scalar=256.0, sliding_window=4096, text_vocab=1000, audio_vocab=65536,
+                       max_slots=max_slots, max_text_len=128, max_dec_len=1024, max_prefill_tokens=2048)
+    sd = {k: v.float().cpu() for k, v in iter_random_state_dict(cfg, seed=5, device="cuda")}
+    ocfg = OracleConfig(hidden=cfg.hidden, inter=cfg.inter, n_enc_layers=cfg.n_enc_layers, n_dec_layers=cfg.n_dec_layers,
+                        n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, head_dim=cfg.head_dim,
+                        sliding_window=cfg.sliding_window, query_pre_attn_scalar=cfg.query_pre_attn_scalar,
+                        attn_softcap=cfg.attn_softcap, text_vocab=cfg.text_vocab, audio_vocab=cfg.audio_vocab,
+                        n_special=cfg.n_special)
+    orc = Oracle(ocfg, sd)
+    eng = T5GemmaVoiceEngine(cfg)
+    eng.load_state_dict(iter_random_state_dict(cfg, seed=5, device="cuda"))
+    rng = np.random.default_rng(7)
+    S, P, N_NEW = 96, 300, 32
+    x = torch.from_numpy(rng.integers(2, cfg.text_vocab, S))[None]
+    y = torch.cat([torch.from_numpy(rng.integers(0, cfg.audio_vocab, P))[None, :, None], torch.tensor([[[cfg.y_sep_token]]])], dim=1)
+    tgt = torch.tensor([y.shape[1] + 200])
+    with torch.no_grad():
+        _, gen, logits = orc.inference_tts(x, torch.tensor([S]), y, tgt, top_k=1, prompt_frames=y.shape[1],
+                                           max_new_tokens=N_NEW, return_logits=True)
+        mem = orc.encoder(x[0]).numpy()
+    gen, logits = gen[0, 0].numpy(), logits.numpy()
+    req = GenerationRequest(text_ids=x[0].numpy(), prompt_ids=y[0, :, 0].numpy(), target_total=int(tgt[0]),
+                            prompt_frames=y.shape[1], top_k=1, forced_tokens=gen)
+    slot = 37 if max_slots > 1 else 0
+    eng.prefill([req], [slot])
+    assert rel_err(eng.read_memory(slot, S), mem) <= TOL_REF
+    eos = cfg.stop_token
+    worst = 0.0
+    for step in range(len(gen)):
+        eng.decode(1)
+        eng.poll()
+        got, ref = eng.read_logits(slot), logits[step].copy()
+        got[eos] = ref[eos] = 0.0
+        worst = max(worst, rel_err(got, ref))
+    assert worst <= TOL_REF, worst
+    assert np.array_equal(eng.read_tokens(slot)[:len(gen)], gen)
+    eng.close()

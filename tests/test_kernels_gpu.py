@@ -61,6 +61,29 @@ def test_gemm_tcgen05_vs_torch(M, N, K):
     assert err < 2e-5, err
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 2304, 2304), (1000, 4608, 256), (257, 18432, 64), (8192, 2304, 512)])
+@pytest.mark.parametrize("epi", ["f32", "bf16", "geglu"])
+def test_gemm_cta_pair_epilogues_vs_torch(M, N, K, epi):
+    """Prefill shapes (more than 128 tokens, tile grid larger than the machine) run on the persistent CTA-pair kernel
+    (tcgen05.mma.cta_group::2, two TMEM accumulators): fp32, bf16 and fused GeGLU epilogues, ragged token / feature tails."""
+    eng = engine_for("tinyA_eager")
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    code = {"f32": 0, "geglu": 1, "bf16": 4}[epi]
+    out = torch.full((M, N // 2 if epi == "geglu" else N), float("nan"), device="cuda",
+                     dtype=torch.float32 if epi == "f32" else torch.bfloat16)
+    torch.cuda.synchronize()
+    L.check(eng.lib, eng.lib.t5g_debug_gemm(eng._h, C.c_void_p(a.data_ptr()), C.c_void_p(w.data_ptr()),
+                                            C.c_void_p(out.data_ptr()), M, N, K, 1 | (code << 8), None))
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().t()
+    if epi == "geglu":
+        ref = torch.nn.functional.gelu(ref[:, 0::2], approximate="tanh") * ref[:, 1::2]
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < (2e-5 if epi == "f32" else 8e-3), err     # bf16 outputs: one rounding (2^-9) + tanh.approx in the GeGLU
+
+
 ATTN_CASES = [
     # D, Hq, Hkv, q_lens, k_lens, causal, window, softcap
     (64, 4, 2, [5], [5], False, 0, 0.0),

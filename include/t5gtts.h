@@ -61,7 +61,7 @@ typedef struct T5GConfig {
   int32_t max_text_len;         /* per request encoder tokens */
   int32_t max_dec_len;          /* per request decoder tokens (BOS+prompt+generated) */
   int32_t max_prefill_tokens;   /* tokens per prefill call (sum over requests, max(enc, dec)) */
-  int32_t kv_page_tokens;       /* KV page size in tokens (16) */
+  int32_t kv_page_tokens;       /* KV page size in tokens (multiple of 4; 32 = default, 16 or 32 for the TMA attention front end) */
   int32_t reserved0;
 } T5GConfig;
 

@@ -48,7 +48,7 @@ class EngineConfig:
     max_text_len: int = 512
     max_dec_len: int = 2560
     max_prefill_tokens: int = 2560
-    kv_page_tokens: int = 16
+    kv_page_tokens: int = 32              # one 32-token attention tile = one page = one TMA box per 64-dim slab (16 also supported)
 
     def __post_init__(self):
         V = self.audio_vocab

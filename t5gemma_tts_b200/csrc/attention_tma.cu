@@ -1,9 +1,10 @@
-// Decode attention for BATCHED rows, TMA front end (head_dim 64 / 128 / 256, 16-token KV pages).
+// Decode attention for BATCHED rows, TMA front end (head_dim 64 / 128 / 256, 16- or 32-token KV pages).
 //
 // Same math, fused glue (PM-RoPE of q and of the new k, in-place KV append) and chunked work partition as the tile kernel
 // of attention_mma.cu; what changes is how a 32-token tile reaches shared memory.  The KV pool is one 2-D tensor
-// [layer * 2 * page * kv head * 16 tokens, head_dim]: the 16 tokens of a (page, kv head) are 16 consecutive rows, so ONE
-// thread moves a tile with 2 pages x (K, V) x head_dim/64 TMA boxes of [16 tokens x 64 dims] (2 KB each, 128-byte swizzle,
+// [layer * 2 * page * kv head * page tokens, head_dim]: the tokens of a (page, kv head) are consecutive rows, so ONE thread
+// moves a tile with (K, V) x head_dim/64 TMA boxes of [32 tokens x 64 dims] at 32-token pages (4 KB each; two 2 KB boxes
+// of 16 tokens at 16-token pages), 128-byte swizzle,
 // conflict-free ldmatrix through the same XOR) instead of 2048 16-byte cp.async issued by all threads -- ncu had 37 % of
 // the cp.async kernel's instructions in that issue loop and `barrier` as its top stall (five CTA barriers per tile).  The
 // producer thread runs ahead of the 8 consumer warps through full / empty mbarriers (two consumer-only barriers per tile
@@ -136,30 +137,31 @@ __global__ void __launch_bounds__(AM_NT, 3) attn_decode_tma_kernel(const __grid_
   for (int i = tid; i < (G + 1) * (AM_TT + 8); i += AM_NT) pb[i] = __float2bfloat16(0.f);
   const int t_begin = lo + split * chunk, t_end = min(L, t_begin + chunk);
   const bool has_new = (!a.is_cross) && (t_end == L) && (t_end > t_begin);
-  const int t0a = t_begin & ~15;                              // tiles start on a page boundary; keys before t_begin are masked
+  const int t0a = t_begin & ~(PT - 1);                        // tiles start on a page boundary (PT = 16 or 32); keys before t_begin are masked
   const int n_tiles = (t_end > t_begin) ? (t_end - t0a + AM_TT - 1) / AM_TT : 0;
-  const int last_page = (t_end > t_begin) ? (t_end - 1) >> 4 : 0;
+  const int last_page = (t_end > t_begin) ? (t_end - 1) / PT : 0;
   __syncthreads();                                          // the only CTA-wide barrier: roles split below
   auto page_of = [&](int t) -> int { const int pi = t / PT; return pi < AM_BT_CACHE ? bt_s[pi] : bt[pi]; };
   auto stage_ptr = [&](int stage, int kv) -> unsigned char* { return ring + (size_t)stage * Geo::STAGE_BYTES + (size_t)kv * Geo::TILE_BYTES; };
 
   if (warp == AM_WARPS) {
     // ===== producer: one thread.  Row of (layer, K|V, page, kv head, token 0) in the pool tensor =
-    //       (((layer * 2 + kv) * n_pages + page) * Hkv + hk) * 16; a box is the 16 tokens of that page x 64 dims. =====
+    //       (((layer * 2 + kv) * n_pages + page) * Hkv + hk) * PT; a box is the PT tokens of that page x 64 dims: with
+    //       32-token pages (the default) a tile is 8 boxes of 4 KB, with 16-token pages 16 boxes of 2 KB (measured
+    //       equal within noise: 26.9 vs 27.2 us per layer at contexts U[0,900) -- the request size is not the limit). =====
     if (lane == 0) {
-      const int n_pages = a.pool.n_pages;
+      const int n_pages = a.pool.n_pages, ppt = AM_TT / PT;   // pages per tile
       for (int ti = 0; ti < n_tiles; ++ti) {
         const int stage = ti % AM_NST;
         if (ti >= AM_NST) am_mbar_wait(&empty_b[stage], ((ti / AM_NST) - 1) & 1);
         am_mbar_expect_tx(&full_b[stage], (uint32_t)Geo::STAGE_BYTES);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int pi = min((t0a >> 4) + 2 * ti + half, last_page);       // a page past the range: the last one again (finite, masked)
-          const int page = page_of(pi << 4);
+        for (int half = 0; half < ppt; ++half) {
+          const int pi = min(t0a / PT + ppt * ti + half, last_page);       // a page past the range: the last one again (finite, masked)
+          const int page = page_of(pi * PT);
 #pragma unroll
           for (int kv = 0; kv < 2; ++kv) {
-            const int row = (((a.layer * 2 + kv) * n_pages + page) * a.Hkv + hk) * 16;
-            unsigned char* dst = stage_ptr(stage, kv) + half * (16 * 128);
+            const int row = (((a.layer * 2 + kv) * n_pages + page) * a.Hkv + hk) * PT;
+            unsigned char* dst = stage_ptr(stage, kv) + half * (PT * 128);
 #pragma unroll
             for (int sl_ = 0; sl_ < NA; ++sl_) tc::tma_load_2d(dst + sl_ * (AM_TT * 128), &map_kv, sl_ * 64, row, &full_b[stage]);
           }
@@ -434,7 +436,7 @@ cudaError_t launch_at(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   // the whole pool as one 2-D tensor of token rows; box = one (page, kv head) x 64 dims
   CUtensorMap map;
   const uint64_t rows = (uint64_t)a.n_layers_pool * 2 * a.pool.n_pages * a.pool.Hkv * a.pool.page_tokens;
-  if (!tc::make_map_2d(&map, a.pool.base, rows, (uint64_t)D, (uint64_t)D, 16)) return cudaErrorNotSupported;
+  if (!tc::make_map_2d(&map, a.pool.base, rows, (uint64_t)D, (uint64_t)D, (uint32_t)a.pool.page_tokens)) return cudaErrorNotSupported;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(a.Hkv, a.chunk_tokens > 0 ? a.max_chunks : 1, a.B);
   cfg.blockDim = dim3(AM_NT);
@@ -452,7 +454,7 @@ cudaError_t launch_at(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
 
 bool attn_decode_tma_supported(const AttnDecodeArgs& a) {
   const int G = a.Hkv > 0 ? a.Hq / a.Hkv : 0;
-  if (a.n_splits != 1 || a.pool.page_tokens != 16 || a.n_layers_pool <= 0 || a.pool.D != a.D || a.pool.Hkv != a.Hkv) return false;
+  if (a.n_splits != 1 || (a.pool.page_tokens != 16 && a.pool.page_tokens != 32) || a.n_layers_pool <= 0 || a.pool.D != a.D || a.pool.Hkv != a.Hkv) return false;
   if (a.chunk_tokens > 0 && (a.chunk_tokens % AM_TT || a.max_chunks < 1 || a.max_chunks > AM_MAX_CHUNKS ||
                              !a.part_o || !a.part_ml || !a.part_cnt)) return false;
   return (a.D == 64 || a.D == 128 || a.D == 256) && (G == 1 || G == 2 || G == 4) && !(G == 4 && a.D == 256);

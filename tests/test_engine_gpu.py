@@ -349,10 +349,12 @@ def test_from_pretrained_hf_dir(tmp_path):
 
 @pytest.mark.parametrize("max_slots,env", [(1, {}), (8, {}), (3, {"T5G_GEMV_PAIR": "0"}), (8, {"T5G_ATTN_CHUNK": "32"}),
                                            (8, {"T5G_ATTN_CHUNK": "0"}), (8, {"T5G_ATTN_TMA": "0", "T5G_ATTN_CHUNK": "32"}),
-                                           (8, {"GEOM": "4x1x64", "T5G_ATTN_CHUNK": "32"}), (8, {"GEOM": "2x2x128"}),
+                                           (8, {"GEOM": "4x1x64", "T5G_ATTN_CHUNK": "32"}), (8, {"GEOM": "2x2x128", "PT": "16"}),
+                                           (8, {"PT": "16", "T5G_ATTN_CHUNK": "32"}), (1, {"PT": "16"}),
                                            (3, {"GEOM": "4x1x64"})],
                          ids=["single", "batched-mma", "three-rows-unpaired", "batched-mma-4-chunks", "batched-mma-unchunked",
-                              "batched-cp.async-4-chunks", "batched-G4-D64-chunks", "batched-G1-D128", "three-rows-G4-D64"])
+                              "batched-cp.async-4-chunks", "batched-G4-D64-chunks", "batched-G1-D128-pages16", "batched-pages16-chunks",
+                              "single-pages16", "three-rows-G4-D64"])
 def test_head_dim_256_decode_matches_oracle(max_slots, env, monkeypatch):
     """The production head geometry (head_dim 256, 2 query heads per KV head) on a narrow 2+2-layer model with a
     sliding window of 48: exercises the D=256 instantiations of both decode attention kernels (CUDA-core for
@@ -365,6 +367,7 @@ def test_head_dim_256_decode_matches_oracle(max_slots, env, monkeypatch):
     head at head_dim 64, one at head_dim 128)."""
     env = dict(env)
     nh, nkv, hd = (int(v) for v in env.pop("GEOM", "2x1x256").split("x"))   # other head geometries of the attention kernels
+    page_tokens = int(env.pop("PT", "32"))                                  # KV page size (two TMA boxes per tile at 16)
     for k, v in env.items():
         monkeypatch.setenv(k, v)                     # read by t5g_create
     from oracle.t5gemma_voice_oracle import Oracle, OracleConfig
@@ -372,7 +375,8 @@ def test_head_dim_256_decode_matches_oracle(max_slots, env, monkeypatch):
     from t5gemma_tts_b200.random_init import iter_random_state_dict
     cfg = EngineConfig(hidden=512, inter=1024, n_enc_layers=2, n_dec_layers=2, n_heads=nh, n_kv_heads=nkv, head_dim=hd,
                        query_pre_attn_scalar=float(hd), sliding_window=48, text_vocab=300, audio_vocab=400,
-                       max_slots=max_slots, max_text_len=96, max_dec_len=512, max_prefill_tokens=1024)
+                       max_slots=max_slots, max_text_len=96, max_dec_len=512, max_prefill_tokens=1024,
+                       kv_page_tokens=page_tokens)
     sd = {k: v.float().cpu() for k, v in iter_random_state_dict(cfg, seed=3, device="cuda")}
     ocfg = OracleConfig(hidden=cfg.hidden, inter=cfg.inter, n_enc_layers=cfg.n_enc_layers, n_dec_layers=cfg.n_dec_layers,
                         n_heads=cfg.n_heads, n_kv_heads=cfg.n_kv_heads, head_dim=cfg.head_dim,

@@ -212,19 +212,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     cluster.sync();                                   // all partial tiles are parked in shared memory
-    if (warp >= 2 && warp < 6) {
+    // all 8 epilogue warps reduce: warp pair (w, w+4) shares a lane quarter's 32 features and alternates over this rank's
+    // tokens; the remote reads of up to 4 tokens x 8 ranks are issued before anything is summed (a dependent chain of
+    // distributed-shared-memory round trips made this reduction 4x slower than the atomic one: fc1 of the batched head 16 us)
+    if (warp >= 2) {
       const int rank = (int)cluster.block_rank(), nr = p.split_k;
-      const int fl = (warp - 2) * 32 + lane, f = f0 + fl;
+      const int fl = (warp & 3) * 32 + lane, f = f0 + fl;
+      const int hsel = (warp - 2) >> 2;
       const float bias = (p.bias && f < p.N) ? p.bias[f] : 0.f;
       float* red = reinterpret_cast<float*>(&S.w[0][0]);
-      for (int j = rank; j < TOKT && t0 + j < p.M; j += nr) {
-        float acc = 0.f, acc_up = 0.f;
-        for (int r = 0; r < nr; ++r) {
-          const float* rr = cluster.map_shared_rank(red, r);
-          acc += rr[j * TC_BM + fl];
-          if (p.epilogue == GE_GEGLU_BF16) acc_up += rr[j * TC_BM + (fl | 1)];
+      const float* rr[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) rr[r] = cluster.map_shared_rank(red, r < nr ? r : 0);
+      const bool geglu = p.epilogue == GE_GEGLU_BF16;
+      constexpr int UT = 4;                                   // tokens in flight per thread
+      for (int j0 = rank + hsel * nr; j0 < TOKT && t0 + j0 < p.M; j0 += 2 * UT * nr) {
+        float v[UT][8], vu[UT][8];
+#pragma unroll
+        for (int u = 0; u < UT; ++u) {
+          const int j = j0 + u * 2 * nr;
+          const bool ok = j < TOKT && t0 + j < p.M;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            v[u][r] = (ok && r < nr) ? rr[r][j * TC_BM + fl] : 0.f;
+            vu[u][r] = (ok && r < nr && geglu) ? rr[r][j * TC_BM + (fl | 1)] : 0.f;
+          }
         }
-        epilogue_store(p, t0 + j, f, acc, acc_up, bias, (fl & 1) == 0);
+#pragma unroll
+        for (int u = 0; u < UT; ++u) {
+          const int j = j0 + u * 2 * nr;
+          if (j < TOKT && t0 + j < p.M) {
+            float acc = 0.f, acc_up = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { acc += v[u][r]; acc_up += vu[u][r]; }   // rank order: same sum as before
+            epilogue_store(p, t0 + j, f, acc, acc_up, bias, (fl & 1) == 0);
+          }
+        }
       }
     }
     cluster.sync();                                   // peers may still be reading this CTA's shared memory
@@ -482,6 +505,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
   // plain fp32 outputs reduce fastest with red.global.add (measured: 17 vs 21 us at 64x2304x2304); the fused
   // epilogues (bias / GELU / GeGLU / bf16) need the full sum and use the cluster/DSMEM reduction instead
   const int atomic = (split > 1 && a.epilogue == GE_F32) ? 1 : 0;
+  // cluster reduction: at one CTA per SM a GPC hosts two 8-CTA clusters, i.e. 16 on the chip -- more 8-CTA clusters than
+  // that run as a second wave (fc1 of the batched head, 18 tiles x 8: 13.7 us); clusters of 4 fit in one wave
+  if (!atomic && split == 8 && tiles > 16) { split = 4; kbps = (kb_total + split - 1) / split; }
   if (atomic && !a.out_zeroed) {
     cudaError_t e = cudaMemsetAsync(a.out, 0, sizeof(float) * ((size_t)(a.M - 1) * a.ldo + a.N), st);
     if (e != cudaSuccess) return e;

@@ -85,3 +85,37 @@ def test_pth_bundle_names_missing_backbone_geometry(tmp_path):
     torch.save({"model": sd, "args": args}, str(p))
     cfg, _ = ck.load_pth_bundle(str(p))
     assert EngineConfig.from_reference(cfg).hidden == 2304
+
+
+def test_pth_bundle_with_unmerged_lora_adapters(tmp_path):
+    """`use_lora=1` bundles keep PEFT's wrapped names (base_layer / lora_A / lora_B under backbone.base_model.model.);
+    the loader returns the plain reference keys with W + (alpha / r) * B @ A, i.e. what merge_and_unload() produces
+    (scripts/export_t5gemma_voice_hf_lora.py)."""
+    _, sd, meta = fixtures.load_model_fixture("tinyA_eager")
+    g = torch.Generator().manual_seed(0)
+    r, alpha = 4, 8
+    lora_sd, want = {}, {}
+    targets = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
+    for k, v in sd.items():
+        if k.startswith("backbone.") and k.endswith(".weight") and k.split(".")[-2] in targets:
+            pre = "backbone.base_model.model." + k[len("backbone."):-len(".weight")]
+            A, B = torch.randn(r, v.shape[1], generator=g) * 0.1, torch.randn(v.shape[0], r, generator=g) * 0.1
+            lora_sd[pre + ".base_layer.weight"] = v
+            lora_sd[pre + ".lora_A.default.weight"] = A
+            lora_sd[pre + ".lora_B.default.weight"] = B
+            want[k] = v + (alpha / r) * (B @ A)
+        elif k.startswith("backbone."):
+            lora_sd["backbone.base_model.model." + k[len("backbone."):]] = v
+            want[k] = v
+        else:
+            lora_sd[k] = v
+            want[k] = v
+    args = argparse.Namespace(audio_vocab_size=100, use_lora=1, lora_r=r, lora_alpha=alpha)
+    p = tmp_path / "bundle_lora.pth"
+    torch.save({"model": lora_sd, "args": args}, str(p))
+    cfg, got = ck.load_pth_bundle(str(p), t5_config_dict=meta["t5_config_dict"])
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.allclose(got[k], want[k], atol=1e-6), k
+    n_merged = sum(1 for k in want if not torch.equal(want[k], sd[k]))
+    assert n_merged == 7 * 3 + 7 * 3 + 4 * 3       # 7 projections per layer side (3+3 layers) + 4 cross projections per decoder layer

@@ -62,3 +62,75 @@ def generate_batch(engine, requests: List[GenerationRequest], chunk_steps: int =
         res.append((strip_sep_and_eos(concat.numpy(), cfg.y_sep_token, cfg.stop_token),
                     strip_sep_and_eos(gen.numpy(), cfg.y_sep_token, cfg.stop_token)))
     return res
+
+
+def inference_batch(engine, model_args, text_tokenizer, audio_tokenizer, items, decode_config, tokenize_audio_fn=None,
+                    normalize_text_fn=None, chunk_steps: int = 32, return_frames: bool = False):
+    """Multi-utterance front door: what inference_tts_utils.inference_one_sample (`:141-379`) does for ONE utterance, done
+    for a list so that batch sizes > 1 are reachable from the CLI / UI code.  `items` is a sequence of dicts with the
+    per-utterance arguments of inference_one_sample: `target_text`, `target_generation_length` (seconds) and optionally
+    `audio_fn` (reference speech; None / "" / "none" = no voice prompt), `prompt_end_frame`, `prefix_transcript`, `lang`.
+    `decode_config` carries the same keys (`top_k`, `top_p`, `min_p`, `temperature`, `stop_repetition`, `silence_tokens`,
+    `codec_sr`).  Tokenisers stay the reference's objects: `text_tokenizer.encode(text, add_special_tokens=False)`,
+    `audio_tokenizer.decode(frames)`, and `tokenize_audio_fn(audio_tokenizer, audio_fn, offset=0, num_frames=...)`
+    (= data.tokenizer.tokenize_audio); `normalize_text_fn(text, lang) -> (text, lang)` is the reference's
+    `normalize_text_with_lang` when Japanese normalisation is wanted.
+    Returns a list of `(concat_sample, gen_sample)` (plus the stripped frames with `return_frames`), in item order."""
+    import torch
+    silence = decode_config.get("silence_tokens", [])
+    if isinstance(silence, str):
+        import ast
+        silence = ast.literal_eval(silence)
+    if int(getattr(model_args, "n_codebooks", 1)) != 1:
+        raise ValueError("XCodec2 backend supports only n_codebooks=1.")
+    cfg = SimpleNamespaceView(model_args, encodec_sr=int(decode_config.get("codec_sr", getattr(model_args, "encodec_sr", 50))))
+    requests, has_ref = [], []
+
+    def encode_text(text):
+        if isinstance(text, list):
+            text = " ".join(text)
+        return list(text_tokenizer.encode(text.strip(), add_special_tokens=False))
+
+    for it in items:
+        audio_fn = it.get("audio_fn")
+        ref = audio_fn is not None and str(audio_fn).lower() not in {"", "none", "null"}
+        prompt = None
+        if ref:
+            if tokenize_audio_fn is None:
+                from data.tokenizer import tokenize_audio as tokenize_audio_fn      # the reference's own helper
+            pef = int(it.get("prompt_end_frame", -1))
+            frames = tokenize_audio_fn(audio_tokenizer, audio_fn, offset=0, num_frames=pef if pef > 0 else -1)
+            prompt = torch.as_tensor(frames).reshape(-1).cpu().numpy()
+        text, lang = it["target_text"], it.get("lang")
+        prefix = it.get("prefix_transcript")
+        if normalize_text_fn is not None:
+            text, lang = normalize_text_fn(text, lang)
+            if prefix:
+                prefix, _ = normalize_text_fn(prefix, lang)
+        requests.append(build_request(cfg, encode_text(text), float(it["target_generation_length"]), prompt_codes=prompt,
+                                      prefix_text_ids=encode_text(prefix) if prefix else None,
+                                      top_k=decode_config["top_k"], top_p=decode_config["top_p"], min_p=decode_config.get("min_p", 0.0),
+                                      temperature=decode_config["temperature"], stop_repetition=decode_config.get("stop_repetition", 3),
+                                      silence_tokens=silence))
+        has_ref.append(ref)
+    outs = generate_batch(engine, requests, chunk_steps=chunk_steps)
+    res = []
+    for (concat, gen), ref in zip(outs, has_ref):
+        concat_t, gen_t = torch.from_numpy(np.ascontiguousarray(concat)), torch.from_numpy(np.ascontiguousarray(gen))
+        gen_sample = audio_tokenizer.decode(gen_t)
+        concat_sample = audio_tokenizer.decode(concat_t) if ref else gen_sample
+        res.append((concat_sample, gen_sample, concat_t, gen_t) if return_frames else (concat_sample, gen_sample))
+    return res
+
+
+class SimpleNamespaceView:
+    """model_args with a few fields overridden (the front door takes codec_sr from decode_config, not from the model)."""
+
+    def __init__(self, base, **over):
+        self._base, self._over = base, over
+
+    def __getattr__(self, name):
+        over = object.__getattribute__(self, "_over")
+        if name in over:
+            return over[name]
+        return getattr(object.__getattribute__(self, "_base"), name)

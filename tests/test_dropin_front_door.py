@@ -168,3 +168,32 @@ def test_engine_is_a_drop_in_for_inference_one_sample(with_prompt):
     # the codec stub received the stripped frames in both runs
     assert torch.equal(e_tok.decoded[-1], e_gf) and torch.equal(r_tok.decoded[-1], r_gf)
     assert e_gs.shape == r_gs.shape and e_cs.shape == r_cs.shape
+
+
+@needs_reference
+@pytest.mark.gpu
+def test_batched_front_door_equals_one_sample_per_utterance():
+    """request_glue.inference_batch (bs > 1 reachable from the CLI / UI code) must hand the codec, for every utterance, exactly
+    what the reference's inference_one_sample hands it when the same engine is driven one utterance at a time (the bs <= 4
+    decode path is row-independent bit for bit)."""
+    from tests.gpu_util import engine_for
+    from t5gemma_tts_b200.request_glue import inference_batch
+    fd = load_front_door()
+    eng = engine_for("tinyA_eager", max_slots=3, max_prefill_tokens=1024)
+    c = fixtures.load_case("tinyA_eager_prompt")
+    text = " ".join(str(int(t)) for t in c["x"][0])
+    prompt = c["y"][0, :, 0]
+    items = [dict(audio_fn="ref.wav", target_text=text, target_generation_length=0.2),
+             dict(audio_fn=None, target_text="5 6 7 8 9", target_generation_length=0.3),
+             dict(audio_fn="ref.wav", target_text="11 12 13", target_generation_length=0.1, prefix_transcript="3 4")]
+    tok = StubAudioTokenizer(prompt, "cuda")
+    batch = inference_batch(eng, eng.args, StubTextTokenizer(), tok, items, DECODE,
+                            tokenize_audio_fn=lambda t, fn, offset=-1, num_frames=-1: t.prompt_codes.clone(), return_frames=True)
+    for it, (b_cs, b_gs, b_cf, b_gf) in zip(items, batch):
+        tok1 = StubAudioTokenizer(prompt, "cuda")
+        _, _, o_cf, o_gf = fd.inference_one_sample(eng, eng.args, StubTextTokenizer(), tok1, it["audio_fn"], it["target_text"], "en",
+                                                   "cuda", DECODE, prompt_end_frame=-1,
+                                                   target_generation_length=it["target_generation_length"],
+                                                   prefix_transcript=it.get("prefix_transcript"), quiet=True, return_frames=True)
+        assert torch.equal(b_gf, o_gf) and torch.equal(b_cf, o_cf)
+        assert b_gs.shape == o_gf.shape

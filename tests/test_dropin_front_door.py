@@ -187,11 +187,13 @@ def test_batched_front_door_equals_one_sample_per_utterance():
              dict(audio_fn=None, target_text="5 6 7 8 9", target_generation_length=0.3),
              dict(audio_fn="ref.wav", target_text="11 12 13", target_generation_length=0.1, prefix_transcript="3 4")]
     tok = StubAudioTokenizer(prompt, "cuda")
-    batch = inference_batch(eng, eng.args, StubTextTokenizer(), tok, items, DECODE,
+    args = SimpleNamespace(**vars(eng.args))
+    args.x_sep_token = 7                      # the production id (255999) is outside the tiny model's text vocabulary
+    batch = inference_batch(eng, args, StubTextTokenizer(), tok, items, DECODE,
                             tokenize_audio_fn=lambda t, fn, offset=-1, num_frames=-1: t.prompt_codes.clone(), return_frames=True)
     for it, (b_cs, b_gs, b_cf, b_gf) in zip(items, batch):
         tok1 = StubAudioTokenizer(prompt, "cuda")
-        _, _, o_cf, o_gf = fd.inference_one_sample(eng, eng.args, StubTextTokenizer(), tok1, it["audio_fn"], it["target_text"], "en",
+        _, _, o_cf, o_gf = fd.inference_one_sample(eng, args, StubTextTokenizer(), tok1, it["audio_fn"], it["target_text"], "en",
                                                    "cuda", DECODE, prompt_end_frame=-1,
                                                    target_generation_length=it["target_generation_length"],
                                                    prefix_transcript=it.get("prefix_transcript"), quiet=True, return_frames=True)

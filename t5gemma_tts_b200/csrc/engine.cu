@@ -198,13 +198,20 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ---- GEMM dispatch (prefill / batched path) ----------------------------------------------------
 cudaError_t gemm(T5GEngine* e, const bf16* A, const bf16* W, int M, int N, int K, int epi, const float* bias,
-                 void* out, int ldo, cudaStream_t st) {
-  GemmArgs g{A, W, M, N, K, epi, bias, out, ldo, 0};
+                 void* out, int ldo, cudaStream_t st, int out_zeroed = 0) {
+  GemmArgs g{A, W, M, N, K, epi, bias, out, ldo, out_zeroed};
   e->launches++;
   // programmatic dependent launch in the prefill chain as well: the GEMM streams its first weight tiles while the previous
   // kernel drains (kernels that are not PDL-aware simply complete first)
   if (e->gemm_impl == 1 && gemm_tc_supported(g)) return launch_gemm_tc(g, st, e->num_sms, e->use_pdl);
   return launch_gemm_simt(g, st);
+}
+
+// true when the fp32 GEMM [M,N] = A[M,K] W^T will run split-K with red.global.add: the kernel before it zeroes the output
+// (norm_kernel's side job) so that no memset node interrupts the programmatic-dependent-launch chain of a small prefill
+bool wants_zero(T5GEngine* e, int M, int N, int K) {
+  GemmArgs g{e->p_xn, e->p_xn, M, N, K, GE_F32, nullptr, e->p_y, N, 0};
+  return e->gemm_impl == 1 && gemm_tc_wants_zeroed_out(g, e->num_sms);
 }
 
 #define CU(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { t5g_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); return T5G_ERR_CUDA; } } while (0)
@@ -611,13 +618,17 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   CU(cudaEventRecord(e->ev[0], st));
   { int rc = stage_and_upload(false); if (rc) return rc; }
   CU(launch_embed(e->enc_embed, e->p_ids, sqrtf((float)d), e->p_h, Te, d, st)); e->launches++;
+  const int ze_qkv = wants_zero(e, Te, QKV, d), ze_o = wants_zero(e, Te, d, QD), ze_down = wants_zero(e, Te, d, I);
   for (int l = 0; l < c.n_enc_layers; ++l) {
     const EncLayer& L = e->enc[l];
     // h += post_ff(prev y) ; xn = pre_sa(h)
-    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl));
-    else CU(launch_norm(e->p_h, e->p_y, e->enc[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl));
+    // small prefills: the norm kernels zero the fp32 outputs of the split-K GEMMs that follow them (after reading them)
+    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl,
+                               ze_qkv ? e->p_qkv : nullptr, QKV, ze_o ? e->p_y : nullptr, d));
+    else CU(launch_norm(e->p_h, e->p_y, e->enc[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl,
+                        ze_qkv ? e->p_qkv : nullptr, QKV, ze_o ? e->p_y : nullptr, d));
     e->launches++;
-    CU(gemm(e, e->p_xn, L.wqkv, Te, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st));
+    CU(gemm(e, e->p_xn, L.wqkv, Te, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st, ze_qkv));
     RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Te;
     ra.Hq = e->Hq; ra.Hkv = e->Hkv; ra.D = D; ra.inv_freq = e->inv_freq; ra.q_out = e->p_q; ra.k_out = e->p_k; ra.v_out = e->p_v; ra.block_table = nullptr;
     CU(launch_rope_split(ra, st)); e->launches++;
@@ -625,10 +636,11 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     aa.Tq = Te; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.D = D; aa.causal = 0; aa.window = c.enc_layer_sliding[l] ? c.sliding_window : 0;
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
     CU(prefill_attention(e, aa, e->p_v, e->p_vt_off_e, Te, n_req, max_text, max_text, st));
-    CU(gemm(e, e->p_att, L.wo, Te, d, QD, GE_F32, nullptr, e->p_y, d, st));
-    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl)); e->launches++;
+    CU(gemm(e, e->p_att, L.wo, Te, d, QD, GE_F32, nullptr, e->p_y, d, st, ze_o));
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl,
+                   ze_down ? e->p_y : nullptr, d)); e->launches++;
     CU(gemm(e, e->p_xn, L.wgu, Te, 2 * I, d, GE_GEGLU_BF16, nullptr, e->p_act, I, st));
-    CU(gemm(e, e->p_act, L.wd, Te, d, I, GE_F32, nullptr, e->p_y, d, st));
+    CU(gemm(e, e->p_act, L.wd, Te, d, I, GE_F32, nullptr, e->p_y, d, st, ze_down));
   }
   // memory = final_norm(h + post_ff(y))
   CU(launch_norm(e->p_h, e->p_y, e->enc[c.n_enc_layers - 1].g_post_ff, e->g_enc_final, nullptr, e->p_mem_bf, e->p_memory, Te, d, c.rms_eps, st, e->use_pdl)); e->launches++;
@@ -649,12 +661,16 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   { int rc = stage_and_upload(true); if (rc) return rc; }
   CU(cudaMemcpyAsync(e->p_last_rows, h_last, sizeof(int) * n_req, cudaMemcpyHostToDevice, st));
   CU(launch_embed(e->audio_emb, e->p_ids, sqrtf((float)d), e->p_h, Td, d, st)); e->launches++;
+  const int zd_qkv = wants_zero(e, Td, QKV, d), zd_o = wants_zero(e, Td, d, QD), zd_qc = wants_zero(e, Td, QD, d),
+            zd_down = wants_zero(e, Td, d, I);
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
-    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl));
-    else CU(launch_norm(e->p_h, e->p_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl));
+    if (l == 0) CU(launch_norm(e->p_h, nullptr, nullptr, L.g_pre_sa, nullptr, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl,
+                               zd_qkv ? e->p_qkv : nullptr, QKV, zd_o ? e->p_y : nullptr, d));
+    else CU(launch_norm(e->p_h, e->p_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl,
+                        zd_qkv ? e->p_qkv : nullptr, QKV, zd_o ? e->p_y : nullptr, d));
     e->launches++;
-    CU(gemm(e, e->p_xn, L.wqkv, Td, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st));
+    CU(gemm(e, e->p_xn, L.wqkv, Td, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st, zd_qkv));
     RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Td;
     ra.Hq = e->Hq; ra.Hkv = e->Hkv; ra.D = D; ra.inv_freq = e->inv_freq; ra.q_out = e->p_q; ra.k_out = e->p_k; ra.v_out = e->p_v;
     ra.pool = e->pool; ra.layer = l; ra.block_table = e->d_self_bt; ra.bt_stride = e->max_self_pages; ra.tok_slot = e->p_tok_slot; ra.tok_idx = e->p_tok_idx;
@@ -663,10 +679,12 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     aa.Tq = Td; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.D = D; aa.causal = 1; aa.window = c.dec_layer_sliding[l] ? c.sliding_window : 0;
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
     CU(prefill_attention(e, aa, e->p_v, e->p_vt_off_d, Td, n_req, max_dec, max_dec, st));
-    CU(gemm(e, e->p_att, L.wo, Td, d, QD, GE_F32, nullptr, e->p_y, d, st));
-    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ca, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl)); e->launches++;
+    CU(gemm(e, e->p_att, L.wo, Td, d, QD, GE_F32, nullptr, e->p_y, d, st, zd_o));
+    // p_qkv is free again (RoPE split consumed it): rows of width QD for the cross q projection; p_y for o_cross
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ca, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl,
+                   zd_qc ? e->p_qkv : nullptr, QD, zd_o ? e->p_y : nullptr, d)); e->launches++;
     // cross attention: q = RoPE(q_proj(x), decoder pos); K/V of this layer computed once from memory
-    CU(gemm(e, e->p_xn, L.wq_c, Td, QD, d, GE_F32, nullptr, e->p_qkv, QD, st));
+    CU(gemm(e, e->p_xn, L.wq_c, Td, QD, d, GE_F32, nullptr, e->p_qkv, QD, st, zd_qc));
     RopeSplitArgs rq{}; rq.qkv = e->p_qkv; rq.ld = QD; rq.q_off = 0; rq.k_off = -1; rq.v_off = -1; rq.pos = e->p_pos; rq.M = Td;
     rq.Hq = e->Hq; rq.Hkv = e->Hkv; rq.D = D; rq.inv_freq = e->inv_freq; rq.q_out = e->p_q; rq.block_table = nullptr;
     CU(launch_rope_split(rq, st)); e->launches++;
@@ -678,10 +696,11 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     AttnPrefillArgs ac{}; ac.q = e->p_q; ac.k = e->p_ck; ac.v = e->p_cv; ac.q_seg_off = e->p_seg_off_d; ac.k_seg_off = e->p_seg_off_e; ac.q_seg_of = e->p_seg_of;
     ac.Tq = Td; ac.Hq = e->Hq; ac.Hkv = e->Hkv; ac.D = D; ac.causal = 0; ac.window = 0; ac.scale = c.attn_scale; ac.softcap = c.attn_softcap; ac.out = e->p_att;
     CU(prefill_attention(e, ac, e->p_cv, e->p_vt_off_e, Te, n_req, max_dec, max_text, st));
-    CU(gemm(e, e->p_att, L.wo_c, Td, d, QD, GE_F32, nullptr, e->p_y, d, st));
-    CU(launch_norm(e->p_h, e->p_y, L.g_post_ca, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl)); e->launches++;
+    CU(gemm(e, e->p_att, L.wo_c, Td, d, QD, GE_F32, nullptr, e->p_y, d, st, zd_o));
+    CU(launch_norm(e->p_h, e->p_y, L.g_post_ca, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl,
+                   zd_down ? e->p_y : nullptr, d)); e->launches++;
     CU(gemm(e, e->p_xn, L.wgu, Td, 2 * I, d, GE_GEGLU_BF16, nullptr, e->p_act, I, st));
-    CU(gemm(e, e->p_act, L.wd, Td, d, I, GE_F32, nullptr, e->p_y, d, st));
+    CU(gemm(e, e->p_act, L.wd, Td, d, I, GE_F32, nullptr, e->p_y, d, st, zd_down));
   }
   // h = h + post_ff(y) (kept, pre-final-norm) ; p_qkv <- final_norm(h) fp32 for teacher-forced logits
   CU(launch_norm(e->p_h, e->p_y, e->dec[c.n_dec_layers - 1].g_post_ff, e->g_dec_final, e->p_h, nullptr, e->p_final, Td, d, c.rms_eps, st, e->use_pdl)); e->launches++;

@@ -490,6 +490,25 @@ bool gemm_tc_supported(const GemmArgs& a) {
          (reinterpret_cast<uintptr_t>(a.W) & 15) == 0 && (a.epilogue != GE_GEGLU_BF16 || a.N % 2 == 0);
 }
 
+// split-K factor of a launch: K is cut over CTAs while the tile grid is smaller than the machine (weight-streaming regime)
+static int tc_split(int M, int N, int K, int num_sms, int* kbps_out) {
+  const int tokt = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+  const int kb_total = K / TC_BK;
+  const int tiles = ((N + TC_BM - 1) / TC_BM) * ((M + tokt - 1) / tokt);
+  int split = 1;
+  while (split < 8 && tiles * split * 2 <= num_sms + num_sms / 4 && kb_total / (split * 2) >= 3) split *= 2;
+  int kbps = (kb_total + split - 1) / split;
+  while (split > 1 && (split - 1) * kbps >= kb_total) { split >>= 1; kbps = (kb_total + split - 1) / split; }
+  if (kbps_out) *kbps_out = kbps;
+  return split;
+}
+
+// true when this launch accumulates split-K partials with red.global.add into `out`: the caller may zero `out` itself
+// (out_zeroed = 1, e.g. in the kernel that runs before) instead of paying a memset node that also breaks the PDL chain
+bool gemm_tc_wants_zeroed_out(const GemmArgs& a, int num_sms) {
+  return a.M > 0 && gemm_tc_supported(a) && a.epilogue == GE_F32 && tc_split(a.M, a.N, a.K, num_sms, nullptr) > 1;
+}
+
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool pdl) {
   if (a.M <= 0) return cudaSuccess;
   if (!gemm_tc_supported(a)) return cudaErrorNotSupported;
@@ -498,10 +517,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
   if (!make_map_2d(&mw, a.W, a.N, a.K, a.K, TC_BM) || !make_map_2d(&mx, a.A, a.M, a.K, a.K, tokt)) return cudaErrorNotSupported;
   const int kb_total = a.K / TC_BK;
   const int tiles = ((a.N + TC_BM - 1) / TC_BM) * ((a.M + tokt - 1) / tokt);
-  int split = 1;                                          // weight-streaming regime: fill the machine along K
-  while (split < 8 && tiles * split * 2 <= num_sms + num_sms / 4 && kb_total / (split * 2) >= 3) split *= 2;
-  int kbps = (kb_total + split - 1) / split;
-  while (split > 1 && (split - 1) * kbps >= kb_total) { split >>= 1; kbps = (kb_total + split - 1) / split; }
+  int kbps = 0;
+  int split = tc_split(a.M, a.N, a.K, num_sms, &kbps);
   // plain fp32 outputs reduce fastest with red.global.add (measured: 17 vs 21 us at 64x2304x2304); the fused
   // epilogues (bias / GELU / GeGLU / bf16) need the full sum and use the cluster/DSMEM reduction instead
   const int atomic = (split > 1 && a.epilogue == GE_F32) ? 1 : 0;

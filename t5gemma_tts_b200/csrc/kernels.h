@@ -130,6 +130,7 @@ struct GemmArgs {
 cudaError_t launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool pdl = false);   // tcgen05/TMEM/TMA path (gemm_tc.cu)
 bool gemm_tc_supported(const GemmArgs& a);
+bool gemm_tc_wants_zeroed_out(const GemmArgs& a, int num_sms);   // split-K with red.global.add: `out` must start at zero
 // h[b] = table[slots[b].last_token] * scale for every row (batched decode step)
 cudaError_t launch_embed_slots(const bf16* table, const SlotDev* slots, float scale, float* h, int B, int d, cudaStream_t st, bool pdl = false);
 cudaError_t launch_gather_rows(const float* src, const int* rows, float* dst, int n, int d, cudaStream_t st);

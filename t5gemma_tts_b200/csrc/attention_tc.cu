@@ -96,6 +96,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   constexpr int TMEM_COLS = 512;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int seg = blockIdx.z, h = blockIdx.y, hk = h / (p.Hq / p.Hkv);
+  pdl_launch_dependents();           // programmatic dependent in the prefill chain: nothing is read before the wait
+  pdl_wait();
   const int q_beg = p.q_seg_off[seg], Lq = p.q_seg_off[seg + 1] - q_beg;
   const int k_beg = p.k_seg_off[seg], Lk = p.k_seg_off[seg + 1] - k_beg;
   const int vt_beg = p.vt_seg_off[seg];
@@ -308,6 +310,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 __global__ void transpose_v_kernel(const bf16* __restrict__ v, bf16* __restrict__ vt, const int* __restrict__ k_seg_off,
                                    const int* __restrict__ vt_seg_off, int C, int ldt) {
   __shared__ bf16 tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int seg = blockIdx.z;
   const int t_beg = k_seg_off[seg], L = k_seg_off[seg + 1] - t_beg;
   const int o_beg = vt_seg_off[seg], o_len = vt_seg_off[seg + 1] - o_beg;
@@ -325,7 +329,7 @@ __global__ void transpose_v_kernel(const bf16* __restrict__ v, bf16* __restrict_
 }
 
 template <int D>
-cudaError_t launch_fa(const AttnPrefillArgs& a, const bf16* vt, const int* vt_seg_off, int ldt, int Tk, int n_seg, int max_lq, cudaStream_t st) {
+cudaError_t launch_fa(const AttnPrefillArgs& a, const bf16* vt, const int* vt_seg_off, int ldt, int Tk, int n_seg, int max_lq, cudaStream_t st, bool pdl) {
   CUtensorMap mq, mk, mv;
   if (!make_map_2d(&mq, a.q, a.Tq, (uint64_t)a.Hq * D, (uint64_t)a.Hq * D, FA_BQ) ||
       !make_map_2d(&mk, a.k, Tk, (uint64_t)a.Hkv * D, (uint64_t)a.Hkv * D, FA_BK) ||
@@ -340,9 +344,17 @@ cudaError_t launch_fa(const AttnPrefillArgs& a, const bf16* vt, const int* vt_se
     attr_set.here() = 1;
   }
   FaParams p{a.q_seg_off, a.k_seg_off, vt_seg_off, a.Hq, a.Hkv, a.causal, a.window, a.scale, a.softcap, a.out};
-  dim3 grid((max_lq + FA_BQ - 1) / FA_BQ, a.Hq, n_seg);
-  kern<<<grid, FA_THREADS, smem, st>>>(mq, mk, mv, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((max_lq + FA_BQ - 1) / FA_BQ, a.Hq, n_seg);
+  cfg.blockDim = dim3(FA_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, p);
 }
 
 }  // namespace
@@ -350,20 +362,27 @@ cudaError_t launch_fa(const AttnPrefillArgs& a, const bf16* vt, const int* vt_se
 bool attn_prefill_tc_supported(int D) { return D == 64 || D == 128 || D == 256; }
 
 cudaError_t launch_transpose_v(const bf16* v, bf16* vt, const int* k_seg_off, const int* vt_seg_off, int n_seg, int max_lk,
-                               int C, int ldt, cudaStream_t st) {
+                               int C, int ldt, cudaStream_t st, bool pdl) {
   if (n_seg <= 0 || max_lk <= 0) return cudaSuccess;
-  dim3 grid((max_lk + 8 + 31) / 32, (C + 31) / 32, n_seg), block(32, 8);
-  transpose_v_kernel<<<grid, block, 0, st>>>(v, vt, k_seg_off, vt_seg_off, C, ldt);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((max_lk + 8 + 31) / 32, (C + 31) / 32, n_seg);
+  cfg.blockDim = dim3(32, 8);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, transpose_v_kernel, v, vt, k_seg_off, vt_seg_off, C, ldt);
 }
 
 cudaError_t launch_attn_prefill_tc(const AttnPrefillArgs& a, const bf16* vt, const int* vt_seg_off, int ldt, int Tk, int n_seg,
-                                   int max_lq, cudaStream_t st) {
+                                   int max_lq, cudaStream_t st, bool pdl) {
   if (a.Tq <= 0 || n_seg <= 0) return cudaSuccess;
   switch (a.D) {
-    case 64: return launch_fa<64>(a, vt, vt_seg_off, ldt, Tk, n_seg, max_lq, st);
-    case 128: return launch_fa<128>(a, vt, vt_seg_off, ldt, Tk, n_seg, max_lq, st);
-    case 256: return launch_fa<256>(a, vt, vt_seg_off, ldt, Tk, n_seg, max_lq, st);
+    case 64: return launch_fa<64>(a, vt, vt_seg_off, ldt, Tk, n_seg, max_lq, st, pdl);
+    case 128: return launch_fa<128>(a, vt, vt_seg_off, ldt, Tk, n_seg, max_lq, st, pdl);
+    case 256: return launch_fa<256>(a, vt, vt_seg_off, ldt, Tk, n_seg, max_lq, st, pdl);
     default: return cudaErrorNotSupported;
   }
 }

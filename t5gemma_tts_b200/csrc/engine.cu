@@ -458,10 +458,10 @@ struct StackIO {
 static cudaError_t prefill_attention(T5GEngine* e, const AttnPrefillArgs& a, const bf16* v, const int* vt_off, int Tk, int n_seg,
                                      int max_lq, int max_lk, cudaStream_t st) {
   if (e->use_tc_attn && attn_prefill_tc_supported(a.D)) {
-    cudaError_t er = launch_transpose_v(v, e->p_vt, a.k_seg_off, vt_off, n_seg, max_lk, a.Hkv * a.D, e->vt_ld, st);
+    cudaError_t er = launch_transpose_v(v, e->p_vt, a.k_seg_off, vt_off, n_seg, max_lk, a.Hkv * a.D, e->vt_ld, st, e->use_pdl);
     if (er != cudaSuccess) return er;
     e->launches += 2;
-    return launch_attn_prefill_tc(a, e->p_vt, vt_off, e->vt_ld, Tk, n_seg, max_lq, st);
+    return launch_attn_prefill_tc(a, e->p_vt, vt_off, e->vt_ld, Tk, n_seg, max_lq, st, e->use_pdl);
   }
   e->launches++;
   return launch_attn_prefill(a, st);
@@ -631,7 +631,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     CU(gemm(e, e->p_xn, L.wqkv, Te, QKV, d, GE_F32, nullptr, e->p_qkv, QKV, st, ze_qkv));
     RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Te;
     ra.Hq = e->Hq; ra.Hkv = e->Hkv; ra.D = D; ra.inv_freq = e->inv_freq; ra.q_out = e->p_q; ra.k_out = e->p_k; ra.v_out = e->p_v; ra.block_table = nullptr;
-    CU(launch_rope_split(ra, st)); e->launches++;
+    CU(launch_rope_split(ra, st, e->use_pdl)); e->launches++;
     AttnPrefillArgs aa{}; aa.q = e->p_q; aa.k = e->p_k; aa.v = e->p_v; aa.q_seg_off = e->p_seg_off_e; aa.k_seg_off = e->p_seg_off_e; aa.q_seg_of = e->p_seg_of;
     aa.Tq = Te; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.D = D; aa.causal = 0; aa.window = c.enc_layer_sliding[l] ? c.sliding_window : 0;
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
@@ -674,7 +674,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     RopeSplitArgs ra{}; ra.qkv = e->p_qkv; ra.ld = QKV; ra.q_off = 0; ra.k_off = QD; ra.v_off = QD + KD; ra.pos = e->p_pos; ra.M = Td;
     ra.Hq = e->Hq; ra.Hkv = e->Hkv; ra.D = D; ra.inv_freq = e->inv_freq; ra.q_out = e->p_q; ra.k_out = e->p_k; ra.v_out = e->p_v;
     ra.pool = e->pool; ra.layer = l; ra.block_table = e->d_self_bt; ra.bt_stride = e->max_self_pages; ra.tok_slot = e->p_tok_slot; ra.tok_idx = e->p_tok_idx;
-    CU(launch_rope_split(ra, st)); e->launches++;
+    CU(launch_rope_split(ra, st, e->use_pdl)); e->launches++;
     AttnPrefillArgs aa{}; aa.q = e->p_q; aa.k = e->p_k; aa.v = e->p_v; aa.q_seg_off = e->p_seg_off_d; aa.k_seg_off = e->p_seg_off_d; aa.q_seg_of = e->p_seg_of;
     aa.Tq = Td; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.D = D; aa.causal = 1; aa.window = c.dec_layer_sliding[l] ? c.sliding_window : 0;
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
@@ -687,12 +687,12 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     CU(gemm(e, e->p_xn, L.wq_c, Td, QD, d, GE_F32, nullptr, e->p_qkv, QD, st, zd_qc));
     RopeSplitArgs rq{}; rq.qkv = e->p_qkv; rq.ld = QD; rq.q_off = 0; rq.k_off = -1; rq.v_off = -1; rq.pos = e->p_pos; rq.M = Td;
     rq.Hq = e->Hq; rq.Hkv = e->Hkv; rq.D = D; rq.inv_freq = e->inv_freq; rq.q_out = e->p_q; rq.block_table = nullptr;
-    CU(launch_rope_split(rq, st)); e->launches++;
+    CU(launch_rope_split(rq, st, e->use_pdl)); e->launches++;
     CU(gemm(e, e->p_mem_bf, L.wkv_c, Te, 2 * KD, d, GE_F32, nullptr, e->p_ckv, 2 * KD, st));
     RopeSplitArgs rk{}; rk.qkv = e->p_ckv; rk.ld = 2 * KD; rk.q_off = -1; rk.k_off = 0; rk.v_off = KD; rk.pos = pos_e; rk.M = Te;
     rk.Hq = e->Hq; rk.Hkv = e->Hkv; rk.D = D; rk.inv_freq = e->inv_freq; rk.k_out = e->p_ck; rk.v_out = e->p_cv;
     rk.pool = e->pool; rk.layer = l; rk.block_table = e->d_cross_bt; rk.bt_stride = e->max_cross_pages; rk.tok_slot = tslot_e; rk.tok_idx = tidx_e;
-    CU(launch_rope_split(rk, st)); e->launches++;
+    CU(launch_rope_split(rk, st, e->use_pdl)); e->launches++;
     AttnPrefillArgs ac{}; ac.q = e->p_q; ac.k = e->p_ck; ac.v = e->p_cv; ac.q_seg_off = e->p_seg_off_d; ac.k_seg_off = e->p_seg_off_e; ac.q_seg_of = e->p_seg_of;
     ac.Tq = Td; ac.Hq = e->Hq; ac.Hkv = e->Hkv; ac.D = D; ac.causal = 0; ac.window = 0; ac.scale = c.attn_scale; ac.softcap = c.attn_softcap; ac.out = e->p_att;
     CU(prefill_attention(e, ac, e->p_cv, e->p_vt_off_e, Te, n_req, max_dec, max_text, st));

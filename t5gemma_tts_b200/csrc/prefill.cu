@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(NK_THREADS) norm_kernel(const float* h_in, con
 
 // one CTA per token; threads over (head, j<D/2)
 __global__ void rope_split_kernel(RopeSplitArgs a) {
+  pdl_launch_dependents();           // launched as a programmatic dependent in the prefill chain: nothing is read before the wait
+  pdl_wait();
   const int t = blockIdx.x;
   const int D = a.D, half = D / 2;
   const float pos = a.pos ? a.pos[t] : 0.f;
@@ -297,10 +299,18 @@ cudaError_t launch_norm(const float* h_in, const float* y, const float* g_post, 
   return cudaLaunchKernelEx(&cfg, norm_kernel<512, 2>, h_in, y, g_post, g_pre, h_out, xn, xf, d, eps, zero_a, na, zero_b, nb, trace);
 }
 
-cudaError_t launch_rope_split(const RopeSplitArgs& a, cudaStream_t st) {
+cudaError_t launch_rope_split(const RopeSplitArgs& a, cudaStream_t st, bool pdl) {
   if (a.M <= 0) return cudaSuccess;
-  rope_split_kernel<<<a.M, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(a.M);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, rope_split_kernel, a);
 }
 
 cudaError_t launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {

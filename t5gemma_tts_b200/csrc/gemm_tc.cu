@@ -100,7 +100,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   // dynamic shared memory is only guaranteed 16-byte aligned: realign to the 1024 B the swizzle atom needs
   TcSmem<TOKT, NSTAGE>& S = *reinterpret_cast<TcSmem<TOKT, NSTAGE>*>(
       (reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
-  constexpr int TMEM_COLS = TOKT < 32 ? 32 : TOKT;
+  constexpr int TMEM_COLS = TOKT < 32 ? 32 : TOKT == 192 ? 256 : TOKT;     // power of two
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f0 = blockIdx.x * TC_BM, t0 = blockIdx.y * TOKT;
   const int kb_total = p.K / TC_BK;
@@ -490,9 +490,13 @@ bool gemm_tc_supported(const GemmArgs& a) {
          (reinterpret_cast<uintptr_t>(a.W) & 15) == 0 && (a.epilogue != GE_GEGLU_BF16 || a.N % 2 == 0);
 }
 
+// token tile (UMMA N) of a launch.  192 serves the voice-prompt prefill of one utterance (152 tokens): a 5-stage ring with
+// 24 KB activation tiles instead of 4 stages with 32 KB tiles, a third of which would be padding
+static int tc_tokt(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : M <= 192 ? 192 : 256; }
+
 // split-K factor of a launch: K is cut over CTAs while the tile grid is smaller than the machine (weight-streaming regime)
 static int tc_split(int M, int N, int K, int num_sms, int* kbps_out) {
-  const int tokt = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+  const int tokt = tc_tokt(M);
   const int kb_total = K / TC_BK;
   const int tiles = ((N + TC_BM - 1) / TC_BM) * ((M + tokt - 1) / tokt);
   int split = 1;
@@ -512,7 +516,7 @@ bool gemm_tc_wants_zeroed_out(const GemmArgs& a, int num_sms) {
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool pdl) {
   if (a.M <= 0) return cudaSuccess;
   if (!gemm_tc_supported(a)) return cudaErrorNotSupported;
-  const int tokt = a.M <= 16 ? 16 : a.M <= 32 ? 32 : a.M <= 64 ? 64 : a.M <= 128 ? 128 : 256;
+  const int tokt = tc_tokt(a.M);
   CUtensorMap mw, mx;
   if (!make_map_2d(&mw, a.W, a.N, a.K, a.K, TC_BM) || !make_map_2d(&mx, a.A, a.M, a.K, a.K, tokt)) return cudaErrorNotSupported;
   const int kb_total = a.K / TC_BK;
@@ -542,6 +546,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
     case 32: return launch_tc<32, 8>(mw, mx, p, grid, st, pdl);
     case 64: return launch_tc<64, 6>(mw, mx, p, grid, st, pdl);
     case 128: return launch_tc<128, 5>(mw, mx, p, grid, st, pdl);
+    case 192: return launch_tc<192, 5>(mw, mx, p, grid, st, pdl);
     default: return launch_tc<256, 4>(mw, mx, p, grid, st, pdl);
   }
 }

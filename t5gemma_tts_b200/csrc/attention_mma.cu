@@ -14,7 +14,7 @@
 //   * O^T[dim, head] += V_tile^T . P^T  on mma.sync, the D dims dealt over the 4 warps.
 // ~120 instructions per warp per 32 tokens.  tcgen05 is not used: the useful M is G = 2 rows and the work is
 // bandwidth / latency bound.  Same fused glue as attention.cu: PM-RoPE of q and of the new k, in-place KV
-// append, split-KV merge of the NS CTAs of a cluster through distributed shared memory.
+// append.
 // Chunked mode (the batched step's default): blockIdx.y = chunk.  A row's key range is cut into ceil(range / chunk_tokens)
 // equal pieces, so a step's attention is dealt in pieces of similar size whatever the spread of the rows' contexts (one
 // CTA per row made the kernel as long as its longest row: 53.6 -> 32.6 us per layer at contexts U[0,900), +27 % on a
@@ -22,14 +22,12 @@
 // Measured and rejected for the tile loads: one producer warp issuing the 16-byte cp.async (63.6 us: a single warp's
 // instruction stream is too slow) and one cp.async.bulk per 512-byte row (38.9 us: 64 small bulk copies per tile).
 #include "kernels.h"
-#include <cooperative_groups.h>
 
 namespace {
 
 constexpr int AM_NT = 256, AM_WARPS = 8;  // the kernel is instruction-issue bound: two warps per scheduler
 constexpr int AM_TT = 32;                 // tokens per tile
 constexpr int AM_NST = 2;                 // ring stages
-constexpr int AM_MAX_NS = 8;
 constexpr int AM_BT_CACHE = 256;
 constexpr int AM_ROWS_PRE = 512;          // key ranges up to this length resolve their page lookups once, before the tile loop
 constexpr int AM_MAX_CHUNKS = 16;         // chunked mode: chunks per (row, kv head)
@@ -65,21 +63,15 @@ template <int D> struct AmGeo {
   static constexpr size_t stage_elems = (size_t)2 * AM_TT * LD; // K tile + V tile
   // q / probability operand tiles hold G real rows + one shared zero row (the MMA's n = 8 columns beyond G read it)
   static constexpr size_t ring_bytes(int G) { return (AM_NST * stage_elems + (size_t)(G + 1) * LD + (size_t)(G + 1) * (AM_TT + 8)) * sizeof(bf16); }
-  // split-KV receive buffers live in dynamic shared memory and only exist when the key range is split (NS > 1): an
-  // unsplit CTA then needs 80 KB in total and fits next to a resident 145 KB GEMM CTA, so its pre-wait work (slot /
-  // block table / first K/V tiles) overlaps the producer GEMM instead of starting when that kernel exits
-  static constexpr size_t split_bytes(int G, int NS) { return NS > 1 ? ((size_t)NS * G * D + (size_t)NS * G * 2 + (size_t)NS * G + (size_t)G * D) * sizeof(float) : 0; }
-  static constexpr size_t dyn_bytes(int G, int NS) { return ring_bytes(G) + split_bytes(G, NS); }
+  static constexpr size_t dyn_bytes(int G) { return ring_bytes(G); }
 };
 
-// grid (Hkv, NS, B), cluster (1, NS, 1), 256 threads
+// grid (Hkv, chunks, B), 256 threads
 template <int G, int D>
 __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a) {
   using Geo = AmGeo<D>;
   constexpr int LD = Geo::LD, KS = Geo::KS, KSH = Geo::KSH, NMT = Geo::NMT, MTW = Geo::MTW;
   static_assert(AM_TT == 32, "one token per lane in the softmax phase, two 16-token groups");
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char am_dyn[];
   bf16* ring = reinterpret_cast<bf16*>(am_dyn);                         // [NST][2][TT][LD]
   bf16* qb = ring + AM_NST * Geo::stage_elems;                          // [G+1][LD]   rotated q, row G is zero
@@ -94,10 +86,6 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   __shared__ float ml_s[G][2];
   __shared__ float cw_s[AM_MAX_CHUNKS][G], cl_s[AM_MAX_CHUNKS][G];      // chunked mode: merge weights / sums of the chunks
   __shared__ int last_s;
-  float* recv_o = reinterpret_cast<float*>(am_dyn + Geo::ring_bytes(G)); // [NS][G][D]  (src rank, g, dslice; NS > 1 only)
-  float* recv_ml = recv_o + (size_t)a.n_splits * G * D;                 // [NS][G][2]
-  float* f_wt = recv_ml + (size_t)a.n_splits * G * 2;                   // [NS][G]
-  float* o_s = f_wt + (size_t)a.n_splits * G;                           // [G][D] unnormalised partial of this CTA
 
   pdl_launch_dependents();
   // rows in descending key count (host-maintained, written before the launch): CTAs are scheduled in blockIdx order, so
@@ -106,7 +94,6 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   unsigned long long* probe = (a.probe && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && b < 64) ? a.probe + b * 11 : nullptr;
 #define AM_PROBE(k) do { if (probe) probe[k] = globaltimer_ns(); } while (0)
   AM_PROBE(0);
-  const int NS = a.n_splits;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int PT = a.pool.page_tokens;
   const int* bt = a.block_table + (size_t)b * a.bt_stride;
@@ -129,10 +116,9 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   for (int i = tid; i < (G + 1) * LD; i += AM_NT) qb[i] = __float2bfloat16(0.f);
   for (int i = tid; i < (G + 1) * (AM_TT + 8); i += AM_NT) pb[i] = __float2bfloat16(0.f);
   const int lo = (!a.is_cross && a.window > 0) ? max(0, L - a.window) : 0;
-  int chunk = (L - lo + NS - 1) / NS;
-  chunk = (chunk + 15) / 16 * 16;
+  int chunk = (L - lo + 15) / 16 * 16;                       // chunking off: the whole range
   int n_chunks = 1;
-  if (a.chunk_tokens > 0) {                                 // chunked mode: equal pieces of at most chunk_tokens keys, NS == 1
+  if (a.chunk_tokens > 0) {                                 // chunked mode: equal pieces of at most chunk_tokens keys
     n_chunks = min(max((L - lo + a.chunk_tokens - 1) / a.chunk_tokens, 1), a.max_chunks);
     if (!active || split >= n_chunks) return;               // nothing to do for this CTA (exited CTAs release the dependents)
     chunk = ((L - lo + n_chunks - 1) / n_chunks + AM_TT - 1) / AM_TT * AM_TT;
@@ -197,7 +183,7 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   pdl_wait();
   trace_begin(a.trace);
   AM_PROBE(2);
-  if (!active) return;                               // uniform over the whole cluster (same b)
+  if (!active) return;                               // CTA-uniform
   // ---- the producer's outputs: raw q and the new k/v.  A thread loads both elements of a rotation pair (j, j + D/2),
   //      rotates in registers (PM-RoPE at the row's progress position) and stores the MMA operand directly. ----
   {
@@ -234,7 +220,6 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
   static_assert(D <= AM_NT, "one thread per element of the new k/v row");
   __syncthreads();
   AM_PROBE(3);
-  if (NS > 1) cluster.barrier_arrive();              // "this CTA is running": waited on before the first remote store
   if (has_new) {   // append to the page (K post-RoPE), visible to later steps
     const int t = L - 1, page = page_of(t), off = t % PT;
     bf16* kd = a.pool.ptr(a.layer, 0, page) + ((size_t)hk * PT + off) * D;
@@ -414,32 +399,10 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
     trace_end(a.trace);
     return;
   }
-  if (NS == 1) {
-    // ---- no split: normalise and store straight from the accumulator registers ----
-    __syncthreads();
-    const float i0 = (2 * t4 < G && ml_s[2 * t4][1] > 0.f) ? 1.f / ml_s[2 * t4][1] : 0.f;
-    const float i1 = (2 * t4 + 1 < G && ml_s[2 * t4 + 1][1] > 0.f) ? 1.f / ml_s[2 * t4 + 1][1] : 0.f;
-#pragma unroll
-    for (int i = 0; i < MTW; ++i) {
-      const int mt = warp + i * AM_WARPS;
-      if (mt < NMT) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int head = 2 * t4 + (r & 1), dim = mt * 16 + g8 + (r >> 1) * 8;
-          if (head < G) {
-            const float o = acc[i][r] * ((r & 1) ? i1 : i0);
-            const size_t idx = (size_t)b * a.Hq * D + (size_t)(hk * G + head) * D + dim;
-            if (a.out) a.out[idx] = o;
-            if (a.out_bf) a.out_bf[idx] = __float2bfloat16(o);
-          }
-        }
-      }
-    }
-    AM_PROBE(10);
-    trace_end(a.trace);
-    return;
-  }
-  // ---- CTA partial -> shared memory: o_s[head][dim] (unnormalised) ----
+  // ---- no split: normalise and store straight from the accumulator registers ----
+  __syncthreads();
+  const float i0 = (2 * t4 < G && ml_s[2 * t4][1] > 0.f) ? 1.f / ml_s[2 * t4][1] : 0.f;
+  const float i1 = (2 * t4 + 1 < G && ml_s[2 * t4 + 1][1] > 0.f) ? 1.f / ml_s[2 * t4 + 1][1] : 0.f;
 #pragma unroll
   for (int i = 0; i < MTW; ++i) {
     const int mt = warp + i * AM_WARPS;
@@ -447,48 +410,14 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int head = 2 * t4 + (r & 1), dim = mt * 16 + g8 + (r >> 1) * 8;
-        if (head < G) o_s[head * D + dim] = acc[i][r];
+        if (head < G) {
+          const float o = acc[i][r] * ((r & 1) ? i1 : i0);
+          const size_t idx = (size_t)b * a.Hq * D + (size_t)(hk * G + head) * D + dim;
+          if (a.out) a.out[idx] = o;
+          if (a.out_bf) a.out_bf[idx] = __float2bfloat16(o);
+        }
       }
     }
-  }
-  __syncthreads();
-  // ---- split-KV merge across the cluster (same scheme as attention.cu): push the slice rank r finalises ----
-  const int dslice = D / NS;
-  cluster.barrier_wait();                                  // every peer has started: its shared memory may be written
-  for (int i = tid; i < G * D; i += AM_NT) {
-    const int g = i / D, d = i - g * D;
-    const int dst = d / dslice;
-    float* ro = cluster.map_shared_rank(recv_o, dst);
-    ro[((size_t)split * G + g) * D + (d - dst * dslice)] = o_s[g * D + d];
-  }
-  if (tid < G * NS) {
-    const int g = tid % G, dst = tid / G;
-    float* rm = cluster.map_shared_rank(recv_ml, dst);
-    rm[(split * G + g) * 2] = ml_s[g][0]; rm[(split * G + g) * 2 + 1] = ml_s[g][1];
-  }
-  cluster.sync();                                          // all pushes have landed
-  AM_PROBE(9);
-  if (tid < G) {
-    float M = -INFINITY;
-    for (int r = 0; r < NS; ++r) M = fmaxf(M, recv_ml[(r * G + tid) * 2]);
-    float den = 0.f;
-    for (int r = 0; r < NS; ++r) {
-      const float m = recv_ml[(r * G + tid) * 2];
-      const float wt = (m == -INFINITY) ? 0.f : __expf(m - M);
-      den = fmaf(wt, recv_ml[(r * G + tid) * 2 + 1], den);
-      f_wt[r * G + tid] = wt;
-    }
-    const float inv = den > 0.f ? 1.f / den : 0.f;
-    for (int r = 0; r < NS; ++r) f_wt[r * G + tid] *= inv;
-  }
-  __syncthreads();
-  for (int i = tid; i < G * dslice; i += AM_NT) {
-    const int g = i / dslice, dd = i - g * dslice;
-    float o = 0.f;
-    for (int r = 0; r < NS; ++r) o = fmaf(f_wt[r * G + g], recv_o[((size_t)r * G + g) * D + dd], o);
-    const int d = split * dslice + dd;
-    if (a.out) a.out[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = o;
-    if (a.out_bf) a.out_bf[(size_t)b * a.Hq * D + (size_t)(hk * G + g) * D + d] = __float2bfloat16(o);
   }
   AM_PROBE(10);
   trace_end(a.trace);
@@ -498,7 +427,7 @@ __global__ void __launch_bounds__(AM_NT) attn_decode_mma_kernel(AttnDecodeArgs a
 template <int G, int D>
 cudaError_t launch_am(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
   auto kern = attn_decode_mma_kernel<G, D>;
-  const size_t smem = AmGeo<D>::dyn_bytes(G, a.n_splits);
+  const size_t smem = AmGeo<D>::dyn_bytes(G);
   static PerDeviceFlag attr_set;
   if (smem > attr_set.here()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -508,17 +437,15 @@ cudaError_t launch_am(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
     attr_set.here() = smem;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(a.Hkv, a.chunk_tokens > 0 ? a.max_chunks : a.n_splits, a.B);
+  cfg.gridDim = dim3(a.Hkv, a.chunk_tokens > 0 ? a.max_chunks : 1, a.B);
   cfg.blockDim = dim3(AM_NT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = a.n_splits; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 2 : 1;
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
@@ -527,10 +454,10 @@ cudaError_t launch_am(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {
 bool attn_decode_mma_supported(const AttnDecodeArgs& a) {
   const int G = a.Hkv > 0 ? a.Hq / a.Hkv : 0;
   const bool d_ok = a.D == 16 || a.D == 32 || a.D == 64 || a.D == 128 || a.D == 256;
-  if (a.chunk_tokens > 0 && (a.n_splits != 1 || a.chunk_tokens % AM_TT || a.max_chunks < 1 || a.max_chunks > AM_MAX_CHUNKS ||
+  if (a.n_splits != 1) return false;                        // key ranges are split by chunks here, not by clusters
+  if (a.chunk_tokens > 0 && (a.chunk_tokens % AM_TT || a.max_chunks < 1 || a.max_chunks > AM_MAX_CHUNKS ||
                              !a.part_o || !a.part_ml || !a.part_cnt)) return false;
-  return d_ok && (G == 1 || G == 2 || G == 4) && a.n_splits >= 1 && a.n_splits <= AM_MAX_NS &&
-         !(a.n_splits & (a.n_splits - 1)) && a.D % a.n_splits == 0;
+  return d_ok && (G == 1 || G == 2 || G == 4);
 }
 
 cudaError_t launch_attn_decode_mma(const AttnDecodeArgs& a, cudaStream_t st, bool pdl) {

@@ -1,4 +1,4 @@
-// Shared pieces of the decode-attention kernels (attention.cu, decode_persist.cu): lane geometry of a K/V row,
+// Shared pieces of the CUDA-core attention kernels (attention.cu): lane geometry of a K/V row,
 // online-softmax state of a token group and its update / warp-level merge (HF:modeling_t5gemma.py:209-240 semantics:
 // scores * scale, optional softcap*tanh(s/softcap), fp32 softmax).
 #pragma once

@@ -340,6 +340,8 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   DM(e->d_qc, (size_t)B * QD); DM(e->d_act, (size_t)B * I); DM(e->d_t1, (size_t)B * d); DM(e->d_logits, (size_t)B * e->Vpad);
   DM(e->d_rope, (size_t)B * D);
   T5G_CUDA(cudaMemset(e->d_y, 0, sizeof(float) * (size_t)B * d));
+  T5G_CUDA(cudaMemset(e->d_qkv, 0, sizeof(float) * (size_t)B * QKV));   // batched step: split-K outputs start every layer at zero
+  T5G_CUDA(cudaMemset(e->d_qc, 0, sizeof(float) * (size_t)B * QD));
   T5G_CUDA(cudaMemset(e->d_hA, 0, sizeof(float) * (size_t)B * d));
   T5G_CUDA(cudaMemset(e->d_hB, 0, sizeof(float) * (size_t)B * d));
   DM(e->d_sample_u, 4096); DM(e->d_sample_slots, 4096); DM(e->d_sample_silence, 256);
@@ -845,8 +847,13 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
     CU(cudaMemsetAsync(e->d_trace, 0xFF, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
     CU(cudaMemsetAsync(e->d_trace + T5G_TRACE_STRIDE, 0, sizeof(unsigned long long) * T5G_TRACE_STRIDE, st));
   }
-  auto G = [&](const bf16* A, const bf16* W, int N, int K, int epi, const float* bias, void* out, int ldo) -> cudaError_t {
-    GemmArgs g{A, W, B, N, K, epi, bias, out, ldo, 1};   // fp32 outputs are pre-zeroed by the preceding norm kernel
+  // fp32 outputs of the split-K GEMMs are zeroed ahead of time by the idle epilogue warps of an EARLIER GEMM of the step
+  // (za / zb): d_y by the qkv, q_c and gate|up GEMMs (each after the norm kernel that read it), d_qc by the qkv GEMM, d_qkv
+  // of the next layer by the gate|up GEMM.  (The norm kernels did this before: 1 us of their 3.4 us at 64 rows.)
+  auto G = [&](const bf16* A, const bf16* W, int N, int K, int epi, const float* bias, void* out, int ldo,
+               float* za = nullptr, size_t na = 0, float* zb = nullptr, size_t nb = 0) -> cudaError_t {
+    GemmArgs g{A, W, B, N, K, epi, bias, out, ldo, 1};
+    g.zero_a = za; g.zero_na = na; g.zero_b = zb; g.zero_nb = nb;
     g.trace = next_trace();
     if (g.trace && kidx - 1 == 4 + 5 * 11 + 9) g.probe = e->d_trace + 1016;   // layer 5 gate|up: in-kernel checkpoints
     nl += 1;
@@ -869,10 +876,10 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
   CU(launch_embed_slots(e->audio_emb, e->d_slots, sqrtf((float)d), h, B, d, st, false)); nl++;
   for (int l = 0; l < c.n_dec_layers; ++l) {
     const DecLayer& L = e->dec[l];
-    if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d, next_trace()));
-    else CU(launch_norm(h, e->d_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qkv, QKV, e->d_y, d, next_trace()));
+    if (l == 0) CU(launch_norm(h, nullptr, nullptr, L.g_pre_sa, nullptr, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, nullptr, 0, nullptr, 0, next_trace()));
+    else CU(launch_norm(h, e->d_y, e->dec[l - 1].g_post_ff, L.g_pre_sa, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, nullptr, 0, nullptr, 0, next_trace()));
     nl++;
-    CU(G(e->d_xn, L.wqkv, QKV, d, GE_F32, nullptr, e->d_qkv, QKV));
+    CU(G(e->d_xn, L.wqkv, QKV, d, GE_F32, nullptr, e->d_qkv, QKV, e->d_y, (size_t)B * d, e->d_qc, (size_t)B * QD));
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_self_bt; a.bt_stride = e->max_self_pages; a.q = e->d_qkv; a.q_stride = QKV;
       a.kv_new = e->d_qkv + QD; a.kv_stride = QKV; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_self;
       a.is_cross = 0; a.window = c.dec_layer_sliding[l] ? c.sliding_window : 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
@@ -887,8 +894,8 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       else CU(launch_attn_decode(a, st, pdl_attn));
       nl++; }
     CU(G(e->d_attn_bf, L.wo, d, QD, GE_F32, nullptr, e->d_y, d));
-    CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_qc, QD, e->d_y, d, next_trace())); nl++;
-    CU(G(e->d_xn, L.wq_c, QD, d, GE_F32, nullptr, e->d_qc, QD));
+    CU(launch_norm(h, e->d_y, L.g_post_sa, L.g_pre_ca, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, nullptr, 0, nullptr, 0, next_trace())); nl++;
+    CU(G(e->d_xn, L.wq_c, QD, d, GE_F32, nullptr, e->d_qc, QD, e->d_y, (size_t)B * d));
     { AttnDecodeArgs a{}; a.pool = e->pool; a.layer = l; a.block_table = e->d_cross_bt; a.bt_stride = e->max_cross_pages; a.q = e->d_qc; a.q_stride = QD;
       a.kv_new = nullptr; a.kv_stride = 0; a.slots = e->d_slots; a.B = B; a.Hq = e->Hq; a.Hkv = e->Hkv; a.D = D; a.n_splits = e->ns_cross;
       a.is_cross = 1; a.window = 0; a.scale = c.attn_scale; a.softcap = c.attn_softcap; a.inv_freq = e->inv_freq; a.rope_cs = e->d_rope;
@@ -902,8 +909,8 @@ int enqueue_step_batched(T5GEngine* e, cudaStream_t st, int* n_launch) {
       else CU(launch_attn_decode(a, st, pdl_attn));
       nl++; }
     CU(G(e->d_attn_bf, L.wo_c, d, QD, GE_F32, nullptr, e->d_y, d));
-    CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, e->d_y, d, nullptr, 0, next_trace())); nl++;
-    CU(G(e->d_xn, L.wgu, 2 * I, d, GE_GEGLU_BF16, nullptr, e->d_act_bf, I));
+    CU(launch_norm(h, e->d_y, L.g_post_ca, L.g_pre_ff, h, e->d_xn, nullptr, B, d, c.rms_eps, st, pdl_norm, nullptr, 0, nullptr, 0, next_trace())); nl++;
+    CU(G(e->d_xn, L.wgu, 2 * I, d, GE_GEGLU_BF16, nullptr, e->d_act_bf, I, e->d_y, (size_t)B * d, e->d_qkv, (size_t)B * QKV));
     CU(G(e->d_act_bf, L.wd, d, I, GE_F32, nullptr, e->d_y, d));
   }
   *n_launch = nl;

@@ -40,6 +40,8 @@ struct TcParams {
   int atomic;                 // split-K partials reduced with red.global.add.f32 into a zeroed fp32 output (GE_F32)
   unsigned long long* trace;
   unsigned long long* probe;
+  float* zero_a; size_t zero_na;
+  float* zero_b; size_t zero_nb;
 };
 
 // GeGLU in the bf16 epilogues: tanh.approx.f32 (MUFU, rel. error ~2^-11, far inside bf16's 2^-8) -- the batched
@@ -178,6 +180,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int ch0 = (NCH >= 2) ? hsel * (NCH / 2) : 0;
     const int ch1 = (NCH >= 2) ? (hsel + 1) * (NCH / 2) : (hsel == 0 ? NCH : 0);
     pdl_wait();                                       // the output buffer may still be read by the previous kernel
+    if (p.zero_a) {                                   // side job while the main loop runs (see GemmArgs)
+      const size_t nthr = (size_t)gridDim.x * gridDim.y * gridDim.z * (TC_THREADS - 64);
+      const size_t gtid = ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (TC_THREADS - 64) + (threadIdx.x - 64);
+      for (size_t i = gtid; i < p.zero_na / 4; i += nthr) reinterpret_cast<float4*>(p.zero_a)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.zero_b) for (size_t i = gtid; i < p.zero_nb / 4; i += nthr) reinterpret_cast<float4*>(p.zero_b)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     mbar_wait(&S.acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* red = reinterpret_cast<float*>(&S.w[0][0]);   // ring storage is free once acc_full has fired
@@ -415,6 +423,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     const bool even = (lane & 1) == 0;
     const uint32_t acc_empty_leader = mapa_u32(smem_u32(&S.acc_empty[0]), 0);
     pdl_wait();                                        // the output buffer may still be read by the previous kernel
+    if (p.zero_a) {                                    // side job while the first tile's main loop runs (see GemmArgs)
+      const size_t nthr = (size_t)gridDim.x * (TC_THREADS - 64);
+      const size_t gtid = (size_t)blockIdx.x * (TC_THREADS - 64) + (threadIdx.x - 64);
+      for (size_t i = gtid; i < p.zero_na / 4; i += nthr) reinterpret_cast<float4*>(p.zero_a)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.zero_b) for (size_t i = gtid; i < p.zero_nb / 4; i += nthr) reinterpret_cast<float4*>(p.zero_b)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     uint32_t tl = 0;
     for (int tile = pair; tile < ntiles; tile += npairs, ++tl) {
       int fp, tt;
@@ -534,7 +548,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool
     if (e != cudaSuccess) return e;
     pdl = false;
   }
-  TcParams p{a.M, a.N, a.K, a.epilogue, a.bias, a.out, a.ldo, kbps, split, atomic, a.trace, a.probe};
+  TcParams p{a.M, a.N, a.K, a.epilogue, a.bias, a.out, a.ldo, kbps, split, atomic, a.trace, a.probe, a.zero_a, a.zero_na, a.zero_b, a.zero_nb};
   dim3 grid((a.N + TC_BM - 1) / TC_BM, (a.M + tokt - 1) / tokt, split);
   if (tokt == 256 && split == 1 && use_tc2()) {            // prefill: persistent CTA pairs
     CUtensorMap mxh;

@@ -126,6 +126,10 @@ struct GemmArgs {
   int out_zeroed;         // GE_F32 split-K: the caller guarantees `out` is already zero (no memset node is inserted)
   unsigned long long* trace = nullptr;   // optional in-step timestamps (T5G_TRACE)
   unsigned long long* probe = nullptr;   // optional [8] in-kernel checkpoints of one CTA (debug)
+  // optional side job of the tcgen05 kernel's epilogue warps while they wait for the accumulator: zero up to two fp32
+  // buffers (counts in floats, multiples of 4) that LATER split-K GEMMs accumulate into with red.global.add
+  float* zero_a = nullptr; size_t zero_na = 0;
+  float* zero_b = nullptr; size_t zero_nb = 0;
 };
 cudaError_t launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
 cudaError_t launch_gemm_tc(const GemmArgs& a, cudaStream_t st, int num_sms, bool pdl = false);   // tcgen05/TMEM/TMA path (gemm_tc.cu)

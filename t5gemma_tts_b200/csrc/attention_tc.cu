@@ -15,7 +15,8 @@
 // O += P_j V_j) keep K two blocks ahead of the score MMAs.  Interior key blocks (no causal / window / length edge inside
 // the tile) skip the per-element mask arithmetic.  Softcap uses one MUFU (tanh.approx, rel. error 2^-11 -- below the bf16
 // rounding of P) so a score costs two MUFU operations (tanh, ex2).
-// V is consumed as V^T [Hkv*D, tokens] (K-major B operand); `launch_transpose_v` produces it once per layer.
+// V is consumed as it is stored ([key][dim], dims contiguous): an MN-major B operand -- no transposed copy (round 1 and the
+// first version of this kernel staged V^T through a transpose kernel and an 8-token-aligned scratch tensor).
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -34,13 +35,13 @@ struct __align__(1024) FaSmem {
   static constexpr int NA = D / 64;                         // 64-element K atoms along head_dim
   unsigned char q[NA][FA_BQ * 128];                         // Q tile: NA atoms of [128 rows x 128 B]
   unsigned char k[FA_KST][NA][FA_BK * 128];                 // K block stages: NA atoms of [64 keys x 128 B]
-  unsigned char vt[FA_VST][D * 128];                        // V^T block stages: [D rows x 64 keys (128 B)]
+  unsigned char v[FA_VST][NA][FA_BK * 128];                 // V block stages: NA slabs of [64 keys x 64 dims (128 B)]
   uint64_t q_full, k_full[FA_KST], k_empty[FA_KST], v_full[FA_VST], v_empty[FA_VST], s_full[2], p_ready[2], pv_done;
   uint32_t tmem_base;
 };
 
 struct FaParams {
-  const int* q_seg_off; const int* k_seg_off; const int* vt_seg_off;   // vt_seg_off: 8-aligned column of each request in V^T
+  const int* q_seg_off; const int* k_seg_off;
   int Hq, Hkv, causal, window;
   float scale, softcap;
   bf16* out;                                               // [Tq, Hq*D]
@@ -88,7 +89,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
 template <int D>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                       const __grid_constant__ CUtensorMap map_vt, FaParams p) {
+                       const __grid_constant__ CUtensorMap map_v, FaParams p) {
   extern __shared__ __align__(1024) unsigned char smraw[];
   FaSmem<D>& S = *reinterpret_cast<FaSmem<D>*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
   constexpr int NA = D / 64;
@@ -100,7 +101,6 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   pdl_wait();
   const int q_beg = p.q_seg_off[seg], Lq = p.q_seg_off[seg + 1] - q_beg;
   const int k_beg = p.k_seg_off[seg], Lk = p.k_seg_off[seg + 1] - k_beg;
-  const int vt_beg = p.vt_seg_off[seg];
   const int q0 = blockIdx.x * FA_BQ;                        // first query (within the request) of this tile
   if (q0 >= Lq) return;                                     // uniform: tiles beyond this request's length
   // key range this tile can attend to (block granularity; exact masks are applied per element in the edge blocks)
@@ -118,7 +118,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_vt) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(TMEM_COLS) : "memory");
@@ -149,14 +149,14 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int st = j & 1;
         if (j >= FA_VST) mbar_wait(&S.v_empty[st], ((j >> 1) - 1) & 1);
         mbar_expect_tx(&S.v_full[st], D * 128);
-        tma_load_2d(S.vt[st], &map_vt, vt_beg + (b0 + j) * FA_BK, hk * D, &S.v_full[st]);   // 16-byte aligned start
+        for (int a = 0; a < NA; ++a) tma_load_2d(S.v[st][a], &map_v, hk * D + a * 64, k_beg + (b0 + j) * FA_BK, &S.v_full[st]);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0 && nb > 0) {
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BK >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
-      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) /* B is MN-major */ | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
       mbar_wait(&S.q_full, 0);
       int kst = 0; uint32_t kround = 0;
       auto issue_scores = [&](int j) {
@@ -181,10 +181,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         mbar_wait(&S.v_full[b], (j >> 1) & 1);
         mbar_wait(&S.p_ready[b], (j >> 1) & 1);             // P_j sits in TMEM over S_j
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t pa = tmem + S_COL + (uint32_t)b * S_STRIDE, va = smem_u32(S.vt[b]);
+        const uint32_t pa = tmem + S_COL + (uint32_t)b * S_STRIDE, va = smem_u32(S.v[b][0]);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_ts(tmem + O_COL, pa + kk * 8, umma_desc_sw128(va + kk * 32), idesc_o, (j > 0 || kk) ? 1u : 0u);
+          {
+            // MN-major B operand with the 128-byte swizzle: a 64-dim slab of the tile is 64 key rows x 128 B, i.e. 8-row
+            // swizzle atoms of 1024 B along K (stride-dimension offset) and slabs 8 KB apart along N (leading-dimension
+            // offset); one MMA consumes 16 keys = 2048 B of every slab
+            constexpr uint64_t lbo = FA_BK * 128, sbo = 1024;
+            const uint64_t db = (uint64_t)(((va + kk * 2048) & 0x3FFFF) >> 4) | ((lbo >> 4) << 16) | ((sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            umma_bf16_ts(tmem + O_COL, pa + kk * 8, db, idesc_o, (j > 0 || kk) ? 1u : 0u);
+          }
         umma_commit(&S.v_empty[b]);
         umma_commit(&S.pv_done);
       }
@@ -305,35 +312,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   }
 }
 
-// v [T, C] -> vt [C, ldt] (bf16), 32x32 shared-memory tiles; request `z` lands at column vt_seg_off[z] (a multiple of 8,
-// so every TMA box of V^T starts 16-byte aligned) and is zero-padded up to the next request.
-__global__ void transpose_v_kernel(const bf16* __restrict__ v, bf16* __restrict__ vt, const int* __restrict__ k_seg_off,
-                                   const int* __restrict__ vt_seg_off, int C, int ldt) {
-  __shared__ bf16 tile[32][33];
-  pdl_launch_dependents();
-  pdl_wait();
-  const int seg = blockIdx.z;
-  const int t_beg = k_seg_off[seg], L = k_seg_off[seg + 1] - t_beg;
-  const int o_beg = vt_seg_off[seg], o_len = vt_seg_off[seg + 1] - o_beg;
-  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  if (t0 >= o_len) return;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int t = t0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (t < L && c < C) ? v[(size_t)(t_beg + t) * C + c] : __float2bfloat16(0.f);
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, t = t0 + threadIdx.x;
-    if (c < C && t < o_len && o_beg + t < ldt) vt[(size_t)c * ldt + o_beg + t] = tile[threadIdx.x][i];
-  }
-}
-
 template <int D>
-cudaError_t launch_fa(const AttnPrefillArgs& a, const bf16* vt, const int* vt_seg_off, int ldt, int Tk, int n_seg, int max_lq, cudaStream_t st, bool pdl) {
+cudaError_t launch_fa(const AttnPrefillArgs& a, int Tk, int n_seg, int max_lq, cudaStream_t st, bool pdl) {
   CUtensorMap mq, mk, mv;
   if (!make_map_2d(&mq, a.q, a.Tq, (uint64_t)a.Hq * D, (uint64_t)a.Hq * D, FA_BQ) ||
       !make_map_2d(&mk, a.k, Tk, (uint64_t)a.Hkv * D, (uint64_t)a.Hkv * D, FA_BK) ||
-      !make_map_2d(&mv, vt, (uint64_t)a.Hkv * D, ldt, ldt, D))
+      !make_map_2d(&mv, a.v, Tk, (uint64_t)a.Hkv * D, (uint64_t)a.Hkv * D, FA_BK))
     return cudaErrorNotSupported;
   auto kern = attn_prefill_tc_kernel<D>;
   const size_t smem = sizeof(FaSmem<D>) + 1024;
@@ -343,7 +327,7 @@ cudaError_t launch_fa(const AttnPrefillArgs& a, const bf16* vt, const int* vt_se
     if (e != cudaSuccess) return e;
     attr_set.here() = 1;
   }
-  FaParams p{a.q_seg_off, a.k_seg_off, vt_seg_off, a.Hq, a.Hkv, a.causal, a.window, a.scale, a.softcap, a.out};
+  FaParams p{a.q_seg_off, a.k_seg_off, a.Hq, a.Hkv, a.causal, a.window, a.scale, a.softcap, a.out};
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((max_lq + FA_BQ - 1) / FA_BQ, a.Hq, n_seg);
   cfg.blockDim = dim3(FA_THREADS);
@@ -361,28 +345,12 @@ cudaError_t launch_fa(const AttnPrefillArgs& a, const bf16* vt, const int* vt_se
 
 bool attn_prefill_tc_supported(int D) { return D == 64 || D == 128 || D == 256; }
 
-cudaError_t launch_transpose_v(const bf16* v, bf16* vt, const int* k_seg_off, const int* vt_seg_off, int n_seg, int max_lk,
-                               int C, int ldt, cudaStream_t st, bool pdl) {
-  if (n_seg <= 0 || max_lk <= 0) return cudaSuccess;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((max_lk + 8 + 31) / 32, (C + 31) / 32, n_seg);
-  cfg.blockDim = dim3(32, 8);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, transpose_v_kernel, v, vt, k_seg_off, vt_seg_off, C, ldt);
-}
-
-cudaError_t launch_attn_prefill_tc(const AttnPrefillArgs& a, const bf16* vt, const int* vt_seg_off, int ldt, int Tk, int n_seg,
-                                   int max_lq, cudaStream_t st, bool pdl) {
+cudaError_t launch_attn_prefill_tc(const AttnPrefillArgs& a, int Tk, int n_seg, int max_lq, cudaStream_t st, bool pdl) {
   if (a.Tq <= 0 || n_seg <= 0) return cudaSuccess;
   switch (a.D) {
-    case 64: return launch_fa<64>(a, vt, vt_seg_off, ldt, Tk, n_seg, max_lq, st, pdl);
-    case 128: return launch_fa<128>(a, vt, vt_seg_off, ldt, Tk, n_seg, max_lq, st, pdl);
-    case 256: return launch_fa<256>(a, vt, vt_seg_off, ldt, Tk, n_seg, max_lq, st, pdl);
+    case 64: return launch_fa<64>(a, Tk, n_seg, max_lq, st, pdl);
+    case 128: return launch_fa<128>(a, Tk, n_seg, max_lq, st, pdl);
+    case 256: return launch_fa<256>(a, Tk, n_seg, max_lq, st, pdl);
     default: return cudaErrorNotSupported;
   }
 }

@@ -75,9 +75,8 @@ struct T5GEngine {
   // prefill workspaces (T = max_prefill_tokens)
   float *p_h = nullptr, *p_y = nullptr, *p_qkv = nullptr, *p_memory = nullptr, *p_ckv = nullptr, *p_final = nullptr;
   bf16 *p_xn = nullptr, *p_q = nullptr, *p_k = nullptr, *p_v = nullptr, *p_att = nullptr, *p_act = nullptr,
-       *p_mem_bf = nullptr, *p_ck = nullptr, *p_cv = nullptr, *p_vt = nullptr;
-  int vt_ld = 0; bool use_tc_attn = true; int attn_mma = 1, attn_tma = 1;
-  int *p_vt_off_e = nullptr, *p_vt_off_d = nullptr;          // 8-aligned V^T column offsets per request (encoder / decoder tokens)
+       *p_mem_bf = nullptr, *p_ck = nullptr, *p_cv = nullptr;
+  bool use_tc_attn = true; int attn_mma = 1, attn_tma = 1;
   float* p_logits = nullptr; int logits_chunk = 128;
   int *p_ids = nullptr, *p_seg_of = nullptr, *p_seg_off_e = nullptr, *p_seg_off_d = nullptr, *p_tok_slot = nullptr,
       *p_tok_idx = nullptr, *p_last_rows = nullptr;
@@ -312,8 +311,6 @@ extern "C" int t5g_create(const T5GConfig* cfg, int device, T5GEngine** out) {
   DM(e->p_h, T * d); DM(e->p_y, T * d); DM(e->p_qkv, T * QKV); DM(e->p_memory, T * d); DM(e->p_ckv, T * 2 * KD); DM(e->p_final, T * d);
   DM(e->p_xn, T * d); DM(e->p_q, T * QD); DM(e->p_k, T * KD); DM(e->p_v, T * KD); DM(e->p_att, T * QD); DM(e->p_act, T * I);
   DM(e->p_mem_bf, T * d); DM(e->p_ck, T * KD); DM(e->p_cv, T * KD);
-  e->vt_ld = (int)((T + 8 * (size_t)B + 64 + 7) & ~(size_t)7); DM(e->p_vt, (size_t)KD * e->vt_ld);
-  DM(e->p_vt_off_e, B + 1); DM(e->p_vt_off_d, B + 1);
   if (const char* s = getenv("T5G_ATTN_TC")) e->use_tc_attn = atoi(s) != 0;
   if (const char* s = getenv("T5G_GEMV_PAIR")) e->use_pair = atoi(s) != 0;
   if (const char* s = getenv("T5G_ATTN_MMA")) e->attn_mma = atoi(s) != 0;
@@ -457,15 +454,9 @@ struct StackIO {
 
 }  // namespace
 
-static cudaError_t prefill_attention(T5GEngine* e, const AttnPrefillArgs& a, const bf16* v, const int* vt_off, int Tk, int n_seg,
-                                     int max_lq, int max_lk, cudaStream_t st) {
-  if (e->use_tc_attn && attn_prefill_tc_supported(a.D)) {
-    cudaError_t er = launch_transpose_v(v, e->p_vt, a.k_seg_off, vt_off, n_seg, max_lk, a.Hkv * a.D, e->vt_ld, st, e->use_pdl);
-    if (er != cudaSuccess) return er;
-    e->launches += 2;
-    return launch_attn_prefill_tc(a, e->p_vt, vt_off, e->vt_ld, Tk, n_seg, max_lq, st, e->use_pdl);
-  }
+static cudaError_t prefill_attention(T5GEngine* e, const AttnPrefillArgs& a, int Tk, int n_seg, int max_lq, cudaStream_t st) {
   e->launches++;
+  if (e->use_tc_attn && attn_prefill_tc_supported(a.D)) return launch_attn_prefill_tc(a, Tk, n_seg, max_lq, st, e->use_pdl);
   return launch_attn_prefill(a, st);
 }
 
@@ -497,14 +488,6 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
   }
   T5G_CHECK(Te <= c.max_prefill_tokens && Td <= c.max_prefill_tokens, T5G_ERR_INVALID, "prefill tokens (%d text, %d audio) exceed max_prefill_tokens %d", Te, Td, c.max_prefill_tokens);
 
-  {   // 8-aligned V^T column offsets
-    std::vector<int> oe(n_req + 1, 0), od(n_req + 1, 0);
-    for (int r = 0; r < n_req; ++r) { oe[r + 1] = oe[r] + ((reqs[r].n_text + 7) & ~7); od[r + 1] = od[r] + ((reqs[r].n_dec + 7) & ~7); }
-    T5G_CHECK(oe[n_req] + 64 <= e->vt_ld && od[n_req] + 64 <= e->vt_ld, T5G_ERR_INVALID, "V^T scratch too small");
-    CU(cudaMemcpyAsync(e->p_vt_off_e, oe.data(), sizeof(int) * (n_req + 1), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->p_vt_off_d, od.data(), sizeof(int) * (n_req + 1), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
-  }
   // staging layout (pinned): ids_e[Te] ids_d[Td] seg_of_e[Te] seg_of_d[Td] pos_e[Te] pos_d[Td] slot_e idx_e slot_d idx_d offs
   const int Tm = c.max_prefill_tokens;
   int* hs = (int*)e->h_stage;
@@ -637,7 +620,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     AttnPrefillArgs aa{}; aa.q = e->p_q; aa.k = e->p_k; aa.v = e->p_v; aa.q_seg_off = e->p_seg_off_e; aa.k_seg_off = e->p_seg_off_e; aa.q_seg_of = e->p_seg_of;
     aa.Tq = Te; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.D = D; aa.causal = 0; aa.window = c.enc_layer_sliding[l] ? c.sliding_window : 0;
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
-    CU(prefill_attention(e, aa, e->p_v, e->p_vt_off_e, Te, n_req, max_text, max_text, st));
+    CU(prefill_attention(e, aa, Te, n_req, max_text, st));
     CU(gemm(e, e->p_att, L.wo, Te, d, QD, GE_F32, nullptr, e->p_y, d, st, ze_o));
     CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Te, d, c.rms_eps, st, e->use_pdl,
                    ze_down ? e->p_y : nullptr, d)); e->launches++;
@@ -680,7 +663,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     AttnPrefillArgs aa{}; aa.q = e->p_q; aa.k = e->p_k; aa.v = e->p_v; aa.q_seg_off = e->p_seg_off_d; aa.k_seg_off = e->p_seg_off_d; aa.q_seg_of = e->p_seg_of;
     aa.Tq = Td; aa.Hq = e->Hq; aa.Hkv = e->Hkv; aa.D = D; aa.causal = 1; aa.window = c.dec_layer_sliding[l] ? c.sliding_window : 0;
     aa.scale = c.attn_scale; aa.softcap = c.attn_softcap; aa.out = e->p_att;
-    CU(prefill_attention(e, aa, e->p_v, e->p_vt_off_d, Td, n_req, max_dec, max_dec, st));
+    CU(prefill_attention(e, aa, Td, n_req, max_dec, st));
     CU(gemm(e, e->p_att, L.wo, Td, d, QD, GE_F32, nullptr, e->p_y, d, st, zd_o));
     // p_qkv is free again (RoPE split consumed it): rows of width QD for the cross q projection; p_y for o_cross
     CU(launch_norm(e->p_h, e->p_y, L.g_post_sa, L.g_pre_ca, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl,
@@ -697,7 +680,7 @@ extern "C" int t5g_prefill(T5GEngine* e, const T5GRequest* reqs, int n_req, void
     CU(launch_rope_split(rk, st, e->use_pdl)); e->launches++;
     AttnPrefillArgs ac{}; ac.q = e->p_q; ac.k = e->p_ck; ac.v = e->p_cv; ac.q_seg_off = e->p_seg_off_d; ac.k_seg_off = e->p_seg_off_e; ac.q_seg_of = e->p_seg_of;
     ac.Tq = Td; ac.Hq = e->Hq; ac.Hkv = e->Hkv; ac.D = D; ac.causal = 0; ac.window = 0; ac.scale = c.attn_scale; ac.softcap = c.attn_softcap; ac.out = e->p_att;
-    CU(prefill_attention(e, ac, e->p_cv, e->p_vt_off_e, Te, n_req, max_dec, max_text, st));
+    CU(prefill_attention(e, ac, Te, n_req, max_dec, st));
     CU(gemm(e, e->p_att, L.wo_c, Td, d, QD, GE_F32, nullptr, e->p_y, d, st, zd_o));
     CU(launch_norm(e->p_h, e->p_y, L.g_post_ca, L.g_pre_ff, e->p_h, e->p_xn, nullptr, Td, d, c.rms_eps, st, e->use_pdl,
                    zd_down ? e->p_y : nullptr, d)); e->launches++;
@@ -1229,18 +1212,8 @@ extern "C" int t5g_debug_attn_prefill(T5GEngine* e, const void* q, const void* k
   if (impl == 1) {
     T5G_CHECK(attn_prefill_tc_supported(e->D), T5G_ERR_UNSUPPORTED, "tensor-core prefill attention needs head_dim 64/128/256");
     T5G_CHECK(n_seg <= e->c.max_slots + 64 && n_seg >= 1, T5G_ERR_INVALID, "too many segments");
-    std::vector<int> ko(n_seg + 1), vo(n_seg + 1, 0);
-    CU(cudaMemcpy(ko.data(), k_seg_off, sizeof(int) * (n_seg + 1), cudaMemcpyDeviceToHost));
-    int max_lk = 0;
-    for (int i = 0; i < n_seg; ++i) { vo[i + 1] = vo[i] + ((ko[i + 1] - ko[i] + 7) & ~7); max_lk = std::max(max_lk, ko[i + 1] - ko[i]); }
-    T5G_CHECK(vo[n_seg] + 64 <= e->vt_ld, T5G_ERR_INVALID, "keys exceed the V^T scratch (%d)", e->vt_ld);
-    int* d_vo = nullptr;
-    CU(cudaMalloc(&d_vo, sizeof(int) * (n_seg + 1)));
-    CU(cudaMemcpy(d_vo, vo.data(), sizeof(int) * (n_seg + 1), cudaMemcpyHostToDevice));
-    cudaError_t er = launch_transpose_v(a.v, e->p_vt, k_seg_off, d_vo, n_seg, max_lk, e->KD, e->vt_ld, st);
-    if (er == cudaSuccess) er = launch_attn_prefill_tc(a, e->p_vt, d_vo, e->vt_ld, Tk, n_seg, max_lq, st);
+    cudaError_t er = launch_attn_prefill_tc(a, Tk, n_seg, max_lq, st);
     if (er == cudaSuccess) er = cudaStreamSynchronize(st);
-    cudaFree(d_vo);
     CU(er);
   } else {
     CU(launch_attn_prefill(a, st));

@@ -111,12 +111,9 @@ struct AttnPrefillArgs {
   bf16* out;                                     // [Tq,Hq*D]
 };
 cudaError_t launch_attn_prefill(const AttnPrefillArgs& a, cudaStream_t st);
-// tensor-core (tcgen05) prefill attention (attention_tc.cu): needs V^T [Hkv*D, ldt] produced by launch_transpose_v
+// tensor-core (tcgen05) prefill attention (attention_tc.cu): q/k/v as above; Tk = rows of k/v, max_lq = longest query segment
 bool attn_prefill_tc_supported(int D);
-cudaError_t launch_transpose_v(const bf16* v, bf16* vt, const int* k_seg_off, const int* vt_seg_off, int n_seg, int max_lk,
-                               int C, int ldt, cudaStream_t st, bool pdl = false);
-cudaError_t launch_attn_prefill_tc(const AttnPrefillArgs& a, const bf16* vt, const int* vt_seg_off, int ldt, int Tk, int n_seg,
-                                   int max_lq, cudaStream_t st, bool pdl = false);
+cudaError_t launch_attn_prefill_tc(const AttnPrefillArgs& a, int Tk, int n_seg, int max_lq, cudaStream_t st, bool pdl = false);
 // C[M,N] = A[M,K] * W[N,K]^T, bf16 inputs, fp32 accumulate.
 enum { GE_F32 = 0, GE_GEGLU_BF16 = 1, GE_BIAS_GELU_BF16 = 2, GE_BIAS_F32 = 3, GE_BF16 = 4 };
 struct GemmArgs {

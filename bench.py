@@ -363,7 +363,8 @@ def main():
             eng.release(s)
 
     # warm-up job (W steps of 64 utterances), then the timed job
-    eng.inference_tts_batch(to_requests(mine_w), chunk_steps=32)
+    CH = int(os.environ.get("T5G_BENCH_CHUNK", "32"))     # decode steps between admissions (host scheduling granularity)
+    eng.inference_tts_batch(to_requests(mine_w), chunk_steps=CH)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -375,7 +376,7 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ev0.record()
-    results = eng.inference_tts_batch(to_requests(mine_t), chunk_steps=32)      # host tensors in, host tensors out
+    results = eng.inference_tts_batch(to_requests(mine_t), chunk_steps=CH)      # host tensors in, host tensors out
     ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0

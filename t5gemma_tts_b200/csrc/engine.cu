@@ -96,7 +96,7 @@ struct T5GEngine {
   // dimensions of the batched attention kernels and follow the longest live row
   struct StepGraph { cudaGraphExec_t exec = nullptr; int nodes = 0; };
   std::map<int, StepGraph> graphs; int graph_steps = 4;
-  int attn_chunk = 256, chunks_self = 1, chunks_cross = 1;    // batched rows: keys per attention CTA, current grid.y
+  int attn_chunk = 384, chunks_self = 1, chunks_cross = 1;    // batched rows: keys per attention CTA, current grid.y
   float *d_part_o = nullptr, *d_part_ml = nullptr; int* d_part_cnt = nullptr;
   int last_nodes_per_step = 0;
   int *d_order_self = nullptr, *d_order_cross = nullptr;                 // batched attention: rows by descending length
